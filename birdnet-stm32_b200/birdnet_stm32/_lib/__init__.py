@@ -1,0 +1,84 @@
+"""ctypes binding of `libbn_b200.so` (the C ABI declared in `include/bn_engine.h`).
+
+The library is built in-tree by `__graft_entry__.build()` (or `make -C csrc`).
+There is no fallback: if the shared object is missing, or no CUDA device is
+present when an engine is created, the call raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbn_b200.so")
+
+# every symbol `include/bn_engine.h` declares
+EXPORTS = (
+    "bn_create", "bn_destroy", "bn_query", "bn_set_option", "bn_infer_spec_f32", "bn_frontend_pcm16",
+    "bn_infer_pcm16", "bn_infer_pool", "bn_pool_scores", "bn_dump_tensor", "bn_launch_count",
+    "bn_host_alloc", "bn_host_free", "bn_last_error", "bn_version",
+)
+
+BN_POOL = {"avg": 0, "mean": 0, "average": 0, "max": 1, "lme": 2, "log_mean_exp": 2, "log_mean_exponential": 2}
+BN_OPT_ROUNDING, BN_OPT_MEAN_VARIANT, BN_OPT_FORCE_GENERIC, BN_OPT_WAVE = 1, 2, 3, 4
+
+
+class BnInfo(C.Structure):
+    _fields_ = [
+        ("frontend_kind", C.c_int32), ("sample_rate", C.c_int32), ("chunk_len", C.c_int32), ("n_fft", C.c_int32),
+        ("hop", C.c_int32), ("spec_width", C.c_int32), ("fft_bins", C.c_int32), ("num_classes", C.c_int32),
+        ("input_elems", C.c_int64), ("n_ops", C.c_int32), ("n_tensors", C.c_int32), ("device", C.c_int32),
+        ("wave", C.c_int32), ("workspace_bytes", C.c_int64), ("fast_path", C.c_int32), ("reserved", C.c_int32 * 7),
+    ]
+
+
+class EngineError(RuntimeError):
+    """A `bn_*` call returned a negative status."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"[bn status {code}] {message}")
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build the CUDA extension first (python -c 'import __graft_entry__ as g; g.build()' "
+            "or make -C birdnet-stm32_b200/csrc).  There is no CPU fallback."
+        )
+    L = C.CDLL(LIB_PATH)
+    vp, i32, f32 = C.c_void_p, C.c_int, C.c_float
+    L.bn_create.argtypes = [vp, C.c_size_t, i32, C.POINTER(vp)]
+    L.bn_destroy.argtypes = [vp]
+    L.bn_destroy.restype = None
+    L.bn_query.argtypes = [vp, C.POINTER(BnInfo)]
+    L.bn_set_option.argtypes = [vp, i32, i32]
+    L.bn_infer_spec_f32.argtypes = [vp, vp, i32, vp, vp]
+    L.bn_frontend_pcm16.argtypes = [vp, vp, vp, i32, vp, vp]
+    L.bn_infer_pcm16.argtypes = [vp, vp, vp, i32, vp, vp]
+    L.bn_infer_pool.argtypes = [vp, vp, vp, vp, i32, i32, f32, vp, vp]
+    L.bn_pool_scores.argtypes = [vp, vp, vp, i32, i32, i32, f32, vp, vp]
+    L.bn_dump_tensor.argtypes = [vp, i32, vp, C.c_size_t]
+    L.bn_launch_count.argtypes = [vp]
+    L.bn_launch_count.restype = C.c_int64
+    L.bn_host_alloc.argtypes = [C.c_size_t]
+    L.bn_host_alloc.restype = vp
+    L.bn_host_free.argtypes = [vp]
+    L.bn_host_free.restype = None
+    L.bn_last_error.restype = C.c_char_p
+    L.bn_version.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+def check(rc: int):
+    if rc != 0:
+        raise EngineError(rc, load().bn_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,75 @@
+// bn_common.cuh -- shared device helpers: TFLite fixed-point requantisation on the GPU.
+//
+// The arithmetic follows gemmlowp's fixedpoint.h / TFLite common.h
+// (MultiplyByQuantizedMultiplier) -- third-party code the reference executes inside
+// tf.lite.Interpreter.invoke (birdnet_stm32/models/runners.py:93-95).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/bn_blob.h"
+#include "../../include/bn_engine.h"
+
+namespace bn {
+
+// SaturatingRoundingDoublingHighMul for a multiplier in [0, 2^31): the saturating case
+// (both INT32_MIN) cannot occur, and gemmlowp's sign-dependent nudge followed by C's
+// truncating division equals (a*b + 2^30) >> 31 with an arithmetic shift (proof in DESIGN.md).
+__device__ __forceinline__ int32_t srdhm(int32_t a, int32_t b) {
+  long long ab = (long long)a * (long long)b;
+  return (int32_t)((ab + (1ll << 30)) >> 31);
+}
+
+// RoundingDivideByPOT: round half away from zero.
+__device__ __forceinline__ int32_t rdivpot(int32_t x, int e) {
+  int32_t mask = (int32_t)((1ll << e) - 1);
+  int32_t rem = x & mask;
+  int32_t thr = (mask >> 1) + (x < 0 ? 1 : 0);
+  return (x >> e) + (rem > thr ? 1 : 0);
+}
+
+// tflite::MultiplyByQuantizedMultiplier. rounding 0 = double rounding (default TFLite build),
+// 1 = single rounding (TFLITE_SINGLE_ROUNDING / ruy).
+__device__ __forceinline__ int32_t mbqm(int32_t x, int32_t qm, int shift, int rounding) {
+  if (rounding == 0) {
+    int left = shift > 0 ? shift : 0;
+    int right = shift > 0 ? 0 : -shift;
+    int32_t xs = (int32_t)((uint32_t)x << left);   // int32 wrap like x * (1 << left)
+    return rdivpot(srdhm(xs, qm), right);
+  } else {
+    int total = 31 - shift;
+    long long r = (long long)x * (long long)qm + (1ll << (total - 1));
+    r >>= total;
+    r = r > 2147483647ll ? 2147483647ll : (r < -2147483648ll ? -2147483648ll : r);
+    return (int32_t)r;
+  }
+}
+
+// Fast path for the common case (double rounding, right shift only).
+__device__ __forceinline__ int32_t mbqm_rshift(int32_t x, int32_t qm, int right) {
+  return rdivpot(srdhm(x, qm), right);
+}
+
+__device__ __forceinline__ int32_t clampi(int32_t v, int32_t lo, int32_t hi) {
+  return max(lo, min(hi, v));
+}
+
+struct ConvParams {
+  const int8_t* w;
+  const int32_t* bias;
+  const int32_t* mult;
+  const int32_t* shift;
+  int kh, kw, sh, sw, pt, pl;
+  int in_zp, out_zp, act_min, act_max;
+  int ih, iw, ic, oh, ow, oc;
+  int rounding;
+};
+
+struct AddParams {
+  int in1_zp, in2_zp, out_zp, left_shift;
+  int m1, s1, m2, s2, mo, so;
+  int act_min, act_max, bcast, C;
+  int rounding;
+};
+
+}  // namespace bn

@@ -1,0 +1,142 @@
+"""GPU parity tests (run on the B200 box): CUDA engine through the C ABI vs the CPU oracle."""
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ACT_TENSORS = [11, 76, 77, 81, 82, 83, 84, 85, 86, 87, 88, 89, 90, 91, 92, 93, 94, 95, 96] + list(range(97, 130))
+
+
+@pytest.fixture(scope="module")
+def runner(blob, cfg):
+    from birdnet_stm32.evaluation.gpu_runner import GpuRunner
+
+    r = GpuRunner(blob, cfg)
+    yield r
+    r.close()
+
+
+@pytest.fixture(scope="module")
+def oracle_spec(pcm_batch):
+    from oracle import bn_oracle
+
+    pcm, peak = pcm_batch
+    return bn_oracle.frontend_hybrid(pcm, peak, 512, 66150 // 256, 256)
+
+
+def test_frontend_matches_oracle(runner, pcm_batch, oracle_spec):
+    """Float frontend tolerance: max-normalised error <= 1e-4 and >= 99.9 % identical
+    int8 input codes after the graph's QUANTIZE (scale 1/255, zp -128)."""
+    pcm, peak = pcm_batch
+    got = runner.frontend(pcm, peak)
+    assert got.shape == oracle_spec.shape and got.dtype == np.float32
+    err = np.abs(got - oracle_spec).reshape(len(pcm), -1).max(axis=1)
+    assert err.max() <= 1e-4, err
+    scale = np.float32(0.003921568859368563)
+    q_ref = np.clip(np.round(oracle_spec / scale) - 128, -128, 127)
+    q_got = np.clip(np.round(got / scale) - 128, -128, 127)
+    same = (q_ref == q_got).mean()
+    assert same >= 0.999, same
+    # silence stays exactly zero
+    np.testing.assert_array_equal(got[-1], 0.0)
+
+
+def test_graph_every_tensor_bit_exact_generic(runner, graph, oracle_model, oracle_spec):
+    """Int8 body: identical quantised input -> every tensor identical (generic plan, debug taps)."""
+    from birdnet_stm32 import _lib as L
+
+    runner.set_option(L.BN_OPT_FORCE_GENERIC, 1)
+    try:
+        B = oracle_spec.shape[0]
+        got = runner.predict(oracle_spec)
+        ref = oracle_model.predict(oracle_spec)
+        np.testing.assert_array_equal(got, ref)
+        for tid in ACT_TENSORS:
+            t = graph.tensor(tid)
+            if t.is_const or t.dtype != np.int8:
+                continue
+            nb = int(np.prod(t.shape[1:]))
+            g = runner.dump_tensor(tid, nb * B)
+            _, o = oracle_model.run(oracle_spec, tap_id=tid)
+            assert np.array_equal(g, o.reshape(-1)), f"tensor {tid} ({t.name}) differs in {(g != o.reshape(-1)).sum()} of {g.size}"
+    finally:
+        runner.set_option(L.BN_OPT_FORCE_GENERIC, 0)
+
+
+def test_graph_bit_exact_default_plan(runner, oracle_model, oracle_spec):
+    got = runner.predict(oracle_spec)
+    ref = oracle_model.predict(oracle_spec)
+    np.testing.assert_array_equal(got, ref)
+    # dynamic batch, like tests/test_runners.py:73-81 in the reference
+    one = runner.predict(oracle_spec[2:3])
+    np.testing.assert_array_equal(one, ref[2:3])
+    assert one.dtype == np.float32 and one.shape == (1, 100)
+
+
+def test_rounding_and_mean_variants_match_oracle(runner, blob, oracle_spec):
+    from birdnet_stm32 import _lib as L
+    from oracle import bn_oracle
+
+    for rounding, variant in ((1, 0), (0, 1), (0, 3)):
+        runner.set_option(L.BN_OPT_ROUNDING, rounding)
+        runner.set_option(L.BN_OPT_MEAN_VARIANT, variant)
+        try:
+            got = runner.predict(oracle_spec)
+        finally:
+            runner.set_option(L.BN_OPT_ROUNDING, 0)
+            runner.set_option(L.BN_OPT_MEAN_VARIANT, 0)
+        ref = bn_oracle.OracleModel(blob, rounding=rounding, mean_variant=variant).predict(oracle_spec)
+        np.testing.assert_array_equal(got, ref)
+
+
+def test_full_path_pcm_to_scores(runner, oracle_model, pcm_batch, oracle_spec):
+    """PCM16 -> scores: top-1 equal, dequantised outputs within 1 LSB (1/256) of the oracle path."""
+    pcm, peak = pcm_batch
+    got = runner.predict_pcm16(pcm, peak)
+    ref = oracle_model.predict(oracle_spec)
+    assert np.abs(got - ref).max() <= 1.0 / 256 + 1e-7
+    np.testing.assert_array_equal(got.argmax(axis=1), ref.argmax(axis=1))
+
+
+def test_wave_splitting_is_invisible(blob, cfg, pcm_batch):
+    from birdnet_stm32.evaluation.gpu_runner import GpuRunner
+
+    pcm, peak = pcm_batch
+    a = GpuRunner(blob, cfg, wave=3)
+    b = GpuRunner(blob, cfg, wave=64)
+    try:
+        np.testing.assert_array_equal(a.predict_pcm16(pcm, peak), b.predict_pcm16(pcm, peak))
+        assert a.launches > 0
+    finally:
+        a.close()
+        b.close()
+
+
+@pytest.mark.parametrize("method", ["avg", "max", "lme"])
+def test_pooled_path_matches_oracle_pooling(runner, pcm_batch, method):
+    from oracle import bn_oracle
+
+    pcm, peak = pcm_batch
+    offs = np.array([0, 3, 3, 4, 8], dtype=np.int32)      # ragged, one empty file
+    chunk = runner.predict_pcm16(pcm, peak)
+    got = runner.predict_pooled(pcm, peak, offs, pooling=method, beta=10.0)
+    assert got.shape == (4, 100)
+    for f in range(4):
+        ref = bn_oracle.pool_scores(chunk[offs[f]:offs[f + 1]], method, 10.0)
+        np.testing.assert_allclose(got[f], ref, rtol=0, atol=2e-6)
+    np.testing.assert_array_equal(got[1], 0.0)             # empty file -> zeros (pooling.py:40-41)
+    np.testing.assert_allclose(runner.pool_scores(chunk, offs, method, 10.0), got, atol=0)
+
+
+def test_errors_are_reported_not_swallowed(runner, blob):
+    from birdnet_stm32 import _lib as L
+    from birdnet_stm32.evaluation.gpu_runner import GpuRunner
+
+    with pytest.raises(ValueError):
+        runner.predict(np.zeros((2, 17), np.float32))
+    with pytest.raises(ValueError, match="Unsupported"):
+        runner.predict_pooled(np.zeros((1, 66150), np.int16), None, [0, 1], pooling="median")
+    with pytest.raises(L.EngineError):
+        GpuRunner(blob[:1000])
+    assert runner.predict(np.zeros((0, 257, 256, 1), np.float32)).shape == (0, 100)
