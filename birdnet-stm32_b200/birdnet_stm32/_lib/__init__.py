@@ -17,11 +17,11 @@ LIB_PATH = os.path.join(_HERE, "libbn_b200.so")
 EXPORTS = (
     "bn_create", "bn_destroy", "bn_query", "bn_set_option", "bn_infer_spec_f32", "bn_frontend_pcm16",
     "bn_infer_pcm16", "bn_infer_pool", "bn_pool_scores", "bn_dump_tensor", "bn_launch_count",
-    "bn_host_alloc", "bn_host_free", "bn_last_error", "bn_version",
+    "bn_profile_read", "bn_host_alloc", "bn_host_free", "bn_last_error", "bn_version",
 )
 
 BN_POOL = {"avg": 0, "mean": 0, "average": 0, "max": 1, "lme": 2, "log_mean_exp": 2, "log_mean_exponential": 2}
-BN_OPT_ROUNDING, BN_OPT_MEAN_VARIANT, BN_OPT_FORCE_GENERIC, BN_OPT_WAVE = 1, 2, 3, 4
+BN_OPT_ROUNDING, BN_OPT_MEAN_VARIANT, BN_OPT_FORCE_GENERIC, BN_OPT_WAVE, BN_OPT_PROFILE = 1, 2, 3, 4, 5
 
 
 class BnInfo(C.Structure):
@@ -69,6 +69,7 @@ def load():
     L.bn_dump_tensor.argtypes = [vp, i32, vp, C.c_size_t]
     L.bn_launch_count.argtypes = [vp]
     L.bn_launch_count.restype = C.c_int64
+    L.bn_profile_read.argtypes = [vp, i32, C.c_char_p, C.c_size_t, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     L.bn_host_alloc.argtypes = [C.c_size_t]
     L.bn_host_alloc.restype = vp
     L.bn_host_free.argtypes = [vp]

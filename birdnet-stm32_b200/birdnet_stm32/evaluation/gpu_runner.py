@@ -211,6 +211,21 @@ class GpuRunner:
         L.check(self._lib.bn_frontend_pcm16(self._h, C.c_void_p(pcm_ptr), C.c_void_p(peak_ptr) if peak_ptr else None, B,
                                             C.c_void_p(spec_ptr), C.c_void_p(stream) if stream else None))
 
+    def profile(self, on: bool = True, reset: bool = False):
+        """Switch per-kernel CUDA-event timing on/off (BN_OPT_PROFILE)."""
+        self.set_option(L.BN_OPT_PROFILE, 2 if (on and reset) else int(on))
+
+    def profile_read(self) -> dict:
+        """{kernel name: (total ms, launches)} accumulated while profiling was on."""
+        out = {}
+        name = C.create_string_buffer(64)
+        ms, cnt = C.c_double(), C.c_int64()
+        i = 0
+        while self._lib.bn_profile_read(self._h, i, name, 64, C.byref(ms), C.byref(cnt)) == 0:
+            out[name.value.decode()] = (ms.value, cnt.value)
+            i += 1
+        return out
+
     # -- debug taps -------------------------------------------------------------
     def dump_tensor(self, tfl_tensor_id: int, nbytes: int, dtype=np.int8) -> np.ndarray:
         """Tensor `tfl_tensor_id` of the last wave as a flat array (see BN_OPT_FORCE_GENERIC)."""

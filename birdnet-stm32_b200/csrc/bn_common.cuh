@@ -15,13 +15,13 @@ namespace bn {
 // SaturatingRoundingDoublingHighMul for a multiplier in [0, 2^31): the saturating case
 // (both INT32_MIN) cannot occur, and gemmlowp's sign-dependent nudge followed by C's
 // truncating division equals (a*b + 2^30) >> 31 with an arithmetic shift (proof in DESIGN.md).
-__device__ __forceinline__ int32_t srdhm(int32_t a, int32_t b) {
+__host__ __device__ __forceinline__ int32_t srdhm(int32_t a, int32_t b) {
   long long ab = (long long)a * (long long)b;
   return (int32_t)((ab + (1ll << 30)) >> 31);
 }
 
 // RoundingDivideByPOT: round half away from zero.
-__device__ __forceinline__ int32_t rdivpot(int32_t x, int e) {
+__host__ __device__ __forceinline__ int32_t rdivpot(int32_t x, int e) {
   int32_t mask = (int32_t)((1ll << e) - 1);
   int32_t rem = x & mask;
   int32_t thr = (mask >> 1) + (x < 0 ? 1 : 0);
@@ -30,7 +30,7 @@ __device__ __forceinline__ int32_t rdivpot(int32_t x, int e) {
 
 // tflite::MultiplyByQuantizedMultiplier. rounding 0 = double rounding (default TFLite build),
 // 1 = single rounding (TFLITE_SINGLE_ROUNDING / ruy).
-__device__ __forceinline__ int32_t mbqm(int32_t x, int32_t qm, int shift, int rounding) {
+__host__ __device__ __forceinline__ int32_t mbqm(int32_t x, int32_t qm, int shift, int rounding) {
   if (rounding == 0) {
     int left = shift > 0 ? shift : 0;
     int right = shift > 0 ? 0 : -shift;
@@ -46,12 +46,12 @@ __device__ __forceinline__ int32_t mbqm(int32_t x, int32_t qm, int shift, int ro
 }
 
 // Fast path for the common case (double rounding, right shift only).
-__device__ __forceinline__ int32_t mbqm_rshift(int32_t x, int32_t qm, int right) {
+__host__ __device__ __forceinline__ int32_t mbqm_rshift(int32_t x, int32_t qm, int right) {
   return rdivpot(srdhm(x, qm), right);
 }
 
-__device__ __forceinline__ int32_t clampi(int32_t v, int32_t lo, int32_t hi) {
-  return max(lo, min(hi, v));
+__host__ __device__ __forceinline__ int32_t clampi(int32_t v, int32_t lo, int32_t hi) {
+  return v < lo ? lo : (v > hi ? hi : v);
 }
 
 struct ConvParams {

@@ -63,6 +63,7 @@ struct bn_engine {
   // options
   int rounding = 0, mean_variant = 0, force_generic = 0;
   FastPlan fast;
+  Profiler prof;
   int64_t launches = 0;
 };
 
@@ -142,13 +143,13 @@ extern "C" int bn_create(const void* blob, size_t nbytes, int device, bn_engine*
   if (ce != cudaSuccess) { bn_destroy(e); return set_err(BN_ERR_CUDA, "bn_create: %s", cudaGetErrorString(ce)); }
   e->buf.assign(e->hdr->n_tensors, nullptr);
   e->last_ptr.assign(e->hdr->n_tensors, nullptr);
-  fast_plan_build(e->fast, e->hdr, e->tensors, e->ops, e->d_blob);
+  fast_plan_build(e->fast, e->blob.data(), e->hdr, e->tensors, e->ops, e->d_blob);
   *out = e;
   return BN_OK;
 }
 
 static void free_workspace(bn_engine* e) {
-  for (uint32_t i = 0; i < e->hdr->n_tensors; i++)
+  for (uint32_t i = 0; i < e->hdr->n_tensors && i < e->buf.size(); i++)
     if (!e->tensors[i].is_const && e->buf[i]) { cudaFree(e->buf[i]); e->buf[i] = nullptr; }
   fast_plan_free_workspace(e->fast);
   if (e->d_mnmx) { cudaFree(e->d_mnmx); e->d_mnmx = nullptr; }
@@ -160,6 +161,7 @@ extern "C" void bn_destroy(bn_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   if (e->hdr) free_workspace(e);
+  fast_plan_destroy(e->fast);
   for (int i = 0; i < 2; i++) {
     if (e->d_pcm[i]) cudaFree(e->d_pcm[i]);
     if (e->d_peak[i]) cudaFree(e->d_peak[i]);
@@ -255,6 +257,11 @@ static int run_generic(bn_engine* e, std::vector<void*>& ptr, int Bw, cudaStream
     const long n_out = t_elems(to) * Bw;
     void* y = ptr[op.out];
     const void* x = op.n_in > 0 ? ptr[op.in[0]] : nullptr;
+    if (e->prof.on) {
+      char nm[40];
+      snprintf(nm, sizeof nm, "G%02u_kind%d", oi, op.kind);
+      e->prof.begin(nm, st);
+    }
     switch (op.kind) {
       case BN_OP_QUANTIZE: launch_quantize((const float*)x, (int8_t*)y, n_out, op.f[0], op.p[0], st); break;
       case BN_OP_DEQUANTIZE: launch_dequantize((const int8_t*)x, (float*)y, n_out, op.f[0], op.p[0], st); break;
@@ -301,6 +308,7 @@ static int run_generic(bn_engine* e, std::vector<void*>& ptr, int Bw, cudaStream
       case BN_OP_LOGISTIC: launch_logistic((const int8_t*)x, (int8_t*)y, n_out, (const int8_t*)(e->d_blob + op.off[0]), st); break;
       default: return set_err(BN_ERR_UNSUPPORTED, "op kind %d", op.kind);
     }
+    if (e->prof.on) e->prof.end(st);
     e->launches++;
   }
   cudaError_t ce = cudaGetLastError();
@@ -313,10 +321,14 @@ static int run_frontend(bn_engine* e, const int16_t* d_pcm, const float* d_peak,
   const bn_blob_header* h = e->hdr;
   if (h->frontend_kind != BN_FE_HYBRID)
     return set_err(BN_ERR_UNSUPPORTED, "frontend kind %u has no CUDA kernel yet", h->frontend_kind);
+  if (e->prof.on) e->prof.begin("K1_stft_binmajor", st);
   int rc = launch_stft_mag(d_pcm, d_peak, d_spec, e->d_mnmx, Bw, (int)h->chunk_len, (int)h->n_fft, (int)h->hop, (int)h->spec_width, st);
+  if (e->prof.on) e->prof.end(st);
   if (rc) return set_err(rc, "stft launch rejected (n_fft %u hop %u)", h->n_fft, h->hop);
   const long per = (long)(h->n_fft / 2 + 1) * h->spec_width;
+  if (e->prof.on) e->prof.begin("K1b_normalize", st);
   launch_minmax_normalize(d_spec, per, per * Bw, e->d_mnmx, st);
+  if (e->prof.on) e->prof.end(st);
   e->launches += 3;
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return set_err(BN_ERR_CUDA, "frontend launch failed: %s", cudaGetErrorString(ce));
@@ -329,8 +341,9 @@ static int run_wave(bn_engine* e, const int16_t* d_pcm, const float* d_peak, con
   const bn_blob_header* h = e->hdr;
   if (use_fast(e)) {
     int rc;
-    if (d_pcm) rc = fast_run_pcm(e->fast, d_pcm, d_peak, Bw, d_scores_out, e->rounding, e->mean_variant, st, &e->launches);
-    else rc = fast_run_spec(e->fast, d_spec_in, Bw, d_scores_out, e->rounding, e->mean_variant, st, &e->launches);
+    Profiler* pr = e->prof.on ? &e->prof : nullptr;
+    if (d_pcm) rc = fast_run_pcm(e->fast, d_pcm, d_peak, Bw, d_scores_out, e->rounding, e->mean_variant, st, &e->launches, pr);
+    else rc = fast_run_spec(e->fast, d_spec_in, Bw, d_scores_out, e->rounding, e->mean_variant, st, &e->launches, pr);
     if (rc) return set_err(rc, "fused plan failed: %s", cudaGetErrorString(cudaGetLastError()));
     e->last_wave_B = Bw;
     return 0;
@@ -618,8 +631,26 @@ extern "C" int bn_set_option(bn_engine* e, int key, int value) {
       if (value < 1 || value > 65535) return set_err(BN_ERR_ARG, "wave must be in [1, 65535]");
       if (value != e->wave_opt) { cudaDeviceSynchronize(); free_workspace(e); }
       e->wave_opt = value; break;
+    case BN_OPT_PROFILE:
+      cudaDeviceSynchronize();
+      e->prof.collect();
+      e->prof.on = value != 0;
+      if (value == 2) e->prof.reset();
+      break;
     default: return set_err(BN_ERR_ARG, "unknown option %d", key);
   }
+  return BN_OK;
+}
+
+extern "C" int bn_profile_read(bn_engine* e, int index, char* name, size_t name_cap, double* ms, int64_t* count) {
+  int rc = check_engine(e);
+  if (rc) return rc;
+  cudaDeviceSynchronize();
+  e->prof.collect();
+  if (index < 0 || (size_t)index >= e->prof.names.size()) return BN_ERR_ARG;
+  if (name && name_cap) { strncpy(name, e->prof.names[index].c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+  if (ms) *ms = e->prof.ms[index];
+  if (count) *count = e->prof.count[index];
   return BN_OK;
 }
 

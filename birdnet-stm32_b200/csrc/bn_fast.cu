@@ -1,21 +1,990 @@
-// bn_fast.cu -- fused kernel plan.  (Round-1 stage 1: no fused pattern registered yet; the
-// engine runs the generic one-kernel-per-op plan.)
+// bn_fast.cu -- the fused kernel plan: host-side pattern matching / weight preparation and the
+// CUDA-core (dp4a) kernels K2..K6 described in bn_fast.cuh.
+//
+// Reference semantics reproduced bit-exactly (TFLite reference integer kernels, SURVEY Appendix B;
+// executed by the reference in tf.lite.Interpreter.invoke, birdnet_stm32/models/runners.py:93-95):
+//   * conv / depthwise / FC: acc = sum((x - in_zp) * w) + bias is computed as sum(x * w) + bias',
+//     bias' = bias - in_zp * sum(w) folded at plan-build time; SAME padding is realised by feeding
+//     the zero point for out-of-range taps, so the folded constant is position independent.
+//   * element-wise int8 chains (the PWL magnitude scaling, models/magnitude.py:179-192, lowered to
+//     DEPTHWISE 1x1 + ADD ops) are pure functions of (channel, input code): they are evaluated once
+//     on the host with the same fixed-point routines and folded into a [C][256] lookup table.
+//   * residual ADD: the two input rescales depend only on the input code, so they become two
+//     256-entry int32 tables; the output rescale is computed per element.
 #include "bn_fast.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+
+#include "bn_kernels.cuh"
 
 namespace bn {
 
-void fast_plan_build(FastPlan& fp, const bn_blob_header* hdr, const bn_blob_tensor* tensors, const bn_blob_op* ops,
-                     uint8_t* d_blob) {
+// =================================================================================================
+// Profiler
+// =================================================================================================
+void Profiler::begin(const char* name, cudaStream_t st) {
+  if (!on) return;
+  int slot = -1;
+  for (size_t i = 0; i < names.size(); i++) if (names[i] == name) { slot = (int)i; break; }
+  if (slot < 0) { names.push_back(name); ms.push_back(0.0); count.push_back(0); slot = (int)names.size() - 1; }
+  cudaEvent_t a;
+  if (!pool.empty()) { a = pool.back(); pool.pop_back(); } else cudaEventCreate(&a);
+  cudaEventRecord(a, st);
+  cur = slot; cur_a = a;
+}
+void Profiler::end(cudaStream_t st) {
+  if (!on || cur < 0) return;
+  cudaEvent_t b;
+  if (!pool.empty()) { b = pool.back(); pool.pop_back(); } else cudaEventCreate(&b);
+  cudaEventRecord(b, st);
+  pending.push_back({cur, cur_a, b});
+  cur = -1;
+}
+void Profiler::collect() {
+  for (auto& p : pending) {
+    cudaEventSynchronize(p.b);
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, p.a, p.b) == cudaSuccess) { ms[p.slot] += t; count[p.slot]++; }
+    pool.push_back(p.a); pool.push_back(p.b);
+  }
+  pending.clear();
+}
+void Profiler::reset() { collect(); names.clear(); ms.clear(); count.clear(); }
+Profiler::~Profiler() { for (auto e : pool) cudaEventDestroy(e); for (auto& p : pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); } }
+
+// =================================================================================================
+// Plan data
+// =================================================================================================
+constexpr int HEAD_N = 64;        // mel channels handled by the head kernel
+constexpr int HEAD_M = 128;       // frames per CTA
+constexpr int GEMM_LDA = 132;     // words per k-row of the transposed A tile (128 + 4 pad, keeps 16-byte alignment)
+
+struct PwParams {                 // pointwise conv (+ residual add) -- device pointers
+  const int* wt;                  // [K/4][N] words: 4 consecutive k of channel n
+  const int* bias;                // folded bias'
+  const int* mult;
+  const int* shift;
+  int K, N;
+  int out_zp, act_min, act_max;   // of the conv itself
+  int has_add;
+  const int* lut_res;             // [256] rescaled residual   (add input 1)
+  const int* lut_conv;            // [256] rescaled conv output (add input 2)
+  int add_mo, add_so, add_out_zp, add_act_min, add_act_max;
+};
+
+struct DwParams {
+  const int* wm;                  // [9][C/4][4] masked weight words
+  const int* bias; const int* mult; const int* shift;   // [C]
+  int C, ih, iw, oh, ow, sh, sw, pt, pl;
+  int in_zp, out_zp, act_min, act_max;
+};
+
+struct StemParams {
+  const int* w;                   // [16][3] words (w0,w1,w2,0) per (co, fy)
+  const int* bias; const int* mult; const int* shift;
+  int ih, iw, oh, ow, in_zp, out_zp, act_min, act_max;
+};
+
+struct HeadParams {
+  const int* wt; const int* bias; const int* mult; const int* shift;
+  const uint8_t* lut;             // [64][256] folded element-wise chain, indexed by code + 128
+  int KW;                         // k words (K_cat / 4)
+  int K_real;                     // 257
+  int fill;                       // FILL value for the concat padding columns
+  float q_scale; int q_zp;
+  int out_zp, act_min, act_max;
+  int W;                          // frames per chunk
+};
+
+struct TailParams {
+  const int8_t* w;                // FC weights [N][K]
+  const int* bias; const int* mult; const int* shift;   // folded bias'
+  const int8_t* lut;              // LOGISTIC
+  int K, N, npix;
+  int mean_in_zp, mean_out_zp, mean_mult, mean_shift, mean_mult_n, mean_shift_n, keep_dims;
+  float mean_in_scale, mean_out_scale;
+  int fc_out_zp, fc_act_min, fc_act_max;
+  float dq_scale; int dq_zp;
+};
+
+struct Block {
+  int dw_op, pw_op, add_op;       // op indices (add_op = -1 if none)
+  int in_slot, dw_slot, out_slot; // tensor slots
+  DwParams dw;
+  PwParams pw;
+};
+
+struct FastImpl {
+  // op / tensor indices
+  int quant_op = -1, mel_op = -1, stem_op = -1, mean_op = -1, fc_op = -1, logi_op = -1, deq_op = -1;
+  std::vector<int> region_ops;    // element-wise chain between the mel conv and the transpose
+  int region_src = -1, region_dst = -1, head_out_slot = -1, stem_out_slot = -1;
+  std::vector<Block> blocks;
+  HeadParams head{};
+  StemParams stem{};
+  TailParams tail{};
+  int ldk = 264;
+  int bins = 257, W = 256, mel = 64;
+  // device constant storage
+  std::vector<void*> d_consts;
+  uint8_t* d_head_lut = nullptr;
+  std::vector<int*> d_add_luts;   // per block: 512 ints (res, conv)
+  int prepared_rounding = -1;
+  // workspace (per wave)
+  float* d_mags = nullptr;
+  unsigned* d_mnmx = nullptr;
+  std::map<int, void*> slot_buf;  // tensor slot -> device buffer
+  std::vector<void*> owned;
+};
+
+static void* upload(FastImpl* im, const void* src, size_t n) {
+  void* d = nullptr;
+  if (cudaMalloc(&d, n ? n : 4) != cudaSuccess) return nullptr;
+  cudaMemcpy(d, src, n, cudaMemcpyHostToDevice);
+  im->d_consts.push_back(d);
+  return d;
+}
+
+static inline int dim_elems(const bn_blob_tensor& t) { return t.dims[0] * t.dims[1] * t.dims[2]; }
+
+// -------------------------------------------------------------------------------------------------
+// host evaluation of the element-wise region -> LUT[c][code+128]
+// -------------------------------------------------------------------------------------------------
+static bool eval_region_lut(const FastPlan& fp, const FastImpl* im, int rounding, std::vector<uint8_t>& lut) {
+  const int C = im->mel;
+  lut.assign((size_t)C * 256, 0);
+  std::map<int, int> val;
+  for (int c = 0; c < C; c++) {
+    for (int q = -128; q < 128; q++) {
+      val.clear();
+      val[im->region_src] = q;
+      for (int oi : im->region_ops) {
+        const bn_blob_op& op = fp.ops[oi];
+        const int32_t* p = op.p;
+        int y;
+        if (op.kind == BN_OP_DWCONV2D) {
+          const int8_t* w = (const int8_t*)(fp.h_blob + op.off[0]);
+          const int32_t* bias = (const int32_t*)(fp.h_blob + op.off[1]);
+          const int32_t* mult = (const int32_t*)(fp.h_blob + op.off[2]);
+          const int32_t* shift = (const int32_t*)(fp.h_blob + op.off[3]);
+          int acc = (val.at(op.in[0]) - p[BN_CONV_IN_ZP]) * (int)w[c] + bias[c];
+          y = clampi(mbqm(acc, mult[c], shift[c], rounding) + p[BN_CONV_OUT_ZP], p[BN_CONV_ACT_MIN], p[BN_CONV_ACT_MAX]);
+        } else if (op.kind == BN_OP_ADD) {
+          int a = val.at(op.in[0]);
+          int b;
+          const bn_blob_tensor& tb = fp.tensors[op.in[1]];
+          if (p[BN_ADD_BCAST] == 1) b = ((const int8_t*)(fp.h_blob + tb.data_off))[c];
+          else b = val.at(op.in[1]);
+          int s1 = mbqm((a - p[BN_ADD_IN1_ZP]) * (1 << p[BN_ADD_LEFT_SHIFT]), p[BN_ADD_M1], p[BN_ADD_S1], rounding);
+          int s2 = mbqm((b - p[BN_ADD_IN2_ZP]) * (1 << p[BN_ADD_LEFT_SHIFT]), p[BN_ADD_M2], p[BN_ADD_S2], rounding);
+          y = clampi(mbqm(s1 + s2, p[BN_ADD_MO], p[BN_ADD_SO], rounding) + p[BN_ADD_OUT_ZP], p[BN_ADD_ACT_MIN], p[BN_ADD_ACT_MAX]);
+        } else {
+          return false;
+        }
+        val[op.out] = y;
+      }
+      lut[(size_t)c * 256 + (q + 128)] = (uint8_t)(int8_t)val.at(im->region_dst);
+    }
+  }
+  return true;
+}
+
+// (re)build the rounding-dependent tables and upload them
+static int prepare_rounding(FastPlan& fp, int rounding) {
+  FastImpl* im = fp.impl;
+  if (im->prepared_rounding == rounding) return 0;
+  std::vector<uint8_t> lut;
+  if (!eval_region_lut(fp, im, rounding, lut)) return BN_ERR_UNSUPPORTED;
+  cudaDeviceSynchronize();
+  if (cudaMemcpy(im->d_head_lut, lut.data(), lut.size(), cudaMemcpyHostToDevice) != cudaSuccess) return BN_ERR_CUDA;
+  for (size_t bi = 0; bi < im->blocks.size(); bi++) {
+    const Block& bl = im->blocks[bi];
+    if (bl.add_op < 0) continue;
+    const int32_t* p = fp.ops[bl.add_op].p;
+    int tab[512];
+    for (int q = -128; q < 128; q++) {
+      tab[q + 128] = mbqm((q - p[BN_ADD_IN1_ZP]) * (1 << p[BN_ADD_LEFT_SHIFT]), p[BN_ADD_M1], p[BN_ADD_S1], rounding);
+      tab[256 + q + 128] = mbqm((q - p[BN_ADD_IN2_ZP]) * (1 << p[BN_ADD_LEFT_SHIFT]), p[BN_ADD_M2], p[BN_ADD_S2], rounding);
+    }
+    if (cudaMemcpy(im->d_add_luts[bi], tab, sizeof tab, cudaMemcpyHostToDevice) != cudaSuccess) return BN_ERR_CUDA;
+  }
+  im->prepared_rounding = rounding;
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// pattern matching + weight preparation
+// -------------------------------------------------------------------------------------------------
+#define FAIL(msg) do { fp.why = msg; return false; } while (0)
+
+static bool is_identity_slice(const FastPlan& fp, const bn_blob_op& op) {
+  if (op.kind != BN_OP_SLICE) return false;
+  const bn_blob_tensor& a = fp.tensors[op.in[0]];
+  const bn_blob_tensor& b = fp.tensors[op.out];
+  return op.p[0] == 0 && op.p[1] == 0 && op.p[2] == 0 && a.dims[0] == b.dims[0] && a.dims[1] == b.dims[1] && a.dims[2] == b.dims[2];
+}
+static bool is_hwc_flip(const bn_blob_op& op) { return op.kind == BN_OP_TRANSPOSE && op.p[0] == 2 && op.p[1] == 1 && op.p[2] == 0; }
+
+// conv constants: folded bias, transposed weight words
+static void prep_pw_weights(const FastPlan& fp, const bn_blob_op& op, int K, int N, std::vector<int>& wt, std::vector<int>& biasf) {
+  const int8_t* w = (const int8_t*)(fp.h_blob + op.off[0]);   // [N][K]
+  const int32_t* bias = (const int32_t*)(fp.h_blob + op.off[1]);
+  const int KW = (K + 3) / 4;
+  wt.assign((size_t)KW * N, 0);
+  biasf.assign(N, 0);
+  for (int n = 0; n < N; n++) {
+    long ws = 0;
+    for (int k = 0; k < K; k++) ws += w[(long)n * K + k];
+    biasf[n] = (int)((long)bias[n] - (long)op.p[BN_CONV_IN_ZP] * ws);
+    for (int kw = 0; kw < KW; kw++) {
+      unsigned word = 0;
+      for (int j = 0; j < 4; j++) {
+        int k = 4 * kw + j;
+        unsigned byte = k < K ? (uint8_t)w[(long)n * K + k] : 0;
+        word |= byte << (8 * j);
+      }
+      wt[(size_t)kw * N + n] = (int)word;
+    }
+  }
+}
+
+static bool build_impl(FastPlan& fp) {
+  const bn_blob_header* h = fp.hdr;
+  const bn_blob_op* ops = fp.ops;
+  const bn_blob_tensor* T = fp.tensors;
+  const int n_ops = (int)h->n_ops;
+  FastImpl* im = fp.impl;
+  if (n_ops < 12) FAIL("too few ops");
+  // ---- head: QUANTIZE, TRANSPOSE, SLICE, FILL, CONCAT, CONV 1x1 --------------------------------
+  int i = 0;
+  if (ops[i].kind != BN_OP_QUANTIZE || ops[i].in[0] != h->input_tensor) FAIL("op0 is not QUANTIZE(graph input)");
+  const bn_blob_tensor& tin = T[h->input_tensor];
+  if (tin.dtype != BN_F32 || tin.dims[2] != 1) FAIL("graph input is not [bins, W, 1] float32");
+  im->bins = tin.dims[0]; im->W = tin.dims[1];
+  im->quant_op = i++;
+  if (!is_hwc_flip(ops[i])) FAIL("op1 is not TRANSPOSE(2,1,0)");
+  i++;
+  if (!is_identity_slice(fp, ops[i])) FAIL("op2 is not an identity SLICE");
+  const int slice_out = ops[i].out;
+  i++;
+  if (ops[i].kind != BN_OP_FILL) FAIL("op3 is not FILL");
+  const int fill_out = ops[i].out, fill_val = ops[i].p[0];
+  i++;
+  if (ops[i].kind != BN_OP_CONCAT || ops[i].p[0] != 2 || ops[i].in[0] != slice_out || ops[i].in[1] != fill_out) FAIL("op4 is not CONCAT(slice, fill) on channels");
+  const int cat_out = ops[i].out;
+  const int K_cat = T[cat_out].dims[2];
+  i++;
+  const bn_blob_op& mel = ops[i];
+  if (mel.kind != BN_OP_CONV2D || mel.p[BN_CONV_KH] != 1 || mel.p[BN_CONV_KW] != 1 || mel.p[BN_CONV_SH] != 1 || mel.p[BN_CONV_SW] != 1 ||
+      mel.in[0] != cat_out || mel.p[BN_CONV_CIN] != K_cat)
+    FAIL("op5 is not the 1x1 mel-mixer conv");
+  if (mel.p[BN_CONV_COUT] != HEAD_N) FAIL("mel mixer must have 64 output channels for the fused head");
+  if (K_cat % 4 || K_cat > 288 || im->bins != 257 || K_cat < im->bins) FAIL("unsupported mel-mixer K");
+  if (im->W % HEAD_M) FAIL("spec_width must be a multiple of 128");
+  im->mel = HEAD_N;
+  im->mel_op = i++;
+  im->ldk = K_cat;
+  // ---- element-wise region until TRANSPOSE ------------------------------------------------------
+  im->region_src = mel.out;
+  std::map<int, bool> in_region;
+  in_region[mel.out] = true;
+  int last = mel.out;
+  while (i < n_ops && !is_hwc_flip(ops[i])) {
+    const bn_blob_op& op = ops[i];
+    if (op.kind == BN_OP_DWCONV2D) {
+      if (op.p[BN_CONV_KH] != 1 || op.p[BN_CONV_KW] != 1 || op.p[BN_CONV_SH] != 1 || op.p[BN_CONV_SW] != 1 || !in_region.count(op.in[0])) FAIL("region: unsupported depthwise");
+    } else if (op.kind == BN_OP_ADD) {
+      if (!in_region.count(op.in[0])) FAIL("region: ADD input outside region");
+      if (op.p[BN_ADD_BCAST] == 0 && !in_region.count(op.in[1])) FAIL("region: ADD input outside region");
+      if (op.p[BN_ADD_BCAST] == 2) FAIL("region: per-chunk broadcast");
+    } else FAIL("region: op is not element-wise");
+    in_region[op.out] = true;
+    last = op.out;
+    im->region_ops.push_back(i);
+    i++;
+  }
+  if (i + 2 >= n_ops) FAIL("no TRANSPOSE after the head");
+  im->region_dst = last;
+  if (ops[i].in[0] != last) FAIL("TRANSPOSE does not consume the region output");
+  i++;
+  if (!is_identity_slice(fp, ops[i])) FAIL("no identity SLICE after TRANSPOSE");
+  im->head_out_slot = ops[i].out;
+  i++;
+  // ---- stem ---------------------------------------------------------------------------------------
+  const bn_blob_op& st = ops[i];
+  if (st.kind != BN_OP_CONV2D || st.p[BN_CONV_KH] != 3 || st.p[BN_CONV_KW] != 3 || st.p[BN_CONV_CIN] != 1 || st.p[BN_CONV_COUT] != 16 ||
+      st.p[BN_CONV_SH] != 1 || st.p[BN_CONV_SW] != 2 || st.p[BN_CONV_PAD_T] != 1 || st.p[BN_CONV_PAD_L] != 0 || st.in[0] != im->head_out_slot)
+    FAIL("stem is not conv3x3 s(1,2) 1->16");
+  if (T[st.in[0]].dims[0] != im->mel || T[st.in[0]].dims[1] != im->W || (im->W % 4)) FAIL("stem input shape");
+  im->stem_op = i;
+  im->stem_out_slot = st.out;
+  i++;
+  // ---- DS blocks ----------------------------------------------------------------------------------
+  int cur = im->stem_out_slot;
+  while (i < n_ops && ops[i].kind == BN_OP_DWCONV2D) {
+    Block bl{};
+    const bn_blob_op& dw = ops[i];
+    if (dw.p[BN_CONV_KH] != 3 || dw.p[BN_CONV_KW] != 3 || dw.in[0] != cur) FAIL("block: depthwise is not 3x3 on the running tensor");
+    if (dw.p[BN_CONV_CIN] % 16) FAIL("block: channels must be a multiple of 16");
+    if (!((dw.p[BN_CONV_SH] == 1 && dw.p[BN_CONV_SW] == 1) || (dw.p[BN_CONV_SH] == 2 && dw.p[BN_CONV_SW] == 2))) FAIL("block: stride");
+    bl.dw_op = i; bl.in_slot = cur; bl.dw_slot = dw.out;
+    i++;
+    if (i >= n_ops) FAIL("block: missing pointwise conv");
+    const bn_blob_op& pw = ops[i];
+    if (pw.kind != BN_OP_CONV2D || pw.p[BN_CONV_KH] != 1 || pw.p[BN_CONV_KW] != 1 || pw.p[BN_CONV_SH] != 1 || pw.p[BN_CONV_SW] != 1 || pw.in[0] != dw.out)
+      FAIL("block: missing pointwise conv");
+    if (pw.p[BN_CONV_CIN] % 16 || pw.p[BN_CONV_COUT] % 64 != 0 && pw.p[BN_CONV_COUT] != 32) FAIL("block: pointwise channel counts");
+    if (pw.p[BN_CONV_CIN] > 256 || pw.p[BN_CONV_COUT] > 256) FAIL("block: too many channels");
+    bl.pw_op = i; bl.add_op = -1; bl.out_slot = pw.out;
+    i++;
+    if (i < n_ops && ops[i].kind == BN_OP_ADD) {
+      const bn_blob_op& ad = ops[i];
+      if (ad.p[BN_ADD_BCAST] != 0) FAIL("block: broadcast ADD");
+      if (!((ad.in[0] == cur && ad.in[1] == pw.out))) FAIL("block: ADD is not residual(block input, conv out)");
+      if (pw.p[BN_CONV_CIN] != pw.p[BN_CONV_COUT] || dw.p[BN_CONV_SH] != 1) FAIL("block: residual shape");
+      bl.add_op = i; bl.out_slot = ad.out;
+      i++;
+    }
+    cur = bl.out_slot;
+    im->blocks.push_back(bl);
+  }
+  if (im->blocks.empty()) FAIL("no DS blocks");
+  // ---- tail ---------------------------------------------------------------------------------------
+  if (i + 4 != n_ops) FAIL("tail is not MEAN, FC, LOGISTIC, DEQUANTIZE");
+  if (ops[i].kind != BN_OP_MEAN || ops[i].in[0] != cur) FAIL("tail: MEAN");
+  im->mean_op = i++;
+  if (ops[i].kind != BN_OP_FC || ops[i].in[0] != ops[im->mean_op].out || (ops[i].p[BN_CONV_CIN] % 4) || ops[i].p[BN_CONV_CIN] > 1024) FAIL("tail: FC");
+  im->fc_op = i++;
+  if (ops[i].kind != BN_OP_LOGISTIC || ops[i].in[0] != ops[im->fc_op].out) FAIL("tail: LOGISTIC");
+  im->logi_op = i++;
+  if (ops[i].kind != BN_OP_DEQUANTIZE || ops[i].in[0] != ops[im->logi_op].out || ops[i].out != h->output_tensor) FAIL("tail: DEQUANTIZE");
+  im->deq_op = i++;
+
+  // =================== constants ===================
+  {  // head
+    std::vector<int> wt, bf;
+    prep_pw_weights(fp, mel, K_cat, HEAD_N, wt, bf);
+    HeadParams& H = im->head;
+    H.wt = (const int*)upload(im, wt.data(), wt.size() * 4);
+    H.bias = (const int*)upload(im, bf.data(), bf.size() * 4);
+    H.mult = (const int*)(fp.d_blob + mel.off[2]);
+    H.shift = (const int*)(fp.d_blob + mel.off[3]);
+    if (cudaMalloc(&im->d_head_lut, HEAD_N * 256) != cudaSuccess) FAIL("cudaMalloc");
+    H.lut = im->d_head_lut;
+    H.KW = K_cat / 4; H.K_real = im->bins; H.fill = fill_val;
+    H.q_scale = ops[im->quant_op].f[0]; H.q_zp = ops[im->quant_op].p[0];
+    H.out_zp = mel.p[BN_CONV_OUT_ZP]; H.act_min = mel.p[BN_CONV_ACT_MIN]; H.act_max = mel.p[BN_CONV_ACT_MAX];
+    H.W = im->W;
+  }
+  {  // stem: weights [16][3][3][1] -> words (w0,w1,w2,0) per (co, fy)
+    const int8_t* w = (const int8_t*)(fp.h_blob + st.off[0]);
+    const int32_t* bias = (const int32_t*)(fp.h_blob + st.off[1]);
+    std::vector<int> ww(16 * 3), bf(16);
+    for (int co = 0; co < 16; co++) {
+      long ws = 0;
+      for (int fy = 0; fy < 3; fy++) {
+        unsigned word = 0;
+        for (int fx = 0; fx < 3; fx++) { int8_t v = w[(co * 3 + fy) * 3 + fx]; ws += v; word |= (unsigned)(uint8_t)v << (8 * fx); }
+        ww[co * 3 + fy] = (int)word;
+      }
+      bf[co] = (int)((long)bias[co] - (long)st.p[BN_CONV_IN_ZP] * ws);
+    }
+    StemParams& S = im->stem;
+    S.w = (const int*)upload(im, ww.data(), ww.size() * 4);
+    S.bias = (const int*)upload(im, bf.data(), bf.size() * 4);
+    S.mult = (const int*)(fp.d_blob + st.off[2]);
+    S.shift = (const int*)(fp.d_blob + st.off[3]);
+    S.ih = T[st.in[0]].dims[0]; S.iw = T[st.in[0]].dims[1]; S.oh = T[st.out].dims[0]; S.ow = T[st.out].dims[1];
+    S.in_zp = st.p[BN_CONV_IN_ZP]; S.out_zp = st.p[BN_CONV_OUT_ZP]; S.act_min = st.p[BN_CONV_ACT_MIN]; S.act_max = st.p[BN_CONV_ACT_MAX];
+  }
+  for (Block& bl : im->blocks) {
+    const bn_blob_op& dw = ops[bl.dw_op];
+    const bn_blob_op& pw = ops[bl.pw_op];
+    {  // depthwise: masked words wm[tap][cg][j], folded bias
+      const int C = dw.p[BN_CONV_CIN];
+      const int8_t* w = (const int8_t*)(fp.h_blob + dw.off[0]);   // [3][3][C]
+      const int32_t* bias = (const int32_t*)(fp.h_blob + dw.off[1]);
+      std::vector<int> wm((size_t)9 * C), bf(C);
+      for (int c = 0; c < C; c++) {
+        long ws = 0;
+        for (int t = 0; t < 9; t++) {
+          int8_t v = w[t * C + c];
+          ws += v;
+          wm[((size_t)t * (C / 4) + c / 4) * 4 + (c & 3)] = (int)((unsigned)(uint8_t)v << (8 * (c & 3)));
+        }
+        bf[c] = (int)((long)bias[c] - (long)dw.p[BN_CONV_IN_ZP] * ws);
+      }
+      DwParams& D = bl.dw;
+      D.wm = (const int*)upload(im, wm.data(), wm.size() * 4);
+      D.bias = (const int*)upload(im, bf.data(), bf.size() * 4);
+      D.mult = (const int*)(fp.d_blob + dw.off[2]);
+      D.shift = (const int*)(fp.d_blob + dw.off[3]);
+      D.C = C; D.ih = T[dw.in[0]].dims[0]; D.iw = T[dw.in[0]].dims[1]; D.oh = T[dw.out].dims[0]; D.ow = T[dw.out].dims[1];
+      D.sh = dw.p[BN_CONV_SH]; D.sw = dw.p[BN_CONV_SW]; D.pt = dw.p[BN_CONV_PAD_T]; D.pl = dw.p[BN_CONV_PAD_L];
+      D.in_zp = dw.p[BN_CONV_IN_ZP]; D.out_zp = dw.p[BN_CONV_OUT_ZP]; D.act_min = dw.p[BN_CONV_ACT_MIN]; D.act_max = dw.p[BN_CONV_ACT_MAX];
+    }
+    {  // pointwise
+      const int K = pw.p[BN_CONV_CIN], N = pw.p[BN_CONV_COUT];
+      std::vector<int> wt, bf;
+      prep_pw_weights(fp, pw, K, N, wt, bf);
+      PwParams& P = bl.pw;
+      P.wt = (const int*)upload(im, wt.data(), wt.size() * 4);
+      P.bias = (const int*)upload(im, bf.data(), bf.size() * 4);
+      P.mult = (const int*)(fp.d_blob + pw.off[2]);
+      P.shift = (const int*)(fp.d_blob + pw.off[3]);
+      P.K = K; P.N = N;
+      P.out_zp = pw.p[BN_CONV_OUT_ZP]; P.act_min = pw.p[BN_CONV_ACT_MIN]; P.act_max = pw.p[BN_CONV_ACT_MAX];
+      P.has_add = bl.add_op >= 0;
+      int* d_lut = nullptr;
+      if (P.has_add) {
+        if (cudaMalloc(&d_lut, 512 * sizeof(int)) != cudaSuccess) FAIL("cudaMalloc");
+        const int32_t* p = ops[bl.add_op].p;
+        P.add_mo = p[BN_ADD_MO]; P.add_so = p[BN_ADD_SO]; P.add_out_zp = p[BN_ADD_OUT_ZP];
+        P.add_act_min = p[BN_ADD_ACT_MIN]; P.add_act_max = p[BN_ADD_ACT_MAX];
+      }
+      im->d_add_luts.push_back(d_lut);
+      P.lut_res = d_lut; P.lut_conv = d_lut ? d_lut + 256 : nullptr;
+    }
+  }
+  {  // tail
+    const bn_blob_op& mo = ops[im->mean_op];
+    const bn_blob_op& fc = ops[im->fc_op];
+    const int K = fc.p[BN_CONV_CIN], N = fc.p[BN_CONV_COUT];
+    if (T[mo.in[0]].dims[2] != K) FAIL("tail: MEAN channels != FC inputs");
+    const int8_t* w = (const int8_t*)(fp.h_blob + fc.off[0]);
+    const int32_t* bias = (const int32_t*)(fp.h_blob + fc.off[1]);
+    std::vector<int> bf(N);
+    for (int n = 0; n < N; n++) {
+      long ws = 0;
+      for (int k = 0; k < K; k++) ws += w[(long)n * K + k];
+      bf[n] = (int)((long)bias[n] - (long)fc.p[BN_CONV_IN_ZP] * ws);
+    }
+    TailParams& Q = im->tail;
+    Q.w = (const int8_t*)(fp.d_blob + fc.off[0]);
+    Q.bias = (const int*)upload(im, bf.data(), bf.size() * 4);
+    Q.mult = (const int*)(fp.d_blob + fc.off[2]);
+    Q.shift = (const int*)(fp.d_blob + fc.off[3]);
+    Q.lut = (const int8_t*)(fp.d_blob + ops[im->logi_op].off[0]);
+    Q.K = K; Q.N = N; Q.npix = mo.p[BN_MEAN_COUNT];
+    Q.mean_in_zp = mo.p[BN_MEAN_IN_ZP]; Q.mean_out_zp = mo.p[BN_MEAN_OUT_ZP];
+    Q.mean_mult = mo.p[BN_MEAN_MULT]; Q.mean_shift = mo.p[BN_MEAN_SHIFT];
+    Q.mean_mult_n = mo.p[BN_MEAN_MULT_N]; Q.mean_shift_n = mo.p[BN_MEAN_SHIFT_N]; Q.keep_dims = mo.p[BN_MEAN_KEEP_DIMS];
+    Q.mean_in_scale = T[mo.in[0]].scale; Q.mean_out_scale = T[mo.out].scale;
+    Q.fc_out_zp = fc.p[BN_CONV_OUT_ZP]; Q.fc_act_min = fc.p[BN_CONV_ACT_MIN]; Q.fc_act_max = fc.p[BN_CONV_ACT_MAX];
+    Q.dq_scale = ops[im->deq_op].f[0]; Q.dq_zp = ops[im->deq_op].p[0];
+    if (N > 256) FAIL("tail: too many classes");
+  }
+  return true;
+}
+
+void fast_plan_build(FastPlan& fp, const uint8_t* h_blob, const bn_blob_header* hdr, const bn_blob_tensor* tensors,
+                     const bn_blob_op* ops, uint8_t* d_blob) {
   fp.ok = false;
-  fp.hdr = hdr; fp.tensors = tensors; fp.ops = ops; fp.d_blob = d_blob;
+  fp.h_blob = h_blob; fp.hdr = hdr; fp.tensors = tensors; fp.ops = ops; fp.d_blob = d_blob;
+  fp.impl = new FastImpl();
+  fp.ok = build_impl(fp);
+  if (!fp.ok) { fast_plan_destroy(fp); }
 }
-int fast_plan_alloc_workspace(FastPlan&, int, size_t* total) { *total = 0; return 0; }
+
+void fast_plan_destroy(FastPlan& fp) {
+  if (!fp.impl) return;
+  fast_plan_free_workspace(fp);
+  for (void* p : fp.impl->d_consts) cudaFree(p);
+  for (int* p : fp.impl->d_add_luts) if (p) cudaFree(p);
+  if (fp.impl->d_head_lut) cudaFree(fp.impl->d_head_lut);
+  delete fp.impl;
+  fp.impl = nullptr;
+  fp.ok = false;
+}
+
+int fast_plan_alloc_workspace(FastPlan& fp, int wave, size_t* total) {
+  FastImpl* im = fp.impl;
+  *total = 0;
+  if (!im) return BN_ERR_STATE;
+  fast_plan_free_workspace(fp);
+  auto alloc = [&](size_t n) -> void* {
+    void* d = nullptr;
+    n = (n + 255) & ~(size_t)255;
+    if (cudaMalloc(&d, n) != cudaSuccess) return nullptr;
+    im->owned.push_back(d);
+    *total += n;
+    return d;
+  };
+  im->d_mags = (float*)alloc(sizeof(float) * (size_t)im->W * im->ldk * wave);
+  im->d_mnmx = (unsigned*)alloc(sizeof(unsigned) * 2 * wave);
+  if (!im->d_mags || !im->d_mnmx) return BN_ERR_CUDA;
+  std::vector<int> slots = {im->head_out_slot, im->stem_out_slot};
+  for (const Block& bl : im->blocks) { slots.push_back(bl.dw_slot); slots.push_back(bl.out_slot); }
+  for (int s : slots) {
+    void* d = alloc((size_t)fp.tensors[s].nbytes * wave);
+    if (!d) return BN_ERR_CUDA;
+    im->slot_buf[s] = d;
+  }
+  fp.wave = wave;
+  return 0;
+}
+
 void fast_plan_free_workspace(FastPlan& fp) {
-  for (void* p : fp.bufs) if (p) cudaFree(p);
-  fp.bufs.clear(); fp.tap_ids.clear(); fp.tap_bytes.clear(); fp.wave = 0;
+  FastImpl* im = fp.impl;
+  if (!im) return;
+  for (void* p : im->owned) cudaFree(p);
+  im->owned.clear(); im->slot_buf.clear();
+  im->d_mags = nullptr; im->d_mnmx = nullptr;
+  fp.wave = 0;
 }
-int fast_run_pcm(FastPlan&, const int16_t*, const float*, int, float*, int, int, cudaStream_t, int64_t*) { return BN_ERR_UNSUPPORTED; }
-int fast_run_spec(FastPlan&, const float*, int, float*, int, int, cudaStream_t, int64_t*) { return BN_ERR_UNSUPPORTED; }
-int fast_dump_tensor(FastPlan&, int, int, void*, size_t) { return BN_ERR_UNSUPPORTED; }
+
+int fast_dump_tensor(FastPlan& fp, int tfl_tensor_id, int Bw, void* out, size_t nbytes) {
+  FastImpl* im = fp.impl;
+  if (!im) return BN_ERR_STATE;
+  for (auto& kv : im->slot_buf) {
+    const bn_blob_tensor& t = fp.tensors[kv.first];
+    if (t.id != tfl_tensor_id) continue;
+    if (nbytes != (size_t)t.nbytes * Bw) return BN_ERR_ARG;
+    return cudaMemcpy(out, kv.second, nbytes, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : BN_ERR_CUDA;
+  }
+  return BN_ERR_UNSUPPORTED;
+}
+
+// =================================================================================================
+// device code
+// =================================================================================================
+__device__ __forceinline__ int requant(int acc, int mult, int shift, int R) { return mbqm(acc, mult, shift, R); }
+
+// 128 x 64 int8 GEMM tile on CUDA cores (dp4a).  At: [KW][GEMM_LDA] words (word = 4 consecutive k of one
+// row m), Wt: [KW][ldw] words (4 consecutive k of one channel n).  Thread (tm, tn) owns rows 8tm..8tm+7 and
+// channels n0+4tn..n0+4tn+3.
+__device__ __forceinline__ void gemm_128x64(const int* __restrict__ At, const int* __restrict__ Wt, int ldw, int n0, int KW,
+                                            int tm, int tn, int (&acc)[8][4]) {
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j] = 0;
+#pragma unroll 2
+  for (int kw = 0; kw < KW; kw++) {
+    const int4 a0 = *reinterpret_cast<const int4*>(At + kw * GEMM_LDA + 8 * tm);
+    const int4 a1 = *reinterpret_cast<const int4*>(At + kw * GEMM_LDA + 8 * tm + 4);
+    const int4 w = *reinterpret_cast<const int4*>(Wt + kw * ldw + n0 + 4 * tn);
+    const int a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const int ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) acc[i][j] = __dp4a(a[i], ww[j], acc[i][j]);
+  }
+}
+
+// ---- K2: head -------------------------------------------------------------------------------------
+// MODE 0: mags = raw |STFT| float32 [B][W][ldk] (frame-major) + mnmx;  MODE 1: spec = normalised float32
+// [B][bins][W] (the graph input layout).  out = int8 [B][64][W].
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_head(const float* __restrict__ src, const unsigned* __restrict__ mnmx, int8_t* __restrict__ out, HeadParams H, int ldk, int R) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  int* At = reinterpret_cast<int*>(smem);                       // [KW][132]
+  int* Wt = At + H.KW * GEMM_LDA;                               // [KW][64]
+  uint8_t* lut = reinterpret_cast<uint8_t*>(Wt + H.KW * HEAD_N);   // [64][256]
+  int* prm = reinterpret_cast<int*>(lut + HEAD_N * 256);        // bias[64] mult[64] shift[64]
+  const int tid = threadIdx.x;
+  const int halves = H.W / HEAD_M;
+  const int b = blockIdx.x / halves;
+  const int t0 = (blockIdx.x % halves) * HEAD_M;
+
+  for (int i = tid; i < H.KW * HEAD_N; i += 256) Wt[i] = __ldg(H.wt + i);
+  for (int i = tid; i < HEAD_N * 256 / 4; i += 256) reinterpret_cast<int*>(lut)[i] = __ldg(reinterpret_cast<const int*>(H.lut) + i);
+  if (tid < HEAD_N) { prm[tid] = __ldg(H.bias + tid); prm[64 + tid] = __ldg(H.mult + tid); prm[128 + tid] = __ldg(H.shift + tid); }
+
+  const unsigned fillw = 0x01010101u * (unsigned)(uint8_t)H.fill;
+  if (MODE == 0) {
+    const float mn = __uint_as_float(mnmx[2 * b]), mx = __uint_as_float(mnmx[2 * b + 1]);
+    const float den = (float)((double)(mx - mn) + 1e-10);       // normalize(): numpy 1.26 scalar promotion
+    const float4* s4 = reinterpret_cast<const float4*>(src + ((long)b * H.W + t0) * ldk);
+    const int row_w = ldk / 4;                                  // float4 per frame row (== KW)
+    for (int i = tid; i < HEAD_M * row_w; i += 256) {
+      const int row = i / row_w, c4 = i - row * row_w;
+      const int k = 4 * c4;
+      unsigned word = fillw;
+      if (k < H.K_real) {
+        const float4 v = s4[i];
+        const float f[4] = {v.x, v.y, v.z, v.w};
+        word = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          int q;
+          if (k + j < H.K_real) {
+            const float nrm = __fdiv_rn(f[j] - mn, den);
+            q = clampi((int)roundf(__fdiv_rn(nrm, H.q_scale)) + H.q_zp, -128, 127);
+          } else q = H.fill;
+          word |= (unsigned)(uint8_t)q << (8 * j);
+        }
+      }
+      At[c4 * GEMM_LDA + row] = (int)word;
+    }
+  } else {
+    // bin-major normalised input: element (k, t) at src[b][k][t]
+    const float* sb = src + (long)b * H.K_real * H.W + t0;
+    for (int i = tid; i < HEAD_M * H.KW; i += 256) {
+      const int c4 = i / HEAD_M, row = i - c4 * HEAD_M;         // lanes along frames: coalesced per k
+      unsigned word = 0;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int k = 4 * c4 + j;
+        int q = H.fill;
+        if (k < H.K_real) q = clampi((int)roundf(__fdiv_rn(sb[(long)k * H.W + row], H.q_scale)) + H.q_zp, -128, 127);
+        word |= (unsigned)(uint8_t)q << (8 * j);
+      }
+      At[c4 * GEMM_LDA + row] = (int)word;
+    }
+  }
+  __syncthreads();
+
+  const int tn = tid & 15, tm = tid >> 4;
+  int acc[8][4];
+  gemm_128x64(At, Wt, HEAD_N, 0, H.KW, tm, tn, acc);
+
+  // epilogue: requant (ReLU clamp) -> folded element-wise chain LUT -> transposed store [c][t]
+  int8_t* ob = out + (long)b * HEAD_N * H.W + t0 + 8 * tm;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int c = 4 * tn + j;
+    const int bias = prm[c], mult = prm[64 + c], shift = prm[128 + c];
+    unsigned lo = 0, hi = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      int v = clampi(requant(acc[i][j] + bias, mult, shift, R) + H.out_zp, H.act_min, H.act_max);
+      unsigned q = lut[c * 256 + (v + 128)];
+      if (i < 4) lo |= q << (8 * i); else hi |= q << (8 * (i - 4));
+    }
+    *reinterpret_cast<uint2*>(ob + (long)c * H.W) = make_uint2(lo, hi);
+  }
+}
+
+// ---- K3: stem conv 3x3, stride (1,2), Cin = 1, Cout = 16 ----------------------------------------------
+// in int8 [B][ih][iw]; out int8 [B][oh][ow][16].  CTA = (band of 16 output rows, chunk); thread = 2 adjacent
+// output pixels at a time.
+constexpr int STEM_ROWS = 16;
+__global__ void __launch_bounds__(256)
+k_stem(const int8_t* __restrict__ in, int8_t* __restrict__ out, StemParams S, int R) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int ldt = S.iw + 8;                                     // tile row stride in bytes (multiple of 4)
+  unsigned char* tile = smem;                                   // [(STEM_ROWS+2)][ldt], halo = zero point
+  int* prm = reinterpret_cast<int*>(smem + (STEM_ROWS + 2) * ldt);   // w[48] bias[16] mult[16] shift[16]
+  const int tid = threadIdx.x;
+  const int b = blockIdx.y;
+  const int y0 = blockIdx.x * STEM_ROWS;
+  if (tid < 48) prm[tid] = __ldg(S.w + tid);
+  if (tid < 16) { prm[48 + tid] = __ldg(S.bias + tid); prm[64 + tid] = __ldg(S.mult + tid); prm[80 + tid] = __ldg(S.shift + tid); }
+  const unsigned zpw = 0x01010101u * (unsigned)(uint8_t)S.in_zp;
+  const int words = ldt / 4;
+  const int8_t* ib = in + (long)b * S.ih * S.iw;
+  for (int i = tid; i < (STEM_ROWS + 2) * words; i += 256) {
+    const int r = i / words, w = i - r * words;
+    const int iy = y0 - 1 + r;
+    unsigned v = zpw;
+    if (iy >= 0 && iy < S.ih && 4 * w < S.iw) v = __ldg(reinterpret_cast<const unsigned*>(ib + (long)iy * S.iw) + w);
+    reinterpret_cast<unsigned*>(tile)[r * words + w] = v;
+  }
+  __syncthreads();
+  const int pairs = S.ow / 2;
+  for (int i = tid; i < STEM_ROWS * pairs; i += 256) {
+    const int ry = i / pairs, px = i - ry * pairs;             // output row within band, pixel pair index
+    if (y0 + ry >= S.oh) continue;
+    // input columns: pixel x=2px uses bytes 4px..4px+2 ; pixel x=2px+1 uses bytes 4px+2..4px+4
+    unsigned xa[3], xb[3];
+#pragma unroll
+    for (int fy = 0; fy < 3; fy++) {
+      const unsigned* rowp = reinterpret_cast<const unsigned*>(tile + (ry + fy) * ldt);
+      const unsigned w0 = rowp[px], w1 = rowp[px + 1];
+      xa[fy] = w0;
+      xb[fy] = __funnelshift_r(w0, w1, 16);
+    }
+    unsigned oa[4] = {0, 0, 0, 0}, obv[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int co = 0; co < 16; co++) {
+      int sa = 0, sb = 0;
+#pragma unroll
+      for (int fy = 0; fy < 3; fy++) {
+        const int w = prm[co * 3 + fy];
+        sa = __dp4a((int)xa[fy], w, sa);
+        sb = __dp4a((int)xb[fy], w, sb);
+      }
+      const int bias = prm[48 + co], mult = prm[64 + co], shift = prm[80 + co];
+      const int qa = clampi(requant(sa + bias, mult, shift, R) + S.out_zp, S.act_min, S.act_max);
+      const int qb = clampi(requant(sb + bias, mult, shift, R) + S.out_zp, S.act_min, S.act_max);
+      oa[co >> 2] |= (unsigned)(uint8_t)qa << (8 * (co & 3));
+      obv[co >> 2] |= (unsigned)(uint8_t)qb << (8 * (co & 3));
+    }
+    int8_t* op = out + (((long)b * S.oh + (y0 + ry)) * S.ow + 2 * px) * 16;
+    *reinterpret_cast<uint4*>(op) = make_uint4(oa[0], oa[1], oa[2], oa[3]);
+    *reinterpret_cast<uint4*>(op + 16) = make_uint4(obv[0], obv[1], obv[2], obv[3]);
+  }
+}
+
+// ---- K4: depthwise 3x3 ----------------------------------------------------------------------------------
+// in int8 [B][ih][iw][C], out int8 [B][oh][ow][C]; thread = one output pixel x 4 channels.
+__global__ void __launch_bounds__(256)
+k_dw3x3(const int8_t* __restrict__ in, int8_t* __restrict__ out, long n_items, DwParams D, int R) {
+  extern __shared__ __align__(16) int dsm[];
+  const int CG = D.C / 4;
+  int* wm = dsm;                                  // [9][CG][4]
+  int* prm = dsm + 9 * D.C;                       // bias[C] mult[C] shift[C]
+  for (int i = threadIdx.x; i < 9 * D.C; i += blockDim.x) wm[i] = __ldg(D.wm + i);
+  for (int i = threadIdx.x; i < D.C; i += blockDim.x) {
+    prm[i] = __ldg(D.bias + i); prm[D.C + i] = __ldg(D.mult + i); prm[2 * D.C + i] = __ldg(D.shift + i);
+  }
+  __syncthreads();
+  const unsigned zpw = 0x01010101u * (unsigned)(uint8_t)D.in_zp;
+  for (long it = (long)blockIdx.x * blockDim.x + threadIdx.x; it < n_items; it += (long)gridDim.x * blockDim.x) {
+    const int cg = (int)(it % CG);
+    long r = it / CG;
+    const int ox = (int)(r % D.ow);
+    r /= D.ow;
+    const int oy = (int)(r % D.oh);
+    const long b = r / D.oh;
+    const unsigned* ib = reinterpret_cast<const unsigned*>(in + b * (long)D.ih * D.iw * D.C) + cg;
+    int acc[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int fy = 0; fy < 3; fy++) {
+      const int iy = oy * D.sh - D.pt + fy;
+#pragma unroll
+      for (int fx = 0; fx < 3; fx++) {
+        const int ix = ox * D.sw - D.pl + fx;
+        unsigned x = zpw;
+        if (iy >= 0 && iy < D.ih && ix >= 0 && ix < D.iw) x = __ldg(ib + ((long)iy * D.iw + ix) * CG);
+        const int4 w = *reinterpret_cast<const int4*>(wm + ((fy * 3 + fx) * CG + cg) * 4);
+        acc[0] = __dp4a((int)x, w.x, acc[0]);
+        acc[1] = __dp4a((int)x, w.y, acc[1]);
+        acc[2] = __dp4a((int)x, w.z, acc[2]);
+        acc[3] = __dp4a((int)x, w.w, acc[3]);
+      }
+    }
+    const int4 bias = *reinterpret_cast<const int4*>(prm + 4 * cg);
+    const int4 mult = *reinterpret_cast<const int4*>(prm + D.C + 4 * cg);
+    const int4 shift = *reinterpret_cast<const int4*>(prm + 2 * D.C + 4 * cg);
+    unsigned o = 0;
+    o |= (unsigned)(uint8_t)clampi(requant(acc[0] + bias.x, mult.x, shift.x, R) + D.out_zp, D.act_min, D.act_max);
+    o |= (unsigned)(uint8_t)clampi(requant(acc[1] + bias.y, mult.y, shift.y, R) + D.out_zp, D.act_min, D.act_max) << 8;
+    o |= (unsigned)(uint8_t)clampi(requant(acc[2] + bias.z, mult.z, shift.z, R) + D.out_zp, D.act_min, D.act_max) << 16;
+    o |= (unsigned)(uint8_t)clampi(requant(acc[3] + bias.w, mult.w, shift.w, R) + D.out_zp, D.act_min, D.act_max) << 24;
+    reinterpret_cast<unsigned*>(out)[it] = o;
+  }
+}
+
+// ---- K5: pointwise conv = GEMM [M, K] x [N, K]^T with fused requant (+ residual ADD) --------------------------
+// x int8 [M][K] (NHWC rows), res int8 [M][N] or NULL, y int8 [M][N].  CTA = 128 rows, loops over N in chunks of 64
+// (N == 32 handled as one half-used chunk).
+__global__ void __launch_bounds__(256)
+k_pw(const int8_t* __restrict__ x, const int8_t* __restrict__ res, int8_t* __restrict__ y, long M, PwParams P, int R) {
+  extern __shared__ __align__(16) int psm[];
+  const int KW = P.K / 4;
+  const int NP = P.N < 64 ? 64 : P.N;              // padded channel count in smem
+  int* At = psm;                                   // [KW][132]
+  int* Wt = At + KW * GEMM_LDA;                    // [KW][NP]
+  int* prm = Wt + KW * NP;                         // bias[NP] mult[NP] shift[NP]
+  int* luts = prm + 3 * NP;                        // [512] when has_add
+  const int tid = threadIdx.x;
+  const long m0 = (long)blockIdx.x * 128;
+  for (int i = tid; i < KW * NP; i += 256) {
+    const int kw = i / NP, n = i - kw * NP;
+    Wt[i] = n < P.N ? __ldg(P.wt + kw * P.N + n) : 0;
+  }
+  for (int i = tid; i < NP; i += 256) {
+    const bool ok = i < P.N;
+    prm[i] = ok ? __ldg(P.bias + i) : 0; prm[NP + i] = ok ? __ldg(P.mult + i) : 0; prm[2 * NP + i] = ok ? __ldg(P.shift + i) : 0;
+  }
+  if (P.has_add) for (int i = tid; i < 512; i += 256) luts[i] = __ldg(P.lut_res + i);
+  // stage A transposed: word (m, kw) -> At[kw][m]
+  const unsigned* xw = reinterpret_cast<const unsigned*>(x + m0 * P.K);
+  for (int i = tid; i < 128 * KW; i += 256) {
+    const int m = i / KW, kw = i - m * KW;
+    unsigned v = 0;
+    if (m0 + m < M) v = __ldg(xw + i);
+    At[kw * GEMM_LDA + m] = (int)v;
+  }
+  __syncthreads();
+  const int tn = tid & 15, tm = tid >> 4;
+  for (int n0 = 0; n0 < P.N; n0 += 64) {
+    int acc[8][4];
+    gemm_128x64(At, Wt, NP, n0, KW, tm, tn, acc);
+    const int c0 = n0 + 4 * tn;
+    if (c0 >= P.N) continue;
+    const int4 bias = *reinterpret_cast<const int4*>(prm + c0);
+    const int4 mult = *reinterpret_cast<const int4*>(prm + NP + c0);
+    const int4 shift = *reinterpret_cast<const int4*>(prm + 2 * NP + c0);
+    const int bs[4] = {bias.x, bias.y, bias.z, bias.w}, ms[4] = {mult.x, mult.y, mult.z, mult.w}, ss[4] = {shift.x, shift.y, shift.z, shift.w};
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const long m = m0 + 8 * tm + i;
+      if (m >= M) continue;
+      unsigned rw = 0;
+      if (P.has_add) rw = __ldg(reinterpret_cast<const unsigned*>(res + m * P.N + c0));
+      unsigned o = 0;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        int q = clampi(requant(acc[i][j] + bs[j], ms[j], ss[j], R) + P.out_zp, P.act_min, P.act_max);
+        if (P.has_add) {
+          const int r8 = (int)(int8_t)((rw >> (8 * j)) & 0xffu);
+          const int s = luts[r8 + 128] + luts[256 + q + 128];
+          q = clampi(requant(s, P.add_mo, P.add_so, R) + P.add_out_zp, P.add_act_min, P.add_act_max);
+        }
+        o |= (unsigned)(uint8_t)q << (8 * j);
+      }
+      *reinterpret_cast<unsigned*>(y + m * P.N + c0) = o;
+    }
+  }
+}
+
+// ---- K6: tail: MEAN(H,W) + FC + LOGISTIC + DEQUANTIZE -------------------------------------------------------
+// x int8 [B][npix][K] -> scores float32 [B][N].  One CTA (256 threads) per chunk.
+__global__ void __launch_bounds__(256)
+k_tail(const int8_t* __restrict__ x, float* __restrict__ scores, TailParams Q, int variant, int R) {
+  __shared__ __align__(16) int8_t mean_q[1024];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int8_t* xb = x + (long)b * Q.npix * Q.K;
+  for (int c = tid; c < Q.K; c += 256) {
+    int sum = 0;
+    for (int p = 0; p < Q.npix; p++) sum += xb[(long)p * Q.K + c];
+    int o;
+    const int N = Q.npix;
+    if (variant == 1) {
+      float scale = __fdiv_rn(Q.mean_in_scale, Q.mean_out_scale);
+      float bias = __fmul_rn(-(float)Q.mean_in_zp, scale);
+      float fm = __fdiv_rn((float)sum, (float)N);
+      o = (int)roundf(__fadd_rn(__fmul_rn(fm, scale), bias)) + Q.mean_out_zp;
+    } else if (variant == 2) {
+      o = requant(sum - Q.mean_in_zp * N, Q.mean_mult_n, Q.mean_shift_n, R) + Q.mean_out_zp;
+    } else {
+      int acc = requant(sum - Q.mean_in_zp * N, Q.mean_mult, Q.mean_shift, R);
+      acc = acc > 0 ? (acc + N / 2) / N : (acc - N / 2) / N;
+      o = acc + Q.mean_out_zp;
+    }
+    mean_q[c] = (int8_t)clampi(o, -128, 127);
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  const int KW = Q.K / 4;
+  for (int n = warp; n < Q.N; n += 8) {
+    const int* wrow = reinterpret_cast<const int*>(Q.w + (long)n * Q.K);
+    int acc = 0;
+    for (int kw = lane; kw < KW; kw += 32) acc = __dp4a(reinterpret_cast<const int*>(mean_q)[kw], __ldg(wrow + kw), acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      int q = clampi(requant(acc + __ldg(Q.bias + n), __ldg(Q.mult + n), __ldg(Q.shift + n), R) + Q.fc_out_zp, Q.fc_act_min, Q.fc_act_max);
+      int l = (int)__ldg(Q.lut + (uint8_t)(q + 128));
+      scores[(long)b * Q.N + n] = __fmul_rn(Q.dq_scale, (float)(l - Q.dq_zp));
+    }
+  }
+}
+
+// =================================================================================================
+// run
+// =================================================================================================
+static size_t head_smem(const HeadParams& H) { return (size_t)H.KW * GEMM_LDA * 4 + (size_t)H.KW * HEAD_N * 4 + HEAD_N * 256 + 3 * 64 * 4; }
+static size_t pw_smem(const PwParams& P) {
+  const int KW = P.K / 4, NP = P.N < 64 ? 64 : P.N;
+  return ((size_t)KW * GEMM_LDA + (size_t)KW * NP + 3 * NP + 512) * 4;
+}
+
+static int run_body(FastPlan& fp, int mode, const float* src, int Bw, float* d_scores, int rounding, int mean_variant,
+                    cudaStream_t st, int64_t* launches, Profiler* prof) {
+  FastImpl* im = fp.impl;
+  static bool attrs = false;
+  if (!attrs) {
+    cudaFuncSetAttribute(k_head<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_head<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_pw, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_dw3x3, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    attrs = true;
+  }
+  const int R = rounding;
+  // K2 head
+  int8_t* head_out = (int8_t*)im->slot_buf[im->head_out_slot];
+  {
+    const int grid = Bw * (im->W / HEAD_M);
+    if (prof) prof->begin("K2_head", st);
+    if (mode == 0) k_head<0><<<grid, 256, head_smem(im->head), st>>>(src, im->d_mnmx, head_out, im->head, im->ldk, R);
+    else k_head<1><<<grid, 256, head_smem(im->head), st>>>(src, nullptr, head_out, im->head, im->ldk, R);
+    if (prof) prof->end(st);
+    (*launches)++;
+  }
+  // K3 stem
+  int8_t* stem_out = (int8_t*)im->slot_buf[im->stem_out_slot];
+  {
+    const StemParams& S = im->stem;
+    dim3 grid((S.oh + STEM_ROWS - 1) / STEM_ROWS, Bw);
+    const size_t smem = (size_t)(STEM_ROWS + 2) * (S.iw + 8) + 96 * 4;
+    if (prof) prof->begin("K3_stem", st);
+    k_stem<<<grid, 256, smem, st>>>(head_out, stem_out, S, R);
+    if (prof) prof->end(st);
+    (*launches)++;
+  }
+  // blocks
+  char name[48];
+  int bi = 0;
+  for (const Block& bl : im->blocks) {
+    const int8_t* bin = (const int8_t*)im->slot_buf[bl.in_slot];
+    int8_t* dwo = (int8_t*)im->slot_buf[bl.dw_slot];
+    int8_t* bout = (int8_t*)im->slot_buf[bl.out_slot];
+    {
+      const DwParams& D = bl.dw;
+      const long items = (long)Bw * D.oh * D.ow * (D.C / 4);
+      long g = (items + 255) / 256;
+      if (g > 148L * 16) g = 148L * 16;
+      const size_t smem = (size_t)12 * D.C * 4;
+      snprintf(name, sizeof name, "K4_dw_%02d_c%d_s%d", bi, D.C, D.sh);
+      if (prof) prof->begin(name, st);
+      k_dw3x3<<<(int)g, 256, smem, st>>>(bin, dwo, items, D, R);
+      if (prof) prof->end(st);
+      (*launches)++;
+    }
+    {
+      const PwParams& P = bl.pw;
+      const long M = (long)Bw * bl.dw.oh * bl.dw.ow;
+      const int grid = (int)((M + 127) / 128);
+      snprintf(name, sizeof name, "K5_pw_%02d_k%d_n%d%s", bi, P.K, P.N, P.has_add ? "_add" : "");
+      if (prof) prof->begin(name, st);
+      k_pw<<<grid, 256, pw_smem(P), st>>>(dwo, P.has_add ? bin : nullptr, bout, M, P, R);
+      if (prof) prof->end(st);
+      (*launches)++;
+    }
+    bi++;
+  }
+  // tail
+  {
+    const int variant = mean_variant ? mean_variant : (im->tail.keep_dims ? 3 : 2);
+    const int8_t* last = (const int8_t*)im->slot_buf[im->blocks.back().out_slot];
+    if (prof) prof->begin("K6_tail", st);
+    k_tail<<<Bw, 256, 0, st>>>(last, d_scores, im->tail, variant, R);
+    if (prof) prof->end(st);
+    (*launches)++;
+  }
+  return cudaGetLastError() == cudaSuccess ? 0 : BN_ERR_CUDA;
+}
+
+int fast_run_pcm(FastPlan& fp, const int16_t* d_pcm, const float* d_peak, int Bw, float* d_scores, int rounding,
+                 int mean_variant, cudaStream_t st, int64_t* launches, Profiler* prof) {
+  FastImpl* im = fp.impl;
+  if (!im || Bw > fp.wave) return BN_ERR_STATE;
+  int rc = prepare_rounding(fp, rounding);
+  if (rc) return rc;
+  const bn_blob_header* h = fp.hdr;
+  if (prof) prof->begin("K1_stft", st);
+  rc = launch_stft_mag_fm(d_pcm, d_peak, im->d_mags, im->d_mnmx, Bw, (int)h->chunk_len, (int)h->n_fft, (int)h->hop, im->W, im->ldk, st);
+  if (prof) prof->end(st);
+  if (rc) return rc;
+  *launches += 2;
+  return run_body(fp, 0, im->d_mags, Bw, d_scores, rounding, mean_variant, st, launches, prof);
+}
+
+int fast_run_spec(FastPlan& fp, const float* d_spec, int Bw, float* d_scores, int rounding, int mean_variant,
+                  cudaStream_t st, int64_t* launches, Profiler* prof) {
+  FastImpl* im = fp.impl;
+  if (!im || Bw > fp.wave) return BN_ERR_STATE;
+  int rc = prepare_rounding(fp, rounding);
+  if (rc) return rc;
+  return run_body(fp, 1, d_spec, Bw, d_scores, rounding, mean_variant, st, launches, prof);
+}
 
 }  // namespace bn

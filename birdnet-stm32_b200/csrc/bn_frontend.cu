@@ -67,9 +67,10 @@ __device__ __forceinline__ void fft16(float2 (&v)[16]) {
 //   float2 zbuf[16][256+16]                 per half-warp exchange buffer (padded)
 //   float  tile[257][33]                    magnitude tile
 //   float  red[2*8]
+template <bool FRAME_MAJOR>
 __global__ void __launch_bounds__(FE_THREADS)
 k_stft_mag(const int16_t* __restrict__ pcm, const float* __restrict__ peak, float* __restrict__ out,
-           unsigned* __restrict__ mnmx, int T, int hop, int W) {
+           unsigned* __restrict__ mnmx, int T, int hop, int W, int ldk) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int span = (FRAMES_PER_CTA - 1) * hop + NFFT;
   float2* tw512 = reinterpret_cast<float2*>(smem_raw);
@@ -77,7 +78,7 @@ k_stft_mag(const int16_t* __restrict__ pcm, const float* __restrict__ peak, floa
   float* xs = win + NFFT;
   float2* zbuf = reinterpret_cast<float2*>(xs + ((span + 3) & ~3));
   float* tile = reinterpret_cast<float*>(zbuf + 16 * (NC + 16));
-  float* red = tile + BINS * TILE_LD;
+  float* red = FRAME_MAJOR ? tile : tile + BINS * TILE_LD;
 
   const int tid = threadIdx.x;
   const int b = blockIdx.y;
@@ -176,7 +177,8 @@ k_stft_mag(const int16_t* __restrict__ pcm, const float* __restrict__ peak, floa
         const float re = e.x + ow.x, im = e.y + ow.y;
         const float mag = sqrtf(re * re + im * im);
         if (t0 + f < W) {
-          tile[k * TILE_LD + f] = mag;
+          if (FRAME_MAJOR) out[((long)b * W + t0 + f) * ldk + k] = mag;   // 16 lanes -> 64 contiguous bytes
+          else tile[k * TILE_LD + f] = mag;
           lmin = fminf(lmin, mag);
           lmax = fmaxf(lmax, mag);
         }
@@ -200,6 +202,7 @@ k_stft_mag(const int16_t* __restrict__ pcm, const float* __restrict__ peak, floa
     atomicMax(mnmx + 2 * b + 1, __float_as_uint(mx));
   }
 
+  if (FRAME_MAJOR) return;
   // write the tile bin-major: out[b][k][t0 + f], 32 consecutive floats per bin row
   float* ob = out + (long)b * BINS * W;
   const int lane = tid & 31, wp = tid >> 5;
@@ -213,26 +216,46 @@ __global__ void k_init_minmax(unsigned* mnmx, int B) {
   if (i < B) { mnmx[2 * i] = 0x7f800000u; mnmx[2 * i + 1] = 0u; }
 }
 
-size_t stft_smem_bytes(int hop) {
+size_t stft_smem_bytes(int hop, bool frame_major) {
   const int span = (FRAMES_PER_CTA - 1) * hop + NFFT;
   size_t b = sizeof(float2) * NFFT + sizeof(float) * NFFT + sizeof(float) * ((span + 3) & ~3);
-  b += sizeof(float2) * 16 * (NC + 16) + sizeof(float) * BINS * TILE_LD + sizeof(float) * 16;
+  b += sizeof(float2) * 16 * (NC + 16) + sizeof(float) * 16;
+  b += frame_major ? 0 : sizeof(float) * BINS * TILE_LD;
   return b;
 }
 
 int launch_stft_mag(const int16_t* pcm, const float* peak, float* out, unsigned* mnmx, int B, int T, int n_fft,
                     int hop, int W, cudaStream_t st) {
   if (n_fft != NFFT) return BN_ERR_UNSUPPORTED;
-  const size_t smem = stft_smem_bytes(hop);
+  const size_t smem = stft_smem_bytes(hop, false);
   if (smem > 227 * 1024) return BN_ERR_UNSUPPORTED;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(k_stft_mag, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(k_stft_mag<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(k_stft_mag<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_done = true;
   }
   k_init_minmax<<<(B + 255) / 256, 256, 0, st>>>(mnmx, B);
   dim3 grid((W + FRAMES_PER_CTA - 1) / FRAMES_PER_CTA, B);
-  k_stft_mag<<<grid, FE_THREADS, smem, st>>>(pcm, peak, out, mnmx, T, hop, W);
+  k_stft_mag<false><<<grid, FE_THREADS, smem, st>>>(pcm, peak, out, mnmx, T, hop, W, 0);
+  return 0;
+}
+
+// Frame-major variant for the fused plan: out float32 [B, W, ldk] (raw magnitudes, bins 0..256 of
+// each frame contiguous; columns >= 257 are left untouched).
+int launch_stft_mag_fm(const int16_t* pcm, const float* peak, float* out, unsigned* mnmx, int B, int T, int n_fft,
+                       int hop, int W, int ldk, cudaStream_t st) {
+  if (n_fft != NFFT || ldk < BINS) return BN_ERR_UNSUPPORTED;
+  const size_t smem = stft_smem_bytes(hop, true);
+  if (smem > 227 * 1024) return BN_ERR_UNSUPPORTED;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_stft_mag<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_done = true;
+  }
+  k_init_minmax<<<(B + 255) / 256, 256, 0, st>>>(mnmx, B);
+  dim3 grid((W + FRAMES_PER_CTA - 1) / FRAMES_PER_CTA, B);
+  k_stft_mag<true><<<grid, FE_THREADS, smem, st>>>(pcm, peak, out, mnmx, T, hop, W, ldk);
   return 0;
 }
 

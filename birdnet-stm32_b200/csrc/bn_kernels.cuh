@@ -31,4 +31,7 @@ void launch_pool(const float* scores, const int* offs, float* out, int F, int C,
 int launch_stft_mag(const int16_t* pcm, const float* peak, float* out, unsigned* mnmx, int B, int T, int n_fft,
                     int hop, int W, cudaStream_t st);
 
+int launch_stft_mag_fm(const int16_t* pcm, const float* peak, float* out, unsigned* mnmx, int B, int T, int n_fft,
+                       int hop, int W, int ldk, cudaStream_t st);
+
 }  // namespace bn

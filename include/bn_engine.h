@@ -58,7 +58,8 @@ enum {
   BN_OPT_ROUNDING = 1,      /* 0 = gemmlowp double rounding (TFLite default build), 1 = single rounding */
   BN_OPT_MEAN_VARIANT = 2,  /* 0 auto, 1 float, 2 folded 1/N, 3 reference rounded divide    */
   BN_OPT_FORCE_GENERIC = 3, /* 1 = run one kernel per op and keep every tensor (debug taps)             */
-  BN_OPT_WAVE = 4           /* chunks processed per internal wave (workspace is sized for it)           */
+  BN_OPT_WAVE = 4,          /* chunks processed per internal wave (workspace is sized for it)           */
+  BN_OPT_PROFILE = 5        /* 1 = time every kernel with CUDA events, 0 = off, 2 = on + reset counters  */
 };
 
 typedef struct bn_info {
@@ -118,6 +119,10 @@ BN_API int bn_dump_tensor(bn_engine* e, int tfl_tensor_id, void* out, size_t nby
 
 /* Number of engine kernels launched by this engine since creation. */
 BN_API int64_t bn_launch_count(const bn_engine* e);
+
+/* Per-kernel device times collected while BN_OPT_PROFILE is on (CUDA events on the launching
+ * stream).  Iterate index = 0.. until BN_ERR_ARG.  ms = accumulated milliseconds, count = launches. */
+BN_API int bn_profile_read(bn_engine* e, int index, char* name, size_t name_cap, double* ms, int64_t* count);
 
 /* Pinned host memory helpers for callers that want overlapped staging. */
 BN_API void* bn_host_alloc(size_t nbytes);

@@ -74,6 +74,37 @@ def test_graph_bit_exact_default_plan(runner, oracle_model, oracle_spec):
     assert one.dtype == np.float32 and one.shape == (1, 100)
 
 
+def test_fused_plan_is_active_and_its_tensors_are_bit_exact(runner, graph, oracle_model, oracle_spec):
+    """The shipped graph must match the fused pattern; every tensor the fused plan materialises
+    (head output #96, stem #97, every depthwise / block output) equals the oracle's."""
+    assert runner.query().fast_path == 1
+    B = oracle_spec.shape[0]
+    got = runner.predict(oracle_spec)
+    np.testing.assert_array_equal(got, oracle_model.predict(oracle_spec))
+    fused_taps = [96, 97, 98, 99, 100, 102, 103, 104, 105, 107, 108, 110, 111, 112, 113, 115, 116, 118, 119, 121, 122, 123, 124, 126]
+    for tid in fused_taps:
+        t = graph.tensor(tid)
+        nb = int(np.prod(t.shape[1:]))
+        g = runner.dump_tensor(tid, nb * B)
+        _, o = oracle_model.run(oracle_spec, tap_id=tid)
+        assert np.array_equal(g, o.reshape(-1)), f"fused tensor {tid} differs in {(g != o.reshape(-1)).sum()} of {g.size}"
+
+
+def test_full_path_same_codes_as_generic_plan(runner, pcm_batch):
+    """PCM16 path: fused plan (frame-major STFT + fused quantise) vs generic plan (bin-major STFT,
+    normalise, QUANTIZE op): identical scores -> the fused head quantises exactly like the op chain."""
+    from birdnet_stm32 import _lib as L
+
+    pcm, peak = pcm_batch
+    fused = runner.predict_pcm16(pcm, peak)
+    runner.set_option(L.BN_OPT_FORCE_GENERIC, 1)
+    try:
+        generic = runner.predict_pcm16(pcm, peak)
+    finally:
+        runner.set_option(L.BN_OPT_FORCE_GENERIC, 0)
+    np.testing.assert_array_equal(fused, generic)
+
+
 def test_rounding_and_mean_variants_match_oracle(runner, blob, oracle_spec):
     from birdnet_stm32 import _lib as L
     from oracle import bn_oracle
