@@ -50,6 +50,22 @@ __host__ __device__ __forceinline__ int32_t mbqm_rshift(int32_t x, int32_t qm, i
   return rdivpot(srdhm(x, qm), right);
 }
 
+// Double-rounding requantisation specialised for a right shift n = -shift in [1, 31]:
+//   SRDHM(acc, mult) = (acc*mult + 2^30) >> 31                          (one wide multiply-add + funnel shift)
+//   RoundingDivideByPOT(v, n) = (v + 2^(n-1) + (v >> 31)) >> n          (ties away from zero)
+// Bit-identical to mbqm(acc, mult, -n, 0); see tests/test_oracle_graph.py for the equivalence check.
+__host__ __device__ __forceinline__ int32_t rq_fast(int32_t acc, int32_t mult, int n) {
+  const long long p = (long long)acc * (long long)mult + (1ll << 30);
+  const int32_t v = (int32_t)(p >> 31);
+  return (v + (1 << (n - 1)) + (v >> 31)) >> n;
+}
+
+template <bool FAST>
+__host__ __device__ __forceinline__ int32_t requant_t(int32_t acc, int32_t mult, int shift, int rounding) {
+  if (FAST) return rq_fast(acc, mult, -shift);
+  return mbqm(acc, mult, shift, rounding);
+}
+
 __host__ __device__ __forceinline__ int32_t clampi(int32_t v, int32_t lo, int32_t hi) {
   return v < lo ? lo : (v > hi ? hi : v);
 }

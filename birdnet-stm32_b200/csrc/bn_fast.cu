@@ -68,6 +68,7 @@ struct PwParams {                 // pointwise conv (+ residual add) -- device p
   const int* shift;
   int K, N;
   int out_zp, act_min, act_max;   // of the conv itself
+  int fast;                       // all channels requantise with a right shift >= 1
   int has_add;
   const int* lut_res;             // [256] rescaled residual   (add input 1)
   const int* lut_conv;            // [256] rescaled conv output (add input 2)
@@ -79,12 +80,14 @@ struct DwParams {
   const int* bias; const int* mult; const int* shift;   // [C]
   int C, ih, iw, oh, ow, sh, sw, pt, pl;
   int in_zp, out_zp, act_min, act_max;
+  int fast;
 };
 
 struct StemParams {
   const int* w;                   // [16][3] words (w0,w1,w2,0) per (co, fy)
   const int* bias; const int* mult; const int* shift;
   int ih, iw, oh, ow, in_zp, out_zp, act_min, act_max;
+  int fast;
 };
 
 struct HeadParams {
@@ -96,6 +99,7 @@ struct HeadParams {
   float q_scale; int q_zp;
   int out_zp, act_min, act_max;
   int W;                          // frames per chunk
+  int fast;
 };
 
 struct TailParams {
@@ -218,6 +222,36 @@ static int prepare_rounding(FastPlan& fp, int rounding) {
 // pattern matching + weight preparation
 // -------------------------------------------------------------------------------------------------
 #define FAIL(msg) do { fp.why = msg; return false; } while (0)
+
+// Per-channel (multiplier, shift) of a conv op, with dead channels (multiplier 0, which TFLite encodes as
+// shift 0) re-encoded as (0, -1): the result is 0 either way.  fast = every channel is a right shift >= 1.
+// The closed-form rq_fast works in int32: it is only enabled when |SRDHM(acc)| + 2^(n-1) < 2^31 is guaranteed
+// for every channel, using the exact accumulator bound |bias| + sum|w| * max|x - zp| (taps = weights per channel).
+static void prep_requant(FastPlan& fp, FastImpl* im, const bn_blob_op& op, int C, const int** d_mult, const int** d_shift, int* fast) {
+  const int32_t* mult = (const int32_t*)(fp.h_blob + op.off[2]);
+  const int32_t* shift = (const int32_t*)(fp.h_blob + op.off[3]);
+  const int8_t* w = (const int8_t*)(fp.h_blob + op.off[0]);
+  const int32_t* bias = (const int32_t*)(fp.h_blob + op.off[1]);
+  const int zp = op.p[BN_CONV_IN_ZP];
+  const long xmax = (127 - zp) > (zp + 128) ? (127 - zp) : (zp + 128);
+  const int taps = op.p[BN_CONV_KH] * op.p[BN_CONV_KW];
+  const int cin = op.p[BN_CONV_CIN];
+  std::vector<int> m(mult, mult + C), sh(shift, shift + C);
+  int ok = 1;
+  for (int c = 0; c < C; c++) {
+    if (m[c] == 0) sh[c] = -1;
+    if (sh[c] > -1 || sh[c] < -31) { ok = 0; continue; }
+    long wsum = 0;
+    if (op.kind == BN_OP_DWCONV2D) { for (int t = 0; t < taps; t++) wsum += labs((long)w[(long)t * C + c]); }
+    else { for (long k = 0; k < (long)taps * cin; k++) wsum += labs((long)w[(long)c * taps * cin + k]); }
+    const long amax = labs((long)bias[c]) + wsum * xmax;                    // |acc| bound
+    const long vmax = (long)(((__int128)amax * m[c] + (1ll << 30)) >> 31) + 1;   // |SRDHM| bound
+    if (vmax + (1l << (-sh[c] - 1)) >= (1l << 31)) ok = 0;
+  }
+  *d_mult = (const int*)upload(im, m.data(), (size_t)C * 4);
+  *d_shift = (const int*)upload(im, sh.data(), (size_t)C * 4);
+  *fast = ok;
+}
 
 static bool is_identity_slice(const FastPlan& fp, const bn_blob_op& op) {
   if (op.kind != BN_OP_SLICE) return false;
@@ -369,8 +403,7 @@ static bool build_impl(FastPlan& fp) {
     HeadParams& H = im->head;
     H.wt = (const int*)upload(im, wt.data(), wt.size() * 4);
     H.bias = (const int*)upload(im, bf.data(), bf.size() * 4);
-    H.mult = (const int*)(fp.d_blob + mel.off[2]);
-    H.shift = (const int*)(fp.d_blob + mel.off[3]);
+    prep_requant(fp, im, mel, HEAD_N, &H.mult, &H.shift, &H.fast);
     if (cudaMalloc(&im->d_head_lut, HEAD_N * 256) != cudaSuccess) FAIL("cudaMalloc");
     H.lut = im->d_head_lut;
     H.KW = K_cat / 4; H.K_real = im->bins; H.fill = fill_val;
@@ -394,8 +427,7 @@ static bool build_impl(FastPlan& fp) {
     StemParams& S = im->stem;
     S.w = (const int*)upload(im, ww.data(), ww.size() * 4);
     S.bias = (const int*)upload(im, bf.data(), bf.size() * 4);
-    S.mult = (const int*)(fp.d_blob + st.off[2]);
-    S.shift = (const int*)(fp.d_blob + st.off[3]);
+    prep_requant(fp, im, st, 16, &S.mult, &S.shift, &S.fast);
     S.ih = T[st.in[0]].dims[0]; S.iw = T[st.in[0]].dims[1]; S.oh = T[st.out].dims[0]; S.ow = T[st.out].dims[1];
     S.in_zp = st.p[BN_CONV_IN_ZP]; S.out_zp = st.p[BN_CONV_OUT_ZP]; S.act_min = st.p[BN_CONV_ACT_MIN]; S.act_max = st.p[BN_CONV_ACT_MAX];
   }
@@ -419,8 +451,7 @@ static bool build_impl(FastPlan& fp) {
       DwParams& D = bl.dw;
       D.wm = (const int*)upload(im, wm.data(), wm.size() * 4);
       D.bias = (const int*)upload(im, bf.data(), bf.size() * 4);
-      D.mult = (const int*)(fp.d_blob + dw.off[2]);
-      D.shift = (const int*)(fp.d_blob + dw.off[3]);
+      prep_requant(fp, im, dw, C, &D.mult, &D.shift, &D.fast);
       D.C = C; D.ih = T[dw.in[0]].dims[0]; D.iw = T[dw.in[0]].dims[1]; D.oh = T[dw.out].dims[0]; D.ow = T[dw.out].dims[1];
       D.sh = dw.p[BN_CONV_SH]; D.sw = dw.p[BN_CONV_SW]; D.pt = dw.p[BN_CONV_PAD_T]; D.pl = dw.p[BN_CONV_PAD_L];
       D.in_zp = dw.p[BN_CONV_IN_ZP]; D.out_zp = dw.p[BN_CONV_OUT_ZP]; D.act_min = dw.p[BN_CONV_ACT_MIN]; D.act_max = dw.p[BN_CONV_ACT_MAX];
@@ -432,8 +463,7 @@ static bool build_impl(FastPlan& fp) {
       PwParams& P = bl.pw;
       P.wt = (const int*)upload(im, wt.data(), wt.size() * 4);
       P.bias = (const int*)upload(im, bf.data(), bf.size() * 4);
-      P.mult = (const int*)(fp.d_blob + pw.off[2]);
-      P.shift = (const int*)(fp.d_blob + pw.off[3]);
+      prep_requant(fp, im, pw, N, &P.mult, &P.shift, &P.fast);
       P.K = K; P.N = N;
       P.out_zp = pw.p[BN_CONV_OUT_ZP]; P.act_min = pw.p[BN_CONV_ACT_MIN]; P.act_max = pw.p[BN_CONV_ACT_MAX];
       P.has_add = bl.add_op >= 0;
@@ -551,6 +581,7 @@ int fast_dump_tensor(FastPlan& fp, int tfl_tensor_id, int Bw, void* out, size_t 
 // device code
 // =================================================================================================
 __device__ __forceinline__ int requant(int acc, int mult, int shift, int R) { return mbqm(acc, mult, shift, R); }
+#define RQ(acc, mult, shift) requant_t<FAST>(acc, mult, shift, R)
 
 // 128 x 64 int8 GEMM tile on CUDA cores (dp4a).  At: [KW][GEMM_LDA] words (word = 4 consecutive k of one
 // row m), Wt: [KW][ldw] words (4 consecutive k of one channel n).  Thread (tm, tn) owns rows 8tm..8tm+7 and
@@ -578,7 +609,7 @@ __device__ __forceinline__ void gemm_128x64(const int* __restrict__ At, const in
 // ---- K2: head -------------------------------------------------------------------------------------
 // MODE 0: mags = raw |STFT| float32 [B][W][ldk] (frame-major) + mnmx;  MODE 1: spec = normalised float32
 // [B][bins][W] (the graph input layout).  out = int8 [B][64][W].
-template <int MODE>
+template <int MODE, bool FAST>
 __global__ void __launch_bounds__(256)
 k_head(const float* __restrict__ src, const unsigned* __restrict__ mnmx, int8_t* __restrict__ out, HeadParams H, int ldk, int R) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -652,7 +683,7 @@ k_head(const float* __restrict__ src, const unsigned* __restrict__ mnmx, int8_t*
     unsigned lo = 0, hi = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-      int v = clampi(requant(acc[i][j] + bias, mult, shift, R) + H.out_zp, H.act_min, H.act_max);
+      int v = clampi(RQ(acc[i][j] + bias, mult, shift) + H.out_zp, H.act_min, H.act_max);
       unsigned q = lut[c * 256 + (v + 128)];
       if (i < 4) lo |= q << (8 * i); else hi |= q << (8 * (i - 4));
     }
@@ -664,6 +695,7 @@ k_head(const float* __restrict__ src, const unsigned* __restrict__ mnmx, int8_t*
 // in int8 [B][ih][iw]; out int8 [B][oh][ow][16].  CTA = (band of 16 output rows, chunk); thread = 2 adjacent
 // output pixels at a time.
 constexpr int STEM_ROWS = 16;
+template <bool FAST>
 __global__ void __launch_bounds__(256)
 k_stem(const int8_t* __restrict__ in, int8_t* __restrict__ out, StemParams S, int R) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -710,8 +742,8 @@ k_stem(const int8_t* __restrict__ in, int8_t* __restrict__ out, StemParams S, in
         sb = __dp4a((int)xb[fy], w, sb);
       }
       const int bias = prm[48 + co], mult = prm[64 + co], shift = prm[80 + co];
-      const int qa = clampi(requant(sa + bias, mult, shift, R) + S.out_zp, S.act_min, S.act_max);
-      const int qb = clampi(requant(sb + bias, mult, shift, R) + S.out_zp, S.act_min, S.act_max);
+      const int qa = clampi(RQ(sa + bias, mult, shift) + S.out_zp, S.act_min, S.act_max);
+      const int qb = clampi(RQ(sb + bias, mult, shift) + S.out_zp, S.act_min, S.act_max);
       oa[co >> 2] |= (unsigned)(uint8_t)qa << (8 * (co & 3));
       obv[co >> 2] |= (unsigned)(uint8_t)qb << (8 * (co & 3));
     }
@@ -722,58 +754,91 @@ k_stem(const int8_t* __restrict__ in, int8_t* __restrict__ out, StemParams S, in
 }
 
 // ---- K4: depthwise 3x3 ----------------------------------------------------------------------------------
-// in int8 [B][ih][iw][C], out int8 [B][oh][ow][C]; thread = one output pixel x 4 channels.
+// in int8 [B][ih][iw][C], out int8 [B][oh][ow][C].  Thread = one output column (ox) x 4 channels; it walks down a
+// band of output rows with a 3x3 register window (3 or 6 new input words per output row), the 36 masked weight
+// words and the 12 requantisation parameters stay in registers.  Out-of-range taps read the zero point (SAME pad).
+template <int SH, bool FAST>
 __global__ void __launch_bounds__(256)
-k_dw3x3(const int8_t* __restrict__ in, int8_t* __restrict__ out, long n_items, DwParams D, int R) {
-  extern __shared__ __align__(16) int dsm[];
-  const int CG = D.C / 4;
-  int* wm = dsm;                                  // [9][CG][4]
-  int* prm = dsm + 9 * D.C;                       // bias[C] mult[C] shift[C]
-  for (int i = threadIdx.x; i < 9 * D.C; i += blockDim.x) wm[i] = __ldg(D.wm + i);
-  for (int i = threadIdx.x; i < D.C; i += blockDim.x) {
-    prm[i] = __ldg(D.bias + i); prm[D.C + i] = __ldg(D.mult + i); prm[2 * D.C + i] = __ldg(D.shift + i);
-  }
-  __syncthreads();
-  const unsigned zpw = 0x01010101u * (unsigned)(uint8_t)D.in_zp;
-  for (long it = (long)blockIdx.x * blockDim.x + threadIdx.x; it < n_items; it += (long)gridDim.x * blockDim.x) {
-    const int cg = (int)(it % CG);
-    long r = it / CG;
-    const int ox = (int)(r % D.ow);
-    r /= D.ow;
-    const int oy = (int)(r % D.oh);
-    const long b = r / D.oh;
-    const unsigned* ib = reinterpret_cast<const unsigned*>(in + b * (long)D.ih * D.iw * D.C) + cg;
-    int acc[4] = {0, 0, 0, 0};
+k_dw3x3(const int8_t* __restrict__ in, int8_t* __restrict__ out, DwParams D, int rows_per_band, int R) {
+  const int CG = D.C >> 2;
+  const int ncol = D.ow * CG;
+  const int col_blocks = (ncol + 255) >> 8;
+  const int cb = blockIdx.x % col_blocks, band = blockIdx.x / col_blocks;
+  const int idx = cb * 256 + threadIdx.x;
+  if (idx >= ncol) return;
+  const int ox = idx / CG, cg = idx - ox * CG;
+  const int b = blockIdx.y;
+  int4 w[9];
 #pragma unroll
-    for (int fy = 0; fy < 3; fy++) {
-      const int iy = oy * D.sh - D.pt + fy;
+  for (int t = 0; t < 9; t++) w[t] = __ldg(reinterpret_cast<const int4*>(D.wm) + t * CG + cg);
+  const int4 bias = __ldg(reinterpret_cast<const int4*>(D.bias) + cg);
+  const int4 mult = __ldg(reinterpret_cast<const int4*>(D.mult) + cg);
+  const int4 shift = __ldg(reinterpret_cast<const int4*>(D.shift) + cg);
+  const unsigned zpw = 0x01010101u * (unsigned)(uint8_t)D.in_zp;
+  const unsigned* ib = reinterpret_cast<const unsigned*>(in + (size_t)b * D.ih * D.iw * D.C) + cg;
+  unsigned* ob = reinterpret_cast<unsigned*>(out + (size_t)b * D.oh * D.ow * D.C) + cg;
+  int xoff[3];
+  bool xok[3];
+#pragma unroll
+  for (int fx = 0; fx < 3; fx++) {
+    const int ix = ox * SH - D.pl + fx;
+    xok[fx] = ix >= 0 && ix < D.iw;
+    xoff[fx] = ix * CG;
+  }
+  const int oy0 = band * rows_per_band;
+  const int oy1 = min(oy0 + rows_per_band, D.oh);
+  unsigned win[3][3];
+  auto load_row = [&](int iy, unsigned (&dst)[3]) {
+    const bool yok = iy >= 0 && iy < D.ih;
+    const unsigned* rp = ib + iy * D.iw * CG;
+#pragma unroll
+    for (int fx = 0; fx < 3; fx++) dst[fx] = (yok && xok[fx]) ? __ldg(rp + xoff[fx]) : zpw;
+  };
+  {
+    const int iy = oy0 * SH - D.pt;
+    load_row(iy, win[0]);
+    load_row(iy + 1, win[1]);
+    load_row(iy + 2, win[2]);
+  }
+  for (int oy = oy0; oy < oy1; oy++) {
+    int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+    for (int fy = 0; fy < 3; fy++)
 #pragma unroll
       for (int fx = 0; fx < 3; fx++) {
-        const int ix = ox * D.sw - D.pl + fx;
-        unsigned x = zpw;
-        if (iy >= 0 && iy < D.ih && ix >= 0 && ix < D.iw) x = __ldg(ib + ((long)iy * D.iw + ix) * CG);
-        const int4 w = *reinterpret_cast<const int4*>(wm + ((fy * 3 + fx) * CG + cg) * 4);
-        acc[0] = __dp4a((int)x, w.x, acc[0]);
-        acc[1] = __dp4a((int)x, w.y, acc[1]);
-        acc[2] = __dp4a((int)x, w.z, acc[2]);
-        acc[3] = __dp4a((int)x, w.w, acc[3]);
+        const int x = (int)win[fy][fx];
+        const int4 ww = w[fy * 3 + fx];
+        a0 = __dp4a(x, ww.x, a0);
+        a1 = __dp4a(x, ww.y, a1);
+        a2 = __dp4a(x, ww.z, a2);
+        a3 = __dp4a(x, ww.w, a3);
+      }
+    unsigned o = 0;
+    o |= (unsigned)(uint8_t)clampi(RQ(a0 + bias.x, mult.x, shift.x) + D.out_zp, D.act_min, D.act_max);
+    o |= (unsigned)(uint8_t)clampi(RQ(a1 + bias.y, mult.y, shift.y) + D.out_zp, D.act_min, D.act_max) << 8;
+    o |= (unsigned)(uint8_t)clampi(RQ(a2 + bias.z, mult.z, shift.z) + D.out_zp, D.act_min, D.act_max) << 16;
+    o |= (unsigned)(uint8_t)clampi(RQ(a3 + bias.w, mult.w, shift.w) + D.out_zp, D.act_min, D.act_max) << 24;
+    ob[(oy * D.ow + ox) * CG] = o;
+    if (oy + 1 < oy1) {
+      const int iy = (oy + 1) * SH - D.pt;      // first input row of the next output row
+      if (SH == 1) {
+#pragma unroll
+        for (int fx = 0; fx < 3; fx++) { win[0][fx] = win[1][fx]; win[1][fx] = win[2][fx]; }
+        load_row(iy + 2, win[2]);
+      } else {
+#pragma unroll
+        for (int fx = 0; fx < 3; fx++) win[0][fx] = win[2][fx];
+        load_row(iy + 1, win[1]);
+        load_row(iy + 2, win[2]);
       }
     }
-    const int4 bias = *reinterpret_cast<const int4*>(prm + 4 * cg);
-    const int4 mult = *reinterpret_cast<const int4*>(prm + D.C + 4 * cg);
-    const int4 shift = *reinterpret_cast<const int4*>(prm + 2 * D.C + 4 * cg);
-    unsigned o = 0;
-    o |= (unsigned)(uint8_t)clampi(requant(acc[0] + bias.x, mult.x, shift.x, R) + D.out_zp, D.act_min, D.act_max);
-    o |= (unsigned)(uint8_t)clampi(requant(acc[1] + bias.y, mult.y, shift.y, R) + D.out_zp, D.act_min, D.act_max) << 8;
-    o |= (unsigned)(uint8_t)clampi(requant(acc[2] + bias.z, mult.z, shift.z, R) + D.out_zp, D.act_min, D.act_max) << 16;
-    o |= (unsigned)(uint8_t)clampi(requant(acc[3] + bias.w, mult.w, shift.w, R) + D.out_zp, D.act_min, D.act_max) << 24;
-    reinterpret_cast<unsigned*>(out)[it] = o;
   }
 }
 
 // ---- K5: pointwise conv = GEMM [M, K] x [N, K]^T with fused requant (+ residual ADD) --------------------------
 // x int8 [M][K] (NHWC rows), res int8 [M][N] or NULL, y int8 [M][N].  CTA = 128 rows, loops over N in chunks of 64
 // (N == 32 handled as one half-used chunk).
+template <bool FAST>
 __global__ void __launch_bounds__(256)
 k_pw(const int8_t* __restrict__ x, const int8_t* __restrict__ res, int8_t* __restrict__ y, long M, PwParams P, int R) {
   extern __shared__ __align__(16) int psm[];
@@ -822,7 +887,7 @@ k_pw(const int8_t* __restrict__ x, const int8_t* __restrict__ res, int8_t* __res
       unsigned o = 0;
 #pragma unroll
       for (int j = 0; j < 4; j++) {
-        int q = clampi(requant(acc[i][j] + bs[j], ms[j], ss[j], R) + P.out_zp, P.act_min, P.act_max);
+        int q = clampi(RQ(acc[i][j] + bs[j], ms[j], ss[j]) + P.out_zp, P.act_min, P.act_max);
         if (P.has_add) {
           const int r8 = (int)(int8_t)((rw >> (8 * j)) & 0xffu);
           const int s = luts[r8 + 128] + luts[256 + q + 128];
@@ -892,10 +957,12 @@ static int run_body(FastPlan& fp, int mode, const float* src, int Bw, float* d_s
   FastImpl* im = fp.impl;
   static bool attrs = false;
   if (!attrs) {
-    cudaFuncSetAttribute(k_head<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(k_head<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(k_pw, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(k_dw3x3, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(k_head<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_head<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_head<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_head<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_pw<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_pw<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attrs = true;
   }
   const int R = rounding;
@@ -904,8 +971,10 @@ static int run_body(FastPlan& fp, int mode, const float* src, int Bw, float* d_s
   {
     const int grid = Bw * (im->W / HEAD_M);
     if (prof) prof->begin("K2_head", st);
-    if (mode == 0) k_head<0><<<grid, 256, head_smem(im->head), st>>>(src, im->d_mnmx, head_out, im->head, im->ldk, R);
-    else k_head<1><<<grid, 256, head_smem(im->head), st>>>(src, nullptr, head_out, im->head, im->ldk, R);
+    const bool f = im->head.fast && R == 0;
+    const size_t sm = head_smem(im->head);
+    if (mode == 0) { if (f) k_head<0, true><<<grid, 256, sm, st>>>(src, im->d_mnmx, head_out, im->head, im->ldk, R); else k_head<0, false><<<grid, 256, sm, st>>>(src, im->d_mnmx, head_out, im->head, im->ldk, R); }
+    else { if (f) k_head<1, true><<<grid, 256, sm, st>>>(src, nullptr, head_out, im->head, im->ldk, R); else k_head<1, false><<<grid, 256, sm, st>>>(src, nullptr, head_out, im->head, im->ldk, R); }
     if (prof) prof->end(st);
     (*launches)++;
   }
@@ -916,7 +985,8 @@ static int run_body(FastPlan& fp, int mode, const float* src, int Bw, float* d_s
     dim3 grid((S.oh + STEM_ROWS - 1) / STEM_ROWS, Bw);
     const size_t smem = (size_t)(STEM_ROWS + 2) * (S.iw + 8) + 96 * 4;
     if (prof) prof->begin("K3_stem", st);
-    k_stem<<<grid, 256, smem, st>>>(head_out, stem_out, S, R);
+    if (S.fast && R == 0) k_stem<true><<<grid, 256, smem, st>>>(head_out, stem_out, S, R);
+    else k_stem<false><<<grid, 256, smem, st>>>(head_out, stem_out, S, R);
     if (prof) prof->end(st);
     (*launches)++;
   }
@@ -929,13 +999,14 @@ static int run_body(FastPlan& fp, int mode, const float* src, int Bw, float* d_s
     int8_t* bout = (int8_t*)im->slot_buf[bl.out_slot];
     {
       const DwParams& D = bl.dw;
-      const long items = (long)Bw * D.oh * D.ow * (D.C / 4);
-      long g = (items + 255) / 256;
-      if (g > 148L * 16) g = 148L * 16;
-      const size_t smem = (size_t)12 * D.C * 4;
+      const int ncol = D.ow * (D.C / 4);
+      const int rows_per_band = 8;
+      dim3 grid(((ncol + 255) / 256) * ((D.oh + rows_per_band - 1) / rows_per_band), Bw);
+      const bool f = D.fast && R == 0;
       snprintf(name, sizeof name, "K4_dw_%02d_c%d_s%d", bi, D.C, D.sh);
       if (prof) prof->begin(name, st);
-      k_dw3x3<<<(int)g, 256, smem, st>>>(bin, dwo, items, D, R);
+      if (D.sh == 1) { if (f) k_dw3x3<1, true><<<grid, 256, 0, st>>>(bin, dwo, D, rows_per_band, R); else k_dw3x3<1, false><<<grid, 256, 0, st>>>(bin, dwo, D, rows_per_band, R); }
+      else { if (f) k_dw3x3<2, true><<<grid, 256, 0, st>>>(bin, dwo, D, rows_per_band, R); else k_dw3x3<2, false><<<grid, 256, 0, st>>>(bin, dwo, D, rows_per_band, R); }
       if (prof) prof->end(st);
       (*launches)++;
     }
@@ -945,7 +1016,8 @@ static int run_body(FastPlan& fp, int mode, const float* src, int Bw, float* d_s
       const int grid = (int)((M + 127) / 128);
       snprintf(name, sizeof name, "K5_pw_%02d_k%d_n%d%s", bi, P.K, P.N, P.has_add ? "_add" : "");
       if (prof) prof->begin(name, st);
-      k_pw<<<grid, 256, pw_smem(P), st>>>(dwo, P.has_add ? bin : nullptr, bout, M, P, R);
+      if (P.fast && R == 0) k_pw<true><<<grid, 256, pw_smem(P), st>>>(dwo, P.has_add ? bin : nullptr, bout, M, P, R);
+      else k_pw<false><<<grid, 256, pw_smem(P), st>>>(dwo, P.has_add ? bin : nullptr, bout, M, P, R);
       if (prof) prof->end(st);
       (*launches)++;
     }

@@ -585,5 +585,13 @@ BNO_EXPORT void bno_logistic_lut(float in_scale, int in_zp, float out_scale, int
   }
 }
 
+/* The closed form the CUDA kernels use for a right shift n in [1,31] (bn_common.cuh: rq_fast); exported so a CPU test
+ * can prove it equal to the gemmlowp sequence above for all shifts. */
+BNO_EXPORT int32_t bno_rq_fast(int32_t acc, int32_t mult, int n) {
+  const int64_t p = (int64_t)acc * (int64_t)mult + ((int64_t)1 << 30);
+  const int32_t v = (int32_t)(p >> 31);
+  return (v + (1 << (n - 1)) + (v >> 31)) >> n;
+}
+
 /* expose the fixed-point primitives for unit tests */
 BNO_EXPORT int32_t bno_mbqm(int32_t x, int32_t qm, int shift, int rounding) { return mbqm(x, qm, shift, rounding); }

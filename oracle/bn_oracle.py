@@ -52,6 +52,8 @@ def lib():
         L.bno_logistic_lut.argtypes = [C.c_float, C.c_int, C.c_float, C.c_int, C.c_void_p]
         L.bno_mbqm.restype = C.c_int32
         L.bno_mbqm.argtypes = [C.c_int32, C.c_int32, C.c_int, C.c_int]
+        L.bno_rq_fast.restype = C.c_int32
+        L.bno_rq_fast.argtypes = [C.c_int32, C.c_int32, C.c_int]
         L.bno_last_error.restype = C.c_char_p
         _lib = L
     return _lib
@@ -166,3 +168,7 @@ def logistic_lut(in_scale, in_zp, out_scale, out_zp) -> np.ndarray:
 
 def mbqm(x: int, qm: int, shift: int, rounding: int = 0) -> int:
     return int(lib().bno_mbqm(int(x), int(qm), int(shift), int(rounding)))
+
+
+def rq_fast(x: int, qm: int, n: int) -> int:
+    return int(lib().bno_rq_fast(int(x), int(qm), int(n)))

@@ -218,3 +218,20 @@ def test_rounding_mode_and_mean_variant_are_switchable(blob, spec):
     double = bo.OracleModel(blob, rounding=0).run(spec, tap_id=83)[1]
     d = np.abs(single.astype(int) - double.astype(int))
     assert d.max() <= 1 and 0 < (d > 0).mean() < 0.01
+
+
+def test_gpu_closed_form_requant_equals_gemmlowp():
+    """rq_fast (the closed form the CUDA kernels use for right shifts) == SRDHM + RoundingDivideByPOT."""
+    from oracle import bn_oracle as bo
+
+    rng = np.random.default_rng(1)
+    edge = [0, 1, -1, 2, -2, 3, -3, (1 << 30), -(1 << 30), (1 << 31) - 1, -(1 << 31), 12345, -12345]
+    mults = [0, 1 << 30, (1 << 31) - 1, 1518500250, 1073741825]
+    for n in range(1, 32):
+        xs = edge + rng.integers(-(1 << 31), 1 << 31, 200).tolist() + rng.integers(-(1 << n), 1 << n, 100).tolist()
+        for m in mults + rng.integers(1 << 30, 1 << 31, 5).tolist():
+            for x in xs:
+                v = (x * m + (1 << 30)) >> 31
+                if abs(v) + (1 << (n - 1)) >= (1 << 31):
+                    continue    # outside the int32-safe domain; the engine proves |v| bounds per layer at plan build
+                assert bo.rq_fast(x, m, n) == bo.mbqm(x, m, -n, 0), (x, m, n)
