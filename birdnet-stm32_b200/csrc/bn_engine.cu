@@ -144,6 +144,7 @@ extern "C" int bn_create(const void* blob, size_t nbytes, int device, bn_engine*
   e->buf.assign(e->hdr->n_tensors, nullptr);
   e->last_ptr.assign(e->hdr->n_tensors, nullptr);
   fast_plan_build(e->fast, e->blob.data(), e->hdr, e->tensors, e->ops, e->d_blob);
+  { int sms = 148; if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) e->fast.num_sms = sms; }
   *out = e;
   return BN_OK;
 }
@@ -631,6 +632,8 @@ extern "C" int bn_set_option(bn_engine* e, int key, int value) {
       if (value < 1 || value > 65535) return set_err(BN_ERR_ARG, "wave must be in [1, 65535]");
       if (value != e->wave_opt) { cudaDeviceSynchronize(); free_workspace(e); }
       e->wave_opt = value; break;
+    case BN_OPT_TENSOR_CORE:
+      e->fast.use_tc = value ? 1 : 0; break;
     case BN_OPT_PROFILE:
       cudaDeviceSynchronize();
       e->prof.collect();

@@ -18,6 +18,7 @@
 #include <map>
 
 #include "bn_kernels.cuh"
+#include "bn_pw_tc.cuh"
 
 namespace bn {
 
@@ -118,6 +119,8 @@ struct Block {
   int in_slot, dw_slot, out_slot; // tensor slots
   DwParams dw;
   PwParams pw;
+  PwTcParams tc{};
+  bool tc_ok = false;
 };
 
 struct FastImpl {
@@ -476,6 +479,33 @@ static bool build_impl(FastPlan& fp) {
       }
       im->d_add_luts.push_back(d_lut);
       P.lut_res = d_lut; P.lut_conv = d_lut ? d_lut + 256 : nullptr;
+      // tensor-core variant (needs the proven fast-requant domain and right-shift-only ADD rescales)
+      bl.tc_ok = false;
+      if (pw_tc_supported(K, N) && P.fast) {
+        PwTcParams& Tc = bl.tc;
+        std::vector<uint8_t> img;
+        pw_tc_weight_image((const int8_t*)(fp.h_blob + pw.off[0]), K, N, img, &Tc.KP, &Tc.RW);
+        Tc.w_img = (const uint8_t*)upload(im, img.data(), img.size());
+        Tc.bias = P.bias; Tc.mult = P.mult; Tc.shift = P.shift;
+        Tc.K = K; Tc.N = N;
+        int l = 0; while ((16 << l) < K) l++;
+        Tc.cpr_log = l;
+        int tc_cols = 32; while (tc_cols < 2 * N) tc_cols <<= 1;
+        Tc.tmem_cols = tc_cols;
+        Tc.out_zp = P.out_zp; Tc.act_min = P.act_min; Tc.act_max = P.act_max;
+        Tc.has_add = P.has_add;
+        bool ok = true;
+        if (P.has_add) {
+          const int32_t* p = ops[bl.add_op].p;
+          Tc.add_in1_zp = p[BN_ADD_IN1_ZP]; Tc.add_in2_zp = p[BN_ADD_IN2_ZP]; Tc.add_out_zp = p[BN_ADD_OUT_ZP];
+          Tc.add_m1 = p[BN_ADD_M1]; Tc.add_n1 = -p[BN_ADD_S1]; Tc.add_m2 = p[BN_ADD_M2]; Tc.add_n2 = -p[BN_ADD_S2];
+          Tc.add_mo = p[BN_ADD_MO]; Tc.add_no = -p[BN_ADD_SO];
+          Tc.add_act_min = p[BN_ADD_ACT_MIN]; Tc.add_act_max = p[BN_ADD_ACT_MAX];
+          // closed forms need right shifts in [0, 30] and left_shift 20 (|x| <= 255 * 2^20 keeps every step in int32)
+          ok = p[BN_ADD_LEFT_SHIFT] == 20 && Tc.add_n1 >= 0 && Tc.add_n1 <= 30 && Tc.add_n2 >= 0 && Tc.add_n2 <= 30 && Tc.add_no >= 0 && Tc.add_no <= 30;
+        }
+        bl.tc_ok = ok && Tc.w_img != nullptr;
+      }
     }
   }
   {  // tail
@@ -1014,9 +1044,11 @@ static int run_body(FastPlan& fp, int mode, const float* src, int Bw, float* d_s
       const PwParams& P = bl.pw;
       const long M = (long)Bw * bl.dw.oh * bl.dw.ow;
       const int grid = (int)((M + 127) / 128);
-      snprintf(name, sizeof name, "K5_pw_%02d_k%d_n%d%s", bi, P.K, P.N, P.has_add ? "_add" : "");
+      const bool tc = fp.use_tc && bl.tc_ok && R == 0;
+      snprintf(name, sizeof name, "%s_%02d_k%d_n%d%s", tc ? "K5tc_pw" : "K5_pw", bi, P.K, P.N, P.has_add ? "_add" : "");
       if (prof) prof->begin(name, st);
-      if (P.fast && R == 0) k_pw<true><<<grid, 256, pw_smem(P), st>>>(dwo, P.has_add ? bin : nullptr, bout, M, P, R);
+      if (tc) launch_pw_tc(dwo, P.has_add ? bin : nullptr, bout, M, bl.tc, fp.num_sms, st);
+      else if (P.fast && R == 0) k_pw<true><<<grid, 256, pw_smem(P), st>>>(dwo, P.has_add ? bin : nullptr, bout, M, P, R);
       else k_pw<false><<<grid, 256, pw_smem(P), st>>>(dwo, P.has_add ? bin : nullptr, bout, M, P, R);
       if (prof) prof->end(st);
       (*launches)++;

@@ -49,6 +49,8 @@ struct FastPlan {
   const uint8_t* h_blob = nullptr;
   uint8_t* d_blob = nullptr;
   int wave = 0;
+  int use_tc = 1;              // pointwise convs on tcgen05 (BN_OPT_TENSOR_CORE)
+  int num_sms = 148;
   FastImpl* impl = nullptr;
   std::string why;             // why the pattern did not match (diagnostics)
 };

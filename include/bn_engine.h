@@ -59,7 +59,8 @@ enum {
   BN_OPT_MEAN_VARIANT = 2,  /* 0 auto, 1 float, 2 folded 1/N, 3 reference rounded divide    */
   BN_OPT_FORCE_GENERIC = 3, /* 1 = run one kernel per op and keep every tensor (debug taps)             */
   BN_OPT_WAVE = 4,          /* chunks processed per internal wave (workspace is sized for it)           */
-  BN_OPT_PROFILE = 5        /* 1 = time every kernel with CUDA events, 0 = off, 2 = on + reset counters  */
+  BN_OPT_PROFILE = 5,       /* 1 = time every kernel with CUDA events, 0 = off, 2 = on + reset counters  */
+  BN_OPT_TENSOR_CORE = 6    /* 1 (default) = pointwise convs on tcgen05.mma kind::i8, 0 = dp4a CUDA-core GEMM */
 };
 
 typedef struct bn_info {

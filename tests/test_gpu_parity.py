@@ -105,6 +105,24 @@ def test_full_path_same_codes_as_generic_plan(runner, pcm_batch):
     np.testing.assert_array_equal(fused, generic)
 
 
+def test_tensor_core_pointwise_equals_cuda_core_pointwise(runner, pcm_batch):
+    """tcgen05 kind::i8 GEMM + TMEM epilogue vs the dp4a GEMM: identical scores and block outputs."""
+    from birdnet_stm32 import _lib as L
+
+    pcm, peak = pcm_batch
+    tc = runner.predict_pcm16(pcm, peak)
+    taps_tc = [runner.dump_tensor(t, n * len(pcm)) for t, n in ((99, 32 * 64 * 32), (102, 32 * 64 * 32), (126, 4 * 8 * 256))]
+    runner.set_option(L.BN_OPT_TENSOR_CORE, 0)
+    try:
+        cc = runner.predict_pcm16(pcm, peak)
+        taps_cc = [runner.dump_tensor(t, n * len(pcm)) for t, n in ((99, 32 * 64 * 32), (102, 32 * 64 * 32), (126, 4 * 8 * 256))]
+    finally:
+        runner.set_option(L.BN_OPT_TENSOR_CORE, 1)
+    for a, b in zip(taps_tc, taps_cc):
+        assert np.array_equal(a, b), f"{(a != b).sum()} of {a.size} differ"
+    np.testing.assert_array_equal(tc, cc)
+
+
 def test_rounding_and_mean_variants_match_oracle(runner, blob, oracle_spec):
     from birdnet_stm32 import _lib as L
     from oracle import bn_oracle
