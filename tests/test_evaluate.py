@@ -1,0 +1,165 @@
+"""evaluate(): reference behaviour with a FakeRunner (tests/test_metrics.py:11-101 in the reference),
+the file-sharded wrapper under gloo (world_size 2), and -- on the GPU box -- the device path against the
+oracle path (top-1 and cmAP to 3 decimals)."""
+
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import PKG, ROOT
+
+
+class FakeRunner:
+    """Fixed predictions, like the reference tests' FakeRunner."""
+
+    def __init__(self, scores):
+        self.scores = np.asarray(scores, dtype=np.float32)
+        self._idx = 0
+
+    def predict(self, x_batch):
+        b = x_batch.shape[0]
+        out = np.tile(self.scores[self._idx % len(self.scores)], (b, 1))
+        self._idx += b
+        return out.astype(np.float32)
+
+
+def make_dataset(root, classes, n_per_class=3, sr=22050, seconds=(3.0, 7.4, 1.2)):
+    from birdnet_stm32.audio import io
+
+    files = []
+    for ci, cls in enumerate(classes):
+        os.makedirs(os.path.join(root, cls), exist_ok=True)
+        for i in range(n_per_class):
+            n = int(sr * seconds[i % len(seconds)])
+            rng = np.random.default_rng(100 * ci + i)
+            t = np.arange(n) / sr
+            audio = 0.4 * np.sin(2 * np.pi * (500 + 700 * ci) * t) + 0.1 * rng.standard_normal(n)
+            path = os.path.join(root, cls, f"sample_{i}.wav")
+            io.save_wav(audio.astype(np.float32), path, sr)
+            files.append(path)
+    return files
+
+
+RAW_CFG = {"sample_rate": 22050, "chunk_duration": 3, "num_mels": 64, "spec_width": 256, "fft_length": 512,
+           "audio_frontend": "raw", "mag_scale": "none"}
+
+
+def test_fake_runner_metrics_keys_and_shapes(tmp_path):
+    from birdnet_stm32.evaluation.metrics import evaluate
+
+    classes = ["bird_a", "bird_b"]
+    files = make_dataset(str(tmp_path), classes)
+    os.makedirs(tmp_path / "unknown_label")
+    metrics, per_file, y_true, y_scores = evaluate(FakeRunner([[0.95, 0.05], [0.05, 0.95]]), files, classes, RAW_CFG,
+                                                   pooling="avg", batch_size=64, measure_latency=True, profile_memory=True)
+    for key in ("roc-auc", "f1", "precision", "recall", "cmAP", "mAP", "ap_per_class", "latency_mean_ms", "latency_p99_ms",
+                "total_chunks", "peak_rss_mb"):
+        assert key in metrics, key
+    assert len(per_file) == len(files) and y_true.shape == (len(files), 2) and y_scores.shape == (len(files), 2)
+    assert y_true.dtype == np.float32 and y_scores.dtype == np.float32
+    assert metrics["total_chunks"] == 2 * (1 + 3 + 1)        # 3 s -> 1 chunk, 7.4 s -> 2 + tail, 1.2 s -> 1 padded
+    assert metrics["f1"] > 0.0
+
+
+def test_no_valid_files_raises():
+    from birdnet_stm32.evaluation.metrics import evaluate
+
+    with pytest.raises(RuntimeError, match="No valid test samples"):
+        evaluate(FakeRunner([[0.5, 0.5]]), [], ["a", "b"], RAW_CFG, pooling="avg")
+
+
+def test_hybrid_without_gpu_frontend_is_an_error_not_a_cpu_fallback(tmp_path):
+    from birdnet_stm32.evaluation.metrics import evaluate
+
+    files = make_dataset(str(tmp_path), ["a"], n_per_class=1)
+    cfg = dict(RAW_CFG, audio_frontend="hybrid")
+    with pytest.raises(RuntimeError, match="no CPU spectrogram"):
+        evaluate(FakeRunner([[0.5]]), files, ["a"], cfg)
+
+
+def test_shard_files_partitions_whole_files():
+    from birdnet_stm32.evaluation.sharded import shard_files
+
+    files = [f"f{i}" for i in range(11)]
+    weights = [20, 1, 1, 7, 3, 3, 12, 1, 5, 9, 2]
+    for world in (1, 2, 4, 8):
+        parts = [shard_files(files, world, r, weights) for r in range(world)]
+        assert sorted(sum(parts, [])) == sorted(files)
+        loads = [sum(weights[files.index(f)] for f in p) for p in parts]
+        assert max(loads) - min(loads) <= max(weights)
+    assert shard_files(files, 2, 1) == files[1::2]
+
+
+_WORKER = r"""
+import os, sys, json
+sys.path.insert(0, {root!r}); sys.path.insert(0, {pkg!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import numpy as np, torch.distributed as dist
+from test_evaluate import FakeRunner, RAW_CFG
+from birdnet_stm32.evaluation.sharded import evaluate_sharded
+dist.init_process_group("gloo")
+files = sorted(json.load(open({files!r})))
+classes = ["bird_a", "bird_b", "bird_c"]
+class ByLabel(FakeRunner):
+    pass
+m, per_file, yt, ys = evaluate_sharded(FakeRunner([[0.9, 0.2, 0.1]]), files, classes, RAW_CFG, pooling="lme")
+if dist.get_rank() == 0:
+    json.dump({{"n": int(yt.shape[0]), "labels": yt.argmax(1).tolist(), "cmAP": m["cmAP"], "local": len(per_file)}}, open({out!r}, "w"))
+dist.destroy_process_group()
+"""
+
+
+def test_sharded_evaluate_gloo_world2(tmp_path):
+    import json
+
+    classes = ["bird_a", "bird_b", "bird_c"]
+    files = make_dataset(str(tmp_path / "data"), classes, n_per_class=3)
+    flist, out, script = str(tmp_path / "files.json"), str(tmp_path / "out.json"), str(tmp_path / "worker.py")
+    json.dump(files, open(flist, "w"))
+    open(script, "w").write(_WORKER.format(root=ROOT, pkg=PKG, files=flist, out=out))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29531", script], capture_output=True, text=True, env=env, timeout=240)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    got = json.load(open(out))
+    assert got["n"] == len(files) and got["local"] < len(files)
+    assert sorted(got["labels"]) == sorted([0] * 3 + [1] * 3 + [2] * 3)
+
+
+@pytest.mark.gpu
+def test_gpu_evaluate_matches_oracle_path(tmp_path, blob, cfg, oracle_model):
+    """Device path (PCM16 batched across files, pooled on the GPU) vs the oracle path on the same files:
+    top-1 per file identical, cmAP / ROC-AUC equal to 3 decimals (BASELINE.md parity bar)."""
+    from birdnet_stm32.audio import io
+    from birdnet_stm32.evaluation.gpu_runner import GpuRunner
+    from birdnet_stm32.evaluation.metrics import _metrics_from_scores, evaluate
+    from oracle import bn_oracle
+
+    classes = cfg["class_names"]
+    files = make_dataset(str(tmp_path), classes[:6], n_per_class=3, sr=22050)
+    runner = GpuRunner(blob, cfg)
+    try:
+        metrics, per_file, y_true, y_scores = evaluate(runner, files, classes, cfg, pooling="lme", device_batch_chunks=7)
+        ref_scores = []
+        for path in files:
+            pcm, peak = io.load_pcm16_chunks(path, 22050, 3.0)
+            spec = bn_oracle.frontend_hybrid(pcm, np.full(len(pcm), peak, np.float32), 512, 66150 // 256, 256)
+            ref_scores.append(bn_oracle.pool_scores(oracle_model.predict(spec), "lme", 10.0))
+        ref_scores = np.asarray(ref_scores, dtype=np.float32)
+        assert y_scores.shape == ref_scores.shape == (len(files), 100)
+        np.testing.assert_array_equal(y_scores.argmax(1), ref_scores.argmax(1))
+        assert np.abs(y_scores - ref_scores).max() <= 1 / 256 + 1e-5
+        ref_m = _metrics_from_scores(y_true, ref_scores)
+        assert round(metrics["cmAP"], 3) == round(ref_m["cmAP"], 3)
+        assert round(metrics["roc-auc"], 3) == round(ref_m["roc-auc"], 3)
+        # protocol path (per-file predict() calls on GPU spectrograms + host pooling) agrees with the device path
+        class ProtocolOnly:
+            predict = staticmethod(runner.predict)
+            frontend = staticmethod(runner.frontend)
+
+        _, _, _, ys2 = evaluate(ProtocolOnly(), files, classes, cfg, pooling="lme", batch_size=2)
+        np.testing.assert_allclose(ys2, y_scores, rtol=0, atol=3e-6)
+    finally:
+        runner.close()
