@@ -42,7 +42,7 @@ struct bn_engine {
   const bn_blob_op* ops = nullptr;
   // workspace
   int wave = 0;                       // chunks the workspace is sized for
-  int wave_opt = 256;                 // requested wave size
+  int wave_opt = 2048;                 // requested wave size
   std::vector<void*> buf;             // per tensor slot: device buffer for one wave (const -> into d_blob)
   std::vector<void*> last_ptr;        // pointers used by the last wave (taps)
   size_t workspace_bytes = 0;

@@ -610,6 +610,9 @@ int fast_dump_tensor(FastPlan& fp, int tfl_tensor_id, int Bw, void* out, size_t 
 // =================================================================================================
 // device code
 // =================================================================================================
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ int requant(int acc, int mult, int shift, int R) { return mbqm(acc, mult, shift, R); }
 #define RQ(acc, mult, shift) requant_t<FAST>(acc, mult, shift, R)
 
@@ -652,39 +655,67 @@ k_head(const float* __restrict__ src, const unsigned* __restrict__ mnmx, int8_t*
   const int b = blockIdx.x / halves;
   const int t0 = (blockIdx.x % halves) * HEAD_M;
 
-  for (int i = tid; i < H.KW * HEAD_N; i += 256) Wt[i] = __ldg(H.wt + i);
-  for (int i = tid; i < HEAD_N * 256 / 4; i += 256) reinterpret_cast<int*>(lut)[i] = __ldg(reinterpret_cast<const int*>(H.lut) + i);
+  // weights and the folded PWL table arrive asynchronously (cp.async) while the tile is being quantised
+  for (int i = tid; i < H.KW * HEAD_N / 4; i += 256) cp_async_16(Wt + 4 * i, H.wt + 4 * i);
+  for (int i = tid; i < HEAD_N * 256 / 16; i += 256) cp_async_16(lut + 16 * i, H.lut + 16 * i);
+  asm volatile("cp.async.commit_group;" ::: "memory");
   if (tid < HEAD_N) { prm[tid] = __ldg(H.bias + tid); prm[64 + tid] = __ldg(H.mult + tid); prm[128 + tid] = __ldg(H.shift + tid); }
 
   const unsigned fillw = 0x01010101u * (unsigned)(uint8_t)H.fill;
   if (MODE == 0) {
     const float mn = __uint_as_float(mnmx[2 * b]), mx = __uint_as_float(mnmx[2 * b + 1]);
     const float den = (float)((double)(mx - mn) + 1e-10);       // normalize(): numpy 1.26 scalar promotion
+    const float qmul = (float)(1.0 / ((double)den * (double)H.q_scale));
     const float4* s4 = reinterpret_cast<const float4*>(src + ((long)b * H.W + t0) * ldk);
     const int row_w = ldk / 4;                                  // float4 per frame row (== KW)
-    for (int i = tid; i < HEAD_M * row_w; i += 256) {
-      const int row = i / row_w, c4 = i - row * row_w;
-      const int k = 4 * c4;
-      unsigned word = fillw;
-      if (k < H.K_real) {
-        const float4 v = s4[i];
-        const float f[4] = {v.x, v.y, v.z, v.w};
-        word = 0;
+    const int total4 = HEAD_M * row_w;
+    for (int base = 0; base < total4; base += 256 * 8) {
+      float4 vv[8];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          int q;
-          if (k + j < H.K_real) {
-            const float nrm = __fdiv_rn(f[j] - mn, den);
-            q = clampi((int)roundf(__fdiv_rn(nrm, H.q_scale)) + H.q_zp, -128, 127);
-          } else q = H.fill;
-          word |= (unsigned)(uint8_t)q << (8 * j);
+      for (int u = 0; u < 8; u++) {            // 8 independent 16-byte loads in flight per thread
+        const int i = base + u * 256 + tid;
+        vv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < total4) {
+          const int row = i / row_w, c4 = i - row * row_w;
+          if (4 * c4 < H.K_real) vv[u] = s4[i];
         }
       }
-      At[c4 * GEMM_LDA + row] = (int)word;
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int i = base + u * 256 + tid;
+        if (i >= total4) continue;
+        const int row = i / row_w, c4 = i - row * row_w;
+        const int k = 4 * c4;
+        unsigned word = fillw;
+        if (k < H.K_real) {
+          const float f[4] = {vv[u].x, vv[u].y, vv[u].z, vv[u].w};
+          word = 0;
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            int q;
+            if (k + j < H.K_real) {
+              // round((S - mn) / den / scale): one multiply by the reciprocal decides every element whose value is
+              // not within 2e-3 of a rounding tie (the two-division chain and the product agree to < 1e-4 there);
+              // the rare near-tie elements take the exact IEEE chain of the reference.
+              const float d = f[j] - mn;
+              const float t = d * qmul;
+              const float fl = floorf(t);
+              const float fr = t - fl;
+              int qi;
+              if (fabsf(fr - 0.5f) < 2e-3f) qi = (int)roundf(__fdiv_rn(__fdiv_rn(d, den), H.q_scale));
+              else qi = (int)fl + (fr > 0.5f ? 1 : 0);
+              q = clampi(qi + H.q_zp, -128, 127);
+            } else q = H.fill;
+            word |= (unsigned)(uint8_t)q << (8 * j);
+          }
+        }
+        At[c4 * GEMM_LDA + row] = (int)word;
+      }
     }
   } else {
     // bin-major normalised input: element (k, t) at src[b][k][t]
     const float* sb = src + (long)b * H.K_real * H.W + t0;
+    const float qmul1 = (float)(1.0 / (double)H.q_scale);
     for (int i = tid; i < HEAD_M * H.KW; i += 256) {
       const int c4 = i / HEAD_M, row = i - c4 * HEAD_M;         // lanes along frames: coalesced per k
       unsigned word = 0;
@@ -692,12 +723,22 @@ k_head(const float* __restrict__ src, const unsigned* __restrict__ mnmx, int8_t*
       for (int j = 0; j < 4; j++) {
         const int k = 4 * c4 + j;
         int q = H.fill;
-        if (k < H.K_real) q = clampi((int)roundf(__fdiv_rn(sb[(long)k * H.W + row], H.q_scale)) + H.q_zp, -128, 127);
+        if (k < H.K_real) {
+          const float xv = sb[(long)k * H.W + row];
+          const float t = xv * qmul1;
+          const float fl = floorf(t);
+          const float fr = t - fl;
+          int qi;
+          if (fabsf(fr - 0.5f) < 2e-3f || !(xv >= 0.0f)) qi = (int)roundf(__fdiv_rn(xv, H.q_scale));
+          else qi = (int)fl + (fr > 0.5f ? 1 : 0);
+          q = clampi(qi + H.q_zp, -128, 127);
+        }
         word |= (unsigned)(uint8_t)q << (8 * j);
       }
       At[c4 * GEMM_LDA + row] = (int)word;
     }
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
   const int tn = tid & 15, tm = tid >> 4;
@@ -784,19 +825,24 @@ k_stem(const int8_t* __restrict__ in, int8_t* __restrict__ out, StemParams S, in
 }
 
 // ---- K4: depthwise 3x3 ----------------------------------------------------------------------------------
-// in int8 [B][ih][iw][C], out int8 [B][oh][ow][C].  Thread = one output column (ox) x 4 channels; it walks down a
-// band of output rows with a 3x3 register window (3 or 6 new input words per output row), the 36 masked weight
-// words and the 12 requantisation parameters stay in registers.  Out-of-range taps read the zero point (SAME pad).
+// in int8 [B][ih][iw][C], out int8 [B][oh][ow][C].  Thread = two adjacent output columns x 4 channels; it walks
+// down a band of output rows with a 3 x (3+SH) register window.  The input words of the next output row are
+// requested before the current row is computed (software prefetch), the 36 masked weight words and the 12
+// requantisation parameters stay in registers.  Out-of-range taps read the zero point (SAME padding).
+constexpr int DW_THREADS = 128;
 template <int SH, bool FAST>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(DW_THREADS)
 k_dw3x3(const int8_t* __restrict__ in, int8_t* __restrict__ out, DwParams D, int rows_per_band, int R) {
+  constexpr int NW = 3 + SH;                      // input words per row feeding two adjacent outputs
   const int CG = D.C >> 2;
-  const int ncol = D.ow * CG;
-  const int col_blocks = (ncol + 255) >> 8;
+  const int npair = ((D.ow + 1) >> 1) * CG;
+  const int col_blocks = (npair + DW_THREADS - 1) / DW_THREADS;
   const int cb = blockIdx.x % col_blocks, band = blockIdx.x / col_blocks;
-  const int idx = cb * 256 + threadIdx.x;
-  if (idx >= ncol) return;
-  const int ox = idx / CG, cg = idx - ox * CG;
+  const int idx = cb * DW_THREADS + threadIdx.x;
+  if (idx >= npair) return;
+  const int px = idx / CG, cg = idx - px * CG;
+  const int ox0 = 2 * px;
+  const bool has1 = ox0 + 1 < D.ow;
   const int b = blockIdx.y;
   int4 w[9];
 #pragma unroll
@@ -807,22 +853,30 @@ k_dw3x3(const int8_t* __restrict__ in, int8_t* __restrict__ out, DwParams D, int
   const unsigned zpw = 0x01010101u * (unsigned)(uint8_t)D.in_zp;
   const unsigned* ib = reinterpret_cast<const unsigned*>(in + (size_t)b * D.ih * D.iw * D.C) + cg;
   unsigned* ob = reinterpret_cast<unsigned*>(out + (size_t)b * D.oh * D.ow * D.C) + cg;
-  int xoff[3];
-  bool xok[3];
+  int xoff[NW];
+  bool xok[NW];
 #pragma unroll
-  for (int fx = 0; fx < 3; fx++) {
-    const int ix = ox * SH - D.pl + fx;
-    xok[fx] = ix >= 0 && ix < D.iw;
-    xoff[fx] = ix * CG;
+  for (int c = 0; c < NW; c++) {
+    const int ix = ox0 * SH - D.pl + c;
+    xok[c] = ix >= 0 && ix < D.iw;
+    xoff[c] = ix * CG;
   }
   const int oy0 = band * rows_per_band;
   const int oy1 = min(oy0 + rows_per_band, D.oh);
-  unsigned win[3][3];
-  auto load_row = [&](int iy, unsigned (&dst)[3]) {
+  unsigned win[3][NW];
+  auto load_row = [&](int iy, unsigned (&dst)[NW]) {
     const bool yok = iy >= 0 && iy < D.ih;
     const unsigned* rp = ib + iy * D.iw * CG;
 #pragma unroll
-    for (int fx = 0; fx < 3; fx++) dst[fx] = (yok && xok[fx]) ? __ldg(rp + xoff[fx]) : zpw;
+    for (int c = 0; c < NW; c++) dst[c] = (yok && xok[c]) ? __ldg(rp + xoff[c]) : zpw;
+  };
+  auto finish = [&](int a0, int a1, int a2, int a3) -> unsigned {
+    unsigned o = 0;
+    o |= (unsigned)(uint8_t)clampi(RQ(a0 + bias.x, mult.x, shift.x) + D.out_zp, D.act_min, D.act_max);
+    o |= (unsigned)(uint8_t)clampi(RQ(a1 + bias.y, mult.y, shift.y) + D.out_zp, D.act_min, D.act_max) << 8;
+    o |= (unsigned)(uint8_t)clampi(RQ(a2 + bias.z, mult.z, shift.z) + D.out_zp, D.act_min, D.act_max) << 16;
+    o |= (unsigned)(uint8_t)clampi(RQ(a3 + bias.w, mult.w, shift.w) + D.out_zp, D.act_min, D.act_max) << 24;
+    return o;
   };
   {
     const int iy = oy0 * SH - D.pt;
@@ -831,35 +885,32 @@ k_dw3x3(const int8_t* __restrict__ in, int8_t* __restrict__ out, DwParams D, int
     load_row(iy + 2, win[2]);
   }
   for (int oy = oy0; oy < oy1; oy++) {
-    int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    // prefetch the SH new input rows of the next output row
+    unsigned nxt[SH][NW];
+    const bool more = oy + 1 < oy1;
+    if (more) {
+      const int iy = (oy + 1) * SH - D.pt;
+#pragma unroll
+      for (int r = 0; r < SH; r++) load_row(iy + 3 - SH + r, nxt[r]);
+    }
+    int a0 = 0, a1 = 0, a2 = 0, a3 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
 #pragma unroll
     for (int fy = 0; fy < 3; fy++)
 #pragma unroll
       for (int fx = 0; fx < 3; fx++) {
-        const int x = (int)win[fy][fx];
         const int4 ww = w[fy * 3 + fx];
-        a0 = __dp4a(x, ww.x, a0);
-        a1 = __dp4a(x, ww.y, a1);
-        a2 = __dp4a(x, ww.z, a2);
-        a3 = __dp4a(x, ww.w, a3);
+        const int xa = (int)win[fy][fx], xb = (int)win[fy][fx + SH];
+        a0 = __dp4a(xa, ww.x, a0); a1 = __dp4a(xa, ww.y, a1); a2 = __dp4a(xa, ww.z, a2); a3 = __dp4a(xa, ww.w, a3);
+        b0 = __dp4a(xb, ww.x, b0); b1 = __dp4a(xb, ww.y, b1); b2 = __dp4a(xb, ww.z, b2); b3 = __dp4a(xb, ww.w, b3);
       }
-    unsigned o = 0;
-    o |= (unsigned)(uint8_t)clampi(RQ(a0 + bias.x, mult.x, shift.x) + D.out_zp, D.act_min, D.act_max);
-    o |= (unsigned)(uint8_t)clampi(RQ(a1 + bias.y, mult.y, shift.y) + D.out_zp, D.act_min, D.act_max) << 8;
-    o |= (unsigned)(uint8_t)clampi(RQ(a2 + bias.z, mult.z, shift.z) + D.out_zp, D.act_min, D.act_max) << 16;
-    o |= (unsigned)(uint8_t)clampi(RQ(a3 + bias.w, mult.w, shift.w) + D.out_zp, D.act_min, D.act_max) << 24;
-    ob[(oy * D.ow + ox) * CG] = o;
-    if (oy + 1 < oy1) {
-      const int iy = (oy + 1) * SH - D.pt;      // first input row of the next output row
-      if (SH == 1) {
+    unsigned* orow = ob + (oy * D.ow + ox0) * CG;
+    orow[0] = finish(a0, a1, a2, a3);
+    if (has1) orow[CG] = finish(b0, b1, b2, b3);
+    if (more) {
 #pragma unroll
-        for (int fx = 0; fx < 3; fx++) { win[0][fx] = win[1][fx]; win[1][fx] = win[2][fx]; }
-        load_row(iy + 2, win[2]);
-      } else {
-#pragma unroll
-        for (int fx = 0; fx < 3; fx++) win[0][fx] = win[2][fx];
-        load_row(iy + 1, win[1]);
-        load_row(iy + 2, win[2]);
+      for (int c = 0; c < NW; c++) {
+        if (SH == 1) { win[0][c] = win[1][c]; win[1][c] = win[2][c]; win[2][c] = nxt[0][c]; }
+        else { win[0][c] = win[2][c]; win[1][c] = nxt[0][c]; win[2][c] = nxt[1][c]; }
       }
     }
   }
@@ -1029,14 +1080,14 @@ static int run_body(FastPlan& fp, int mode, const float* src, int Bw, float* d_s
     int8_t* bout = (int8_t*)im->slot_buf[bl.out_slot];
     {
       const DwParams& D = bl.dw;
-      const int ncol = D.ow * (D.C / 4);
+      const int npair = ((D.ow + 1) / 2) * (D.C / 4);
       const int rows_per_band = 8;
-      dim3 grid(((ncol + 255) / 256) * ((D.oh + rows_per_band - 1) / rows_per_band), Bw);
+      dim3 grid(((npair + DW_THREADS - 1) / DW_THREADS) * ((D.oh + rows_per_band - 1) / rows_per_band), Bw);
       const bool f = D.fast && R == 0;
       snprintf(name, sizeof name, "K4_dw_%02d_c%d_s%d", bi, D.C, D.sh);
       if (prof) prof->begin(name, st);
-      if (D.sh == 1) { if (f) k_dw3x3<1, true><<<grid, 256, 0, st>>>(bin, dwo, D, rows_per_band, R); else k_dw3x3<1, false><<<grid, 256, 0, st>>>(bin, dwo, D, rows_per_band, R); }
-      else { if (f) k_dw3x3<2, true><<<grid, 256, 0, st>>>(bin, dwo, D, rows_per_band, R); else k_dw3x3<2, false><<<grid, 256, 0, st>>>(bin, dwo, D, rows_per_band, R); }
+      if (D.sh == 1) { if (f) k_dw3x3<1, true><<<grid, DW_THREADS, 0, st>>>(bin, dwo, D, rows_per_band, R); else k_dw3x3<1, false><<<grid, DW_THREADS, 0, st>>>(bin, dwo, D, rows_per_band, R); }
+      else { if (f) k_dw3x3<2, true><<<grid, DW_THREADS, 0, st>>>(bin, dwo, D, rows_per_band, R); else k_dw3x3<2, false><<<grid, DW_THREADS, 0, st>>>(bin, dwo, D, rows_per_band, R); }
       if (prof) prof->end(st);
       (*launches)++;
     }

@@ -14,6 +14,8 @@
 // max (needed by normalize()) are reduced per CTA and merged with integer atomics
 // (magnitudes are >= +0, so their IEEE bit patterns order like unsigned integers).
 #include "bn_common.cuh"
+#include <cmath>
+
 #include "bn_kernels.cuh"
 
 namespace bn {
@@ -24,6 +26,13 @@ constexpr int BINS = 257;
 constexpr int FRAMES_PER_CTA = 32;
 constexpr int FE_THREADS = 256;  // 8 warps = 16 half-warps = 16 concurrent FFTs, 2 rounds
 constexpr int TILE_LD = FRAMES_PER_CTA + 1;
+
+// sqrt.approx.f32: max relative error 2^-23, far inside the 1e-4 frontend tolerance
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -70,7 +79,7 @@ __device__ __forceinline__ void fft16(float2 (&v)[16]) {
 template <bool FRAME_MAJOR>
 __global__ void __launch_bounds__(FE_THREADS)
 k_stft_mag(const int16_t* __restrict__ pcm, const float* __restrict__ peak, float* __restrict__ out,
-           unsigned* __restrict__ mnmx, int T, int hop, int W, int ldk) {
+           unsigned* __restrict__ mnmx, const float4* __restrict__ tables, int T, int hop, int W, int ldk) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int span = (FRAMES_PER_CTA - 1) * hop + NFFT;
   float2* tw512 = reinterpret_cast<float2*>(smem_raw);
@@ -84,13 +93,8 @@ k_stft_mag(const int16_t* __restrict__ pcm, const float* __restrict__ peak, floa
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * FRAMES_PER_CTA;
 
-  // tables
-  for (int m = tid; m < NFFT; m += FE_THREADS) {
-    float s, c;
-    sincospif(-(float)m / 256.0f, &s, &c);   // exp(-2 pi i m/512) = cos(pi m/256) - i sin(pi m/256)
-    tw512[m] = make_float2(c, s);
-    win[m] = 0.5f - 0.5f * cospif((float)m / 256.0f);   // periodic Hann: 0.5 - 0.5 cos(2 pi m / 512)
-  }
+  // tables (computed once on the host in double precision): tw512[512] float2 followed by win[512] float
+  for (int m = tid; m < (NFFT * 2 + NFFT) / 4; m += FE_THREADS) reinterpret_cast<float4*>(smem_raw)[m] = __ldg(tables + m);
 
   // stage samples [s0, s0 + span) of chunk b, zero outside [0, T)
   const float pk = peak ? peak[b] : 0.0f;
@@ -103,24 +107,39 @@ k_stft_mag(const int16_t* __restrict__ pcm, const float* __restrict__ peak, floa
     const unsigned* p32 = reinterpret_cast<const unsigned*>(pcm);
     const long total = (long)gridDim.y * T;             // samples in the whole buffer
     const int npairs = (int)(((g_lo + span + 1) - g_first + 1) / 2);
-    for (int w = tid; w < npairs; w += FE_THREADS) {
-      const long g = g_first + 2L * w;
-      unsigned word = 0;
-      if (g >= 0 && g + 1 < total) word = __ldg(p32 + (g >> 1));
-      else if (g >= 0 && g < total) word = (unsigned)(unsigned short)pcm[g];
+    // batches of 8 independent 32-bit loads per thread (memory-level parallelism), then decode
+    for (int base = 0; base < npairs; base += FE_THREADS * 8) {
+      unsigned wv[8];
 #pragma unroll
-      for (int h = 0; h < 2; h++) {
-        const long gs = g + h;
-        const long rel = gs - chunk_base;               // chunk-relative sample index
-        const long li = gs - g_lo;                      // index into xs
-        if (li >= 0 && li < span) {
-          float v = 0.0f;
-          if (rel >= 0 && rel < T) {
-            const short sv = (short)(h ? (word >> 16) : (word & 0xffffu));
-            v = (float)sv * (1.0f / 32768.0f);          // exact (power of two)
-            if (pk > 0.0f) v = __fdiv_rn(v, pk);        // y / peak, float32 (audio/io.py:124-126)
+      for (int u = 0; u < 8; u++) {
+        const int w = base + u * FE_THREADS + tid;
+        const long g = g_first + 2L * w;
+        unsigned word = 0;
+        if (w < npairs) {
+          if (g >= 0 && g + 1 < total) word = __ldg(p32 + (g >> 1));
+          else if (g >= 0 && g < total) word = (unsigned)(unsigned short)pcm[g];
+        }
+        wv[u] = word;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int w = base + u * FE_THREADS + tid;
+        if (w >= npairs) continue;
+        const long g = g_first + 2L * w;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const long gs = g + h;
+          const long rel = gs - chunk_base;               // chunk-relative sample index
+          const long li = gs - g_lo;                      // index into xs
+          if (li >= 0 && li < span) {
+            float v = 0.0f;
+            if (rel >= 0 && rel < T) {
+              const short sv = (short)(h ? (wv[u] >> 16) : (wv[u] & 0xffffu));
+              v = (float)sv * (1.0f / 32768.0f);          // exact (power of two)
+              if (pk > 0.0f) v = __fdiv_rn(v, pk);        // y / peak, float32 (audio/io.py:124-126)
+            }
+            xs[li] = v;
           }
-          xs[li] = v;
         }
       }
     }
@@ -164,25 +183,32 @@ k_stft_mag(const int16_t* __restrict__ pcm, const float* __restrict__ peak, floa
 #pragma unroll
     for (int k2 = 0; k2 < 16; k2++) zb[l + 16 * k2] = v[k2];   // natural order Z[0..255]
     __syncwarp(hmask);
-    // real-FFT split: X[k] = (Z[k] + conj(Z[N-k]))/2 - i/2 * W512^k * (Z[k] - conj(Z[N-k]))
-#pragma unroll
-    for (int j = 0; j <= 16; j++) {
-      const int k = l + 16 * j;
-      if (k <= NC) {
-        const float2 zk = zb[k & 255];
-        const float2 zn = zb[(NC - k) & 255];
-        const float2 e = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));      // even part
-        const float2 o = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));     // odd part = (Zk - conj Zn)/(2i)
-        const float2 ow = cmul(o, tw512[k]);
-        const float re = e.x + ow.x, im = e.y + ow.y;
-        const float mag = sqrtf(re * re + im * im);
-        if (t0 + f < W) {
-          if (FRAME_MAJOR) out[((long)b * W + t0 + f) * ldk + k] = mag;   // 16 lanes -> 64 contiguous bytes
-          else tile[k * TILE_LD + f] = mag;
-          lmin = fminf(lmin, mag);
-          lmax = fmaxf(lmax, mag);
-        }
+    // real-FFT split, two bins per step: with E = (Z[k] + conj(Z[N-k]))/2, O = (Z[k] - conj(Z[N-k]))/(2i) and
+    // T = W512^k O:   X[k] = E + T   and   X[N-k] = conj(E - T)   (N = 256), so |X[N-k]| = |E - T|.
+    const bool fok = t0 + f < W;
+    auto emit = [&](int k, float mag) {
+      if (fok) {
+        if (FRAME_MAJOR) out[((long)b * W + t0 + f) * ldk + k] = mag;   // 16 lanes -> 64 contiguous bytes
+        else tile[k * TILE_LD + f] = mag;
+        lmin = fminf(lmin, mag);
+        lmax = fmaxf(lmax, mag);
       }
+    };
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const int k = l + 16 * j;                       // 0..127, partner bin 256 - k
+      const float2 zk = zb[k];
+      const float2 zn = zb[(NC - k) & 255];
+      const float2 e = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+      const float2 o = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
+      const float2 t = cmul(o, tw512[k]);
+      const float ar = e.x + t.x, ai = e.y + t.y, br = e.x - t.x, bi = e.y - t.y;
+      emit(k, fast_sqrt(ar * ar + ai * ai));
+      emit(NC - k, fast_sqrt(br * br + bi * bi));
+    }
+    if (l == 0) {                                     // bin 128 pairs with itself: |X[128]| = |Z[128]|
+      const float2 z = zb[128];
+      emit(128, fast_sqrt(z.x * z.x + z.y * z.y));
     }
     __syncwarp(hmask);
   }
@@ -216,6 +242,26 @@ __global__ void k_init_minmax(unsigned* mnmx, int B) {
   if (i < B) { mnmx[2 * i] = 0x7f800000u; mnmx[2 * i + 1] = 0u; }
 }
 
+// tw512[m] = exp(-2 pi i m / 512) (float2) followed by the periodic Hann window win[m] = 0.5 - 0.5 cos(2 pi m / 512)
+static const float4* stft_tables() {
+  static float4* d_tab = nullptr;
+  static int dev_of = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (d_tab && dev_of == dev) return d_tab;
+  float h[NFFT * 3];
+  const double PI = 3.14159265358979323846;
+  for (int m = 0; m < NFFT; m++) {
+    h[2 * m] = (float)cos(2.0 * PI * m / NFFT);
+    h[2 * m + 1] = (float)(-sin(2.0 * PI * m / NFFT));
+    h[2 * NFFT + m] = (float)(0.5 - 0.5 * cos(2.0 * PI * m / NFFT));
+  }
+  if (cudaMalloc(&d_tab, sizeof h) != cudaSuccess) return nullptr;
+  cudaMemcpy(d_tab, h, sizeof h, cudaMemcpyHostToDevice);
+  dev_of = dev;
+  return d_tab;
+}
+
 size_t stft_smem_bytes(int hop, bool frame_major) {
   const int span = (FRAMES_PER_CTA - 1) * hop + NFFT;
   size_t b = sizeof(float2) * NFFT + sizeof(float) * NFFT + sizeof(float) * ((span + 3) & ~3);
@@ -235,9 +281,11 @@ int launch_stft_mag(const int16_t* pcm, const float* peak, float* out, unsigned*
     cudaFuncSetAttribute(k_stft_mag<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_done = true;
   }
+  const float4* tab = stft_tables();
+  if (!tab) return BN_ERR_CUDA;
   k_init_minmax<<<(B + 255) / 256, 256, 0, st>>>(mnmx, B);
   dim3 grid((W + FRAMES_PER_CTA - 1) / FRAMES_PER_CTA, B);
-  k_stft_mag<false><<<grid, FE_THREADS, smem, st>>>(pcm, peak, out, mnmx, T, hop, W, 0);
+  k_stft_mag<false><<<grid, FE_THREADS, smem, st>>>(pcm, peak, out, mnmx, tab, T, hop, W, 0);
   return 0;
 }
 
@@ -253,9 +301,11 @@ int launch_stft_mag_fm(const int16_t* pcm, const float* peak, float* out, unsign
     cudaFuncSetAttribute(k_stft_mag<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_done = true;
   }
+  const float4* tab = stft_tables();
+  if (!tab) return BN_ERR_CUDA;
   k_init_minmax<<<(B + 255) / 256, 256, 0, st>>>(mnmx, B);
   dim3 grid((W + FRAMES_PER_CTA - 1) / FRAMES_PER_CTA, B);
-  k_stft_mag<true><<<grid, FE_THREADS, smem, st>>>(pcm, peak, out, mnmx, T, hop, W, ldk);
+  k_stft_mag<true><<<grid, FE_THREADS, smem, st>>>(pcm, peak, out, mnmx, tab, T, hop, W, ldk);
   return 0;
 }
 
