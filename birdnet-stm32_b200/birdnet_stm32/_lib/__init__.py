@@ -22,6 +22,7 @@ EXPORTS = (
 
 BN_POOL = {"avg": 0, "mean": 0, "average": 0, "max": 1, "lme": 2, "log_mean_exp": 2, "log_mean_exponential": 2}
 BN_OPT_ROUNDING, BN_OPT_MEAN_VARIANT, BN_OPT_FORCE_GENERIC, BN_OPT_WAVE, BN_OPT_PROFILE, BN_OPT_TENSOR_CORE = 1, 2, 3, 4, 5, 6
+BN_OPT_FUSION = 7
 
 
 class BnInfo(C.Structure):

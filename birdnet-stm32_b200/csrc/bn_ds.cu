@@ -1,0 +1,279 @@
+// bn_ds.cu -- K45: one depthwise-separable block per kernel, intermediates never leave the SM.
+//
+//   in  int8 [B][ih][iw][C]  --DW 3x3 (stride 1|2, SAME, ReLU6)-->  A tile in shared memory (K-major, swizzled)
+//       --tcgen05.mma kind::i8 with the pointwise weights--> int32 accumulators in TMEM
+//       --epilogue: requant (+ residual ADD with the block input still resident in shared memory) + clamp-->
+//   out int8 [B][oh][ow][N]
+//
+// Reference counterpart: ds_conv_block (birdnet_stm32/models/dscnn.py:28-84) as lowered into the .tflite
+// (DEPTHWISE_CONV_2D, CONV_2D 1x1, ADD) and executed by tf.lite.Interpreter.invoke
+// (birdnet_stm32/models/runners.py:93-95).  Integer semantics: SURVEY Appendix B.3-B.5, bit-exact.
+//
+// A CTA is persistent over tiles of TR output rows x ow columns (x NB chunks for the late 4x8 layers) =
+// MT * 128 output pixels.  Per tile: (1) cp.async the input rows (+halo, SAME padding = zero-point bytes) into
+// shared memory, (2) every thread walks one (column, 4-channel group) strip down the rows with a 3x3 register
+// window and dp4a against masked weight words, requantises and writes the int8 result straight into the
+// swizzled A operand, (3) one thread issues the MMAs, (4) all 8 warps drain TMEM (tcgen05.ld 32x32b.x16),
+// requantise, add the residual from the shared-memory input tile and store 16-byte pieces.
+//
+// Requantisation uses per-channel constants prepared on the host so that bias, rounding nudges and the output
+// zero point cost no instructions:   v = (acc * mult + (bias' * mult + 2^30)) >> 31        (SRDHM, 64-bit IMAD)
+//                                    y = (v + (2^(n-1) + zp * 2^n) + (v >> 31)) >> n       (RoundingDivideByPOT + zp)
+// Equality with gemmlowp's sequence and the int32-safe domain are checked at plan-build time (bn_fast.cu).
+#include "bn_ds.cuh"
+
+#include "bn_common.cuh"
+#include "bn_tc.cuh"
+
+namespace bn {
+
+constexpr int DS_THREADS = 256;
+
+__device__ __forceinline__ int rq64(int acc, int c_lo, int c_hi, int mult, int rz, int n) {
+  const long long c = ((long long)c_hi << 32) | (unsigned)c_lo;
+  const long long p = (long long)acc * (long long)mult + c;
+  const int v = (int)(p >> 31);
+  return (v + rz + (v >> 31)) >> n;
+}
+__device__ __forceinline__ int clamp2(int v, int lo, int hi) { return max(lo, min(v, hi)); }
+__device__ __forceinline__ unsigned pack4(int a, int b, int c, int d) {
+  return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
+}
+
+template <int S, int TR, int ADD>
+__global__ void __launch_bounds__(DS_THREADS, 2)
+k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles, DsParams P) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int TRIN = (TR - 1) * S + 3;             // input rows per chunk in a tile
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int C = P.C, CG = C >> 2, N = P.N, KP = P.KP, RW = P.RW;
+  const int TW = P.iw + P.pl + 1;                     // tile columns (left halo only when pad_left = 1)
+  const int b_bytes = N * KP, a_bytes = P.MT * 128 * KP;
+  const int tile_bytes = P.NB * TRIN * TW * C;
+  unsigned char* sB = smem;
+  unsigned char* sA = sB + b_bytes;
+  unsigned char* sT = sA + a_bytes;
+  int4* s_rq = reinterpret_cast<int4*>(sT + ((tile_bytes + 15) & ~15));
+  int* s_rz = reinterpret_cast<int*>(s_rq + N);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(s_rz + ((N + 1) & ~1));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+
+  // ---- one-time setup ---------------------------------------------------------------------------
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), (uint32_t)P.tmem_cols);
+  if (tid == 32) {
+    mbar_init(smem_u32(mbar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < b_bytes / 16; i += DS_THREADS) cp_async16(smem_u32(sB + 16 * i), P.w_img + 16 * (size_t)i);
+  cp_async_commit();
+  for (int i = tid; i < N; i += DS_THREADS) { s_rq[i] = __ldg(P.pw_rq + i); s_rz[i] = __ldg(P.pw_rz + i); }
+  if (P.C < KP) for (int i = tid; i < a_bytes / 16; i += DS_THREADS) *reinterpret_cast<uint4*>(sA + 16 * i) = make_uint4(0, 0, 0, 0);
+  const unsigned zpw = 0x01010101u * (unsigned)(uint8_t)P.dw_in_zp;
+  {  // halo columns hold the zero point for the whole kernel (cp.async never touches them)
+    const int rows = P.NB * TRIN;
+    const int wpc = C >> 2;                           // words per pixel
+    for (int i = tid; i < rows * wpc * 2; i += DS_THREADS) {
+      const int side = i & 1, rest = i >> 1;
+      const int row = rest / wpc, w = rest - row * wpc;
+      if (side == 0 && P.pl == 0) continue;
+      const int col = side ? TW - 1 : 0;
+      reinterpret_cast<unsigned*>(sT)[(row * TW + col) * wpc + w] = zpw;
+    }
+  }
+  // per-thread depthwise constants: the channel group of a thread is the same for all of its strips
+  const int cg = tid & (CG - 1);
+  int4 w[9];
+#pragma unroll
+  for (int t = 0; t < 9; t++) w[t] = __ldg(P.dw_wm + t * CG + cg);
+  int4 drq[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) drq[j] = __ldg(P.dw_rq + 4 * cg + j);
+  const int4 drz = __ldg(reinterpret_cast<const int4*>(P.dw_rz) + cg);
+  // A-operand position of this thread's 4 channels: k-half, 16-byte chunk, byte in chunk
+  const int k0 = 4 * cg;
+  const int a_kh_off = (k0 >> P.rw_log) * (128 * RW);
+  const int a_cc = (k0 & (RW - 1)) >> 4;
+  const int a_b = k0 & 15;
+
+  cp_async_wait_all();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const uint32_t sbo = 8 * RW;
+  const uint32_t lt = RW == 128 ? 2u : (RW == 64 ? 4u : 6u);
+  const uint32_t idesc = make_idesc_i8(128, N);
+  const int ksteps = KP >> 5, ksteps_per_half = RW >> 5;
+  const int q = warp & 3, hsel = warp >> 2;
+  const int NG = N >> 4;                              // 16-column groups
+  const int tiles_per_chunk = P.oh / TR;
+  const int ppr = (P.iw * C) >> 4;                    // 16-byte pieces per input row
+  const int nstrips = P.NB * P.ow * CG;
+
+  int it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+    int b0, oy0;
+    if (P.NB == 1) { b0 = tile / tiles_per_chunk; oy0 = (tile - b0 * tiles_per_chunk) * TR; }
+    else { b0 = tile * P.NB; oy0 = 0; }
+    // ---- (1) stage input rows ------------------------------------------------------------------
+    for (int row = warp; row < P.NB * TRIN; row += DS_THREADS / 32) {
+      const int bb = row / TRIN, tr = row - bb * TRIN;
+      const int iy = oy0 * S - P.pt + tr;
+      const bool ok = (b0 + bb) < Bw && iy >= 0 && iy < P.ih;
+      unsigned char* dst = sT + ((size_t)row * TW + P.pl) * C;
+      const int8_t* src = in + (((size_t)(b0 + bb) * P.ih + iy) * P.iw) * C;
+      if (ok) { for (int p = lane; p < ppr; p += 32) cp_async16(smem_u32(dst + 16 * p), src + 16 * p); }
+      else { for (int p = lane; p < ppr; p += 32) *reinterpret_cast<uint4*>(dst + 16 * p) = make_uint4(zpw, zpw, zpw, zpw); }
+    }
+    cp_async_commit();
+    cp_async_wait_all();
+    __syncthreads();
+    // ---- (2) depthwise 3x3 -> A operand ------------------------------------------------------------
+    for (int sidx = tid; sidx < nstrips; sidx += DS_THREADS) {
+      const int rest = sidx >> P.cg_log;
+      const int ox = rest & (P.ow - 1), bb = rest >> P.ow_log;
+      const unsigned* tp = reinterpret_cast<const unsigned*>(sT) + ((size_t)(bb * TRIN) * TW + ox * S) * CG + cg;
+      const int mbase = ((bb * TR) << P.ow_log) + ox;
+      unsigned x0[3], x1[3], x2[3];
+#pragma unroll
+      for (int fx = 0; fx < 3; fx++) { x0[fx] = tp[fx * CG]; if (S == 1) x1[fx] = tp[(TW + fx) * CG]; }
+#pragma unroll
+      for (int r = 0; r < TR; r++) {
+        const unsigned* rp = tp + (size_t)(r * S) * TW * CG;
+#pragma unroll
+        for (int fx = 0; fx < 3; fx++) {
+          if (S == 2) x1[fx] = rp[(TW + fx) * CG];
+          x2[fx] = rp[(2 * TW + fx) * CG];
+        }
+        int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+        for (int fx = 0; fx < 3; fx++) {
+          const int4 wa = w[fx], wb = w[3 + fx], wc = w[6 + fx];
+          a0 = __dp4a((int)x0[fx], wa.x, a0); a1 = __dp4a((int)x0[fx], wa.y, a1); a2 = __dp4a((int)x0[fx], wa.z, a2); a3 = __dp4a((int)x0[fx], wa.w, a3);
+          a0 = __dp4a((int)x1[fx], wb.x, a0); a1 = __dp4a((int)x1[fx], wb.y, a1); a2 = __dp4a((int)x1[fx], wb.z, a2); a3 = __dp4a((int)x1[fx], wb.w, a3);
+          a0 = __dp4a((int)x2[fx], wc.x, a0); a1 = __dp4a((int)x2[fx], wc.y, a1); a2 = __dp4a((int)x2[fx], wc.z, a2); a3 = __dp4a((int)x2[fx], wc.w, a3);
+        }
+        const int q0 = clamp2(rq64(a0, drq[0].x, drq[0].y, drq[0].z, drz.x, drq[0].w), P.dw_lo, P.dw_hi);
+        const int q1 = clamp2(rq64(a1, drq[1].x, drq[1].y, drq[1].z, drz.y, drq[1].w), P.dw_lo, P.dw_hi);
+        const int q2 = clamp2(rq64(a2, drq[2].x, drq[2].y, drq[2].z, drz.z, drq[2].w), P.dw_lo, P.dw_hi);
+        const int q3 = clamp2(rq64(a3, drq[3].x, drq[3].y, drq[3].z, drz.w, drq[3].w), P.dw_lo, P.dw_hi);
+        const int m = mbase + (r << P.ow_log);
+        const int j = m >> 7, row = m & 127;
+        const int off = j * (128 * KP) + a_kh_off + row * RW + ((a_cc ^ ((row >> P.sw_sh) & P.sw_mask)) << 4) + a_b;
+        *reinterpret_cast<unsigned*>(sA + off) = pack4(q0, q1, q2, q3);
+#pragma unroll
+        for (int fx = 0; fx < 3; fx++) {
+          if (S == 1) { x0[fx] = x1[fx]; x1[fx] = x2[fx]; }
+          else x0[fx] = x2[fx];
+        }
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    // ---- (3) pointwise conv on the tensor core -------------------------------------------------------
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
+      for (int j = 0; j < P.MT; j++) {
+        for (int ks = 0; ks < ksteps; ks++) {
+          const int h = ks / ksteps_per_half, kk = ks - h * ksteps_per_half;
+          const uint64_t ad = make_desc(a_addr + j * (128 * KP) + h * (128 * RW) + kk * 32, sbo, lt);
+          const uint64_t bd = make_desc(b_addr + h * (N * RW) + kk * 32, sbo, lt);
+          umma_i8(tmem_base + (uint32_t)(j * N), ad, bd, idesc, ks > 0 ? 1u : 0u);
+        }
+      }
+      umma_commit(smem_u32(mbar));
+    }
+    mbar_wait(smem_u32(mbar), (uint32_t)(it & 1));
+    tc_fence_after();
+    // ---- (4) epilogue ------------------------------------------------------------------------------------
+    const size_t pix0 = ((size_t)b0 * P.oh + oy0) << P.ow_log;
+    for (int t = hsel; t < P.MT * NG; t += 2) {
+      const int j = t / NG, g = t - j * NG;
+      const int m = j * 128 + 32 * q + lane;
+      const int bb = m >> P.trow_log;
+      const bool ok = (b0 + bb) < Bw;
+      int v[16];
+      tmem_ld16(tmem_base + (uint32_t)(j * N + 16 * g) + ((uint32_t)(32 * q) << 16), v);
+      uint4 rv = make_uint4(0, 0, 0, 0);
+      if (ADD) {
+        const int rem = m & ((1 << P.trow_log) - 1);
+        const int r = rem >> P.ow_log, ox = rem & (P.ow - 1);
+        rv = *reinterpret_cast<const uint4*>(sT + ((size_t)(bb * TRIN + r + P.pt) * TW + ox + P.pl) * C + 16 * g);
+      }
+      const unsigned rw[4] = {rv.x, rv.y, rv.z, rv.w};
+      unsigned ow4[4];
+#pragma unroll
+      for (int gg = 0; gg < 4; gg++) {
+        int o[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) {
+          const int c = 16 * g + 4 * gg + jj;
+          const int4 rq = s_rq[c];
+          const int rz = s_rz[c];
+          int y = clamp2(rq64(v[4 * gg + jj], rq.x, rq.y, rq.z, rz, rq.w), P.pw_lo, P.pw_hi);
+          if (ADD) {
+            // residual term: RoundingDivideByPOT(SRDHM((r - zp1) << 20, m1), n1), zero point folded into c1
+            const int r8 = (int)(int8_t)(rw[gg] >> (8 * jj));
+            int s1 = (int)(((long long)r8 * (long long)P.a_m1 + P.a_c1) >> 11);
+            if (P.a_n1 > 0) s1 = (s1 + P.a_rz1 + (s1 >> 31)) >> P.a_n1;
+            int t2;
+            if (ADD == 2) {
+              t2 = s1 + (y << 19);                    // conv term (y - zp2) << 19, -zp2 << 19 folded into a_co
+            } else {
+              int s2 = (int)(((long long)y * (long long)P.a_m2 + P.a_c2) >> 11);
+              if (P.a_n2 > 0) s2 = (s2 + P.a_rz2 + (s2 >> 31)) >> P.a_n2;
+              t2 = s1 + s2;
+            }
+            const int vv = (int)(((long long)t2 * (long long)P.a_mo + P.a_co) >> 31);
+            const int yo = P.a_no > 0 ? ((vv + P.a_rzo + (vv >> 31)) >> P.a_no) : vv + P.a_zpo;
+            y = clamp2(yo, P.a_lo, P.a_hi);
+          }
+          o[jj] = y;
+        }
+        ow4[gg] = pack4(o[0], o[1], o[2], o[3]);
+      }
+      if (ok) *reinterpret_cast<uint4*>(out + (pix0 + m) * N + 16 * g) = make_uint4(ow4[0], ow4[1], ow4[2], ow4[3]);
+    }
+    tc_fence_before();
+    __syncthreads();                                 // TMEM drained, input tile and A operand free
+  }
+  if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+size_t ds_smem_bytes(const DsParams& P, int S, int TR) {
+  const int trin = (TR - 1) * S + 3, tw = P.iw + P.pl + 1;
+  size_t b = (size_t)P.N * P.KP + (size_t)P.MT * 128 * P.KP;
+  b += ((size_t)P.NB * trin * tw * P.C + 15) & ~(size_t)15;
+  b += (size_t)P.N * 16 + (size_t)((P.N + 1) & ~1) * 4 + 16;
+  return b + 1024;                                   // alignment slack
+}
+
+template <int S, int TR, int ADD>
+static int launch_one(const int8_t* in, int8_t* out, int Bw, int ntiles, int grid, size_t smem, const DsParams& P, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(k_ds<S, TR, ADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; }
+  k_ds<S, TR, ADD><<<grid, DS_THREADS, smem, st>>>(in, out, Bw, ntiles, P);
+  return 0;
+}
+
+int launch_ds(const int8_t* in, int8_t* out, int Bw, const DsParams& P, const DsLaunch& L, int num_sms, cudaStream_t st) {
+  const int ntiles = P.NB == 1 ? Bw * (P.oh / L.TR) : (Bw + P.NB - 1) / P.NB;
+  int grid = num_sms * L.ctas_per_sm;
+  if (grid > ntiles) grid = ntiles;
+  if (grid < 1) return 0;
+#define DS_CASE(s, tr, add) if (L.S == s && L.TR == tr && L.add_mode == add) return launch_one<s, tr, add>(in, out, Bw, ntiles, grid, L.smem, P, st)
+  DS_CASE(1, 4, 0); DS_CASE(1, 4, 1); DS_CASE(1, 4, 2);
+  DS_CASE(1, 8, 0); DS_CASE(1, 8, 1); DS_CASE(1, 8, 2);
+  DS_CASE(2, 4, 0); DS_CASE(2, 8, 0);
+#undef DS_CASE
+  return BN_ERR_UNSUPPORTED;
+}
+
+}  // namespace bn

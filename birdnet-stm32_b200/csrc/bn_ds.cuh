@@ -1,0 +1,44 @@
+// bn_ds.cuh -- fused depthwise-separable block kernel (see bn_ds.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bn {
+
+// One DS block of models/dscnn.py:28-84 (ds_conv_block): DEPTHWISE_CONV_2D 3x3 (+ReLU6) -> CONV_2D 1x1
+// (+ReLU6 | linear) [-> ADD(block input, conv) + ReLU6].  All pointers are device pointers.
+struct DsParams {
+  // depthwise 3x3
+  const int4* dw_wm;      // [9][C/4] masked weight words (byte j of word j = w[tap][4*cg + j], other bytes 0)
+  const int4* dw_rq;      // [C] {mult, c_lo, c_hi, n}:  c = bias' * mult + 2^30 (64 bit), n = right shift >= 1
+  const int* dw_rz;       // [C] 2^(n-1) + out_zp * 2^n
+  // pointwise 1x1
+  const uint8_t* w_img;   // N * KP bytes: K-major swizzled shared-memory image of the weights
+  const int4* pw_rq;      // [N]
+  const int* pw_rz;       // [N]
+  int C, N, KP, RW;       // depthwise channels (= GEMM K), output channels, padded K, swizzle row width
+  int ih, iw, oh, ow, pt, pl;
+  int NB, MT;             // chunks per CTA tile, 128-row MMA tiles per CTA tile
+  int ow_log, trow_log, cg_log, ppr_log;   // log2 of ow, TR*ow, C/4, iw*C/16
+  int sw_sh, sw_mask, rw_log;              // swizzle: chunk ^= (row >> sw_sh) & sw_mask
+  int dw_in_zp, dw_lo, dw_hi;
+  int pw_lo, pw_hi;
+  int tmem_cols;
+  // residual ADD, input 1 = block input, input 2 = conv output
+  int a_m1, a_n1, a_rz1;  long long a_c1;   // u = (r * m1 + c1) >> 11 ; s1 = rshift_round(u, n1)
+  int a_m2, a_n2, a_rz2;  long long a_c2;   // generic conv term
+  int a_mo, a_no, a_rzo;  long long a_co;   // v = (t * mo + co) >> 31 ; y = rshift_round(v, no) (+ zp folded in rzo)
+  int a_zpo;                                // used when no == 0
+  int a_lo, a_hi;
+};
+
+struct DsLaunch {
+  int S, TR, add_mode;    // stride, output rows per tile, 0 none / 1 generic / 2 conv term = (o - zp2) << 19
+  size_t smem;
+  int ctas_per_sm;
+};
+
+int launch_ds(const int8_t* in, int8_t* out, int Bw, const DsParams& P, const DsLaunch& L, int num_sms, cudaStream_t st);
+size_t ds_smem_bytes(const DsParams& P, int S, int TR);
+
+}  // namespace bn

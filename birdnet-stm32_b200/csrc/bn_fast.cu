@@ -14,9 +14,11 @@
 #include "bn_fast.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 
+#include "bn_ds.cuh"
 #include "bn_kernels.cuh"
 #include "bn_pw_tc.cuh"
 
@@ -121,6 +123,9 @@ struct Block {
   PwParams pw;
   PwTcParams tc{};
   bool tc_ok = false;
+  DsParams ds{};                  // fused depthwise + pointwise (+ADD) kernel
+  DsLaunch dsl{};
+  bool ds_ok = false;
 };
 
 struct FastImpl {
@@ -285,6 +290,135 @@ static void prep_pw_weights(const FastPlan& fp, const bn_blob_op& op, int K, int
       wt[(size_t)kw * N + n] = (int)word;
     }
   }
+}
+
+// -------------------------------------------------------------------------------------------------
+// fused DS-block kernel (bn_ds.cu): per-channel constants with bias, rounding nudges and the output zero
+// point folded in.  Returns false (-> the unfused kernels run) when a channel leaves the int32-safe domain.
+// -------------------------------------------------------------------------------------------------
+static int ilog2_exact(int v) { int l = 0; while ((1 << l) < v) l++; return (1 << l) == v ? l : -1; }
+
+static bool build_rq_folded(const FastPlan& fp, const bn_blob_op& op, int C, std::vector<int>& rq, std::vector<int>& rz) {
+  const int32_t* mult = (const int32_t*)(fp.h_blob + op.off[2]);
+  const int32_t* shift = (const int32_t*)(fp.h_blob + op.off[3]);
+  const int8_t* w = (const int8_t*)(fp.h_blob + op.off[0]);
+  const int32_t* bias = (const int32_t*)(fp.h_blob + op.off[1]);
+  const int zp_in = op.p[BN_CONV_IN_ZP], zp_out = op.p[BN_CONV_OUT_ZP];
+  const long xmax = (127 - zp_in) > (zp_in + 128) ? (127 - zp_in) : (zp_in + 128);
+  const int taps = op.p[BN_CONV_KH] * op.p[BN_CONV_KW];
+  const int cin = op.p[BN_CONV_CIN];
+  rq.assign((size_t)C * 4, 0);
+  rz.assign(C, 0);
+  for (int c = 0; c < C; c++) {
+    long long m = mult[c];
+    int n = -shift[c];
+    long wsum = 0, ws = 0;
+    if (op.kind == BN_OP_DWCONV2D) { for (int t = 0; t < taps; t++) { wsum += labs((long)w[(long)t * C + c]); ws += w[(long)t * C + c]; } }
+    else { for (long k = 0; k < (long)taps * cin; k++) { wsum += labs((long)w[(long)c * taps * cin + k]); ws += w[(long)c * taps * cin + k]; } }
+    const long long biasf = (long long)bias[c] - (long long)zp_in * ws;     // acc = sum(x * w) + bias'
+    // constant channels (multiplier 0, or all-zero weights with a saturated bias as the converter emits for dead
+    // channels): the requantised value at both ends of the reachable accumulator range is the same, so the channel
+    // is encoded as v = 0, y = rz >> 1 = that constant.  (mbqm is monotonic in acc for multipliers >= 0.)
+    const long long alo = (long long)bias[c] - (long long)wsum * xmax, ahi = (long long)bias[c] + (long long)wsum * xmax;
+    bool constant = false;
+    int y0 = 0;
+    if (alo >= -(1ll << 31) && ahi < (1ll << 31)) {
+      const int ylo = clampi(mbqm((int)alo, (int)m, shift[c], 0) + zp_out, op.p[BN_CONV_ACT_MIN], op.p[BN_CONV_ACT_MAX]);
+      const int yhi = clampi(mbqm((int)ahi, (int)m, shift[c], 0) + zp_out, op.p[BN_CONV_ACT_MIN], op.p[BN_CONV_ACT_MAX]);
+      if (ylo == yhi) { constant = true; y0 = ylo; }
+    }
+    if (!constant) {
+      if (n < 1 || n > 31) return false;
+      const long long amax = llabs((long long)bias[c]) + (long long)wsum * xmax;
+      const long long vmax = (long long)(((__int128)amax * m + (1ll << 30)) >> 31) + 1;
+      const long long rzv = (1ll << (n - 1)) + (long long)zp_out * (1ll << n);
+      if (vmax + llabs(rzv) + 1 >= (1ll << 31)) return false;
+    }
+    long long c64; int nn; long long rzv;
+    if (constant) { m = 0; nn = 1; c64 = 1ll << 30; rzv = 2ll * y0; }
+    else { nn = n; c64 = biasf * m + (1ll << 30); rzv = (1ll << (nn - 1)) + (long long)zp_out * (1ll << nn); }
+    rq[4 * c + 0] = (int)(uint32_t)(c64 & 0xffffffffll);
+    rq[4 * c + 1] = (int)(c64 >> 32);
+    rq[4 * c + 2] = (int)m;
+    rq[4 * c + 3] = nn;
+    rz[c] = (int)rzv;
+  }
+  return true;
+}
+
+static bool prep_ds(FastPlan& fp, FastImpl* im, Block& bl) {
+  const bn_blob_op& dw = fp.ops[bl.dw_op];
+  const bn_blob_op& pw = fp.ops[bl.pw_op];
+  const bn_blob_tensor* T = fp.tensors;
+  DsParams& D = bl.ds;
+  DsLaunch& L = bl.dsl;
+  const int C = dw.p[BN_CONV_CIN], N = pw.p[BN_CONV_COUT];
+  if (pw.p[BN_CONV_CIN] != C || !pw_tc_supported(C, N) || !bl.tc_ok) { if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: reject at check 1 (line %d)\n", __LINE__); return false; }
+  D.C = C; D.N = N;
+  D.ih = T[dw.in[0]].dims[0]; D.iw = T[dw.in[0]].dims[1]; D.oh = T[dw.out].dims[0]; D.ow = T[dw.out].dims[1];
+  D.pt = dw.p[BN_CONV_PAD_T]; D.pl = dw.p[BN_CONV_PAD_L];
+  const int S = dw.p[BN_CONV_SH];
+  if (!((S == 1 && D.pt == 1 && D.pl == 1) || (S == 2 && D.pt == 0 && D.pl == 0))) { if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: reject at check 2 (line %d)\n", __LINE__); return false; }
+  if (S == 1 && (D.oh != D.ih || D.ow != D.iw)) { if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: reject at check 3 (line %d)\n", __LINE__); return false; }
+  if (S == 2 && (D.oh * 2 != D.ih || D.ow * 2 != D.iw)) { if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: reject at check 4 (line %d)\n", __LINE__); return false; }
+  const int npix = D.oh * D.ow;
+  int TR, NB;
+  if (npix >= 256) { TR = 256 / D.ow; NB = 1; }
+  else if (npix >= 128) { TR = 128 / D.ow; NB = 1; }
+  else { if (128 % npix) { if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: reject at check 5 (line %d)\n", __LINE__); return false; } NB = 128 / npix; TR = D.oh; }
+  if (!(TR == 4 || TR == 8) || TR > D.oh || D.oh % TR) { if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: reject at check 6 (line %d)\n", __LINE__); return false; }
+  D.NB = NB; D.MT = TR * D.ow * NB / 128;
+  if (D.MT < 1 || TR * D.ow * NB != D.MT * 128) { if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: reject at check 7 (line %d)\n", __LINE__); return false; }
+  D.ow_log = ilog2_exact(D.ow); D.trow_log = ilog2_exact(TR * D.ow); D.cg_log = ilog2_exact(C / 4);
+  D.ppr_log = ilog2_exact(D.iw * C / 16);
+  if (D.ow_log < 0 || D.trow_log < 0 || D.cg_log < 0 || D.ppr_log < 0 || C / 4 > 64) { if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: reject at check 8 (line %d)\n", __LINE__); return false; }
+  D.KP = bl.tc.KP; D.RW = bl.tc.RW;
+  D.rw_log = ilog2_exact(D.RW);
+  D.sw_sh = D.RW == 128 ? 0 : (D.RW == 64 ? 1 : 2);
+  D.sw_mask = D.RW == 128 ? 7 : (D.RW == 64 ? 3 : 1);
+  int cols = 32; while (cols < D.MT * N) cols <<= 1;
+  if (cols > 512) { if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: reject at check 9 (line %d)\n", __LINE__); return false; }
+  D.tmem_cols = cols;
+  std::vector<int> rq, rz;
+  if (!build_rq_folded(fp, dw, C, rq, rz)) { if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: reject at check 10 (line %d)\n", __LINE__); return false; }
+  D.dw_rq = (const int4*)upload(im, rq.data(), rq.size() * 4);
+  D.dw_rz = (const int*)upload(im, rz.data(), rz.size() * 4);
+  if (!build_rq_folded(fp, pw, N, rq, rz)) { if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: reject at check 11 (line %d)\n", __LINE__); return false; }
+  D.pw_rq = (const int4*)upload(im, rq.data(), rq.size() * 4);
+  D.pw_rz = (const int*)upload(im, rz.data(), rz.size() * 4);
+  D.dw_wm = (const int4*)bl.dw.wm;
+  D.w_img = bl.tc.w_img;
+  D.dw_in_zp = dw.p[BN_CONV_IN_ZP]; D.dw_lo = dw.p[BN_CONV_ACT_MIN]; D.dw_hi = dw.p[BN_CONV_ACT_MAX];
+  D.pw_lo = pw.p[BN_CONV_ACT_MIN]; D.pw_hi = pw.p[BN_CONV_ACT_MAX];
+  L.S = S; L.TR = TR; L.add_mode = 0;
+  if (bl.add_op >= 0) {
+    if (S != 1 || N != C) { if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: reject at check 12 (line %d)\n", __LINE__); return false; }
+    const int32_t* p = fp.ops[bl.add_op].p;
+    if (p[BN_ADD_LEFT_SHIFT] != 20) { if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: reject at check 13 (line %d)\n", __LINE__); return false; }
+    const int n1 = -p[BN_ADD_S1], n2 = -p[BN_ADD_S2], no = -p[BN_ADD_SO];
+    if (n1 < 0 || n1 > 30 || n2 < 0 || n2 > 30 || no < 0 || no > 30) { if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: reject at check 14 (line %d)\n", __LINE__); return false; }
+    const long long m1 = p[BN_ADD_M1], m2 = p[BN_ADD_M2], mo = p[BN_ADD_MO];
+    const long long zp1 = p[BN_ADD_IN1_ZP], zp2 = p[BN_ADD_IN2_ZP], zpo = p[BN_ADD_OUT_ZP];
+    D.a_m1 = (int)m1; D.a_n1 = n1; D.a_rz1 = n1 > 0 ? (1 << (n1 - 1)) : 0; D.a_c1 = (1ll << 10) - zp1 * m1;
+    D.a_m2 = (int)m2; D.a_n2 = n2; D.a_rz2 = n2 > 0 ? (1 << (n2 - 1)) : 0; D.a_c2 = (1ll << 10) - zp2 * m2;
+    L.add_mode = (m2 == (1ll << 30) && n2 == 0) ? 2 : 1;
+    D.a_mo = (int)mo; D.a_no = no;
+    D.a_co = (1ll << 30) - (L.add_mode == 2 ? zp2 * (1ll << 19) * mo : 0);
+    // |s| <= (255 * m + 2^10) >> 11 (then shifted right) ; |t| <= |s1| + |s2| ; |v| <= (|t| * mo + 2^30) >> 31
+    const long long s1max = ((255 * m1 + (1ll << 10)) >> 11 >> n1) + 1, s2max = ((255 * m2 + (1ll << 10)) >> 11 >> n2) + 1;
+    const long long vmax = (long long)((((__int128)(s1max + s2max)) * mo + (1ll << 30)) >> 31) + 1;
+    const long long rzo = no > 0 ? (1ll << (no - 1)) + zpo * (1ll << no) : 0;
+    if (s1max + s2max >= (1ll << 30) || vmax + llabs(rzo) + 1 >= (1ll << 31)) { if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: reject at check 15 (line %d)\n", __LINE__); return false; }
+    D.a_rzo = (int)rzo; D.a_zpo = (int)zpo;
+    D.a_lo = p[BN_ADD_ACT_MIN]; D.a_hi = p[BN_ADD_ACT_MAX];
+  }
+  L.smem = ds_smem_bytes(D, S, TR);
+  if (L.smem > 225 * 1024) { if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: reject at check 16 (line %d)\n", __LINE__); return false; }
+  int per = (int)((225 * 1024) / L.smem);
+  if (per > 512 / cols) per = 512 / cols;
+  if (per > 2) per = 2;                          // 128 registers x 256 threads
+  L.ctas_per_sm = per < 1 ? 1 : per;
+  return D.dw_rq && D.dw_rz && D.pw_rq && D.pw_rz;
 }
 
 static bool build_impl(FastPlan& fp) {
@@ -507,6 +641,7 @@ static bool build_impl(FastPlan& fp) {
         bl.tc_ok = ok && Tc.w_img != nullptr;
       }
     }
+    bl.ds_ok = prep_ds(fp, im, bl);
   }
   {  // tail
     const bn_blob_op& mo = ops[im->mean_op];
@@ -1078,6 +1213,16 @@ static int run_body(FastPlan& fp, int mode, const float* src, int Bw, float* d_s
     const int8_t* bin = (const int8_t*)im->slot_buf[bl.in_slot];
     int8_t* dwo = (int8_t*)im->slot_buf[bl.dw_slot];
     int8_t* bout = (int8_t*)im->slot_buf[bl.out_slot];
+    if ((fp.fusion & 1) && bl.ds_ok && fp.use_tc && R == 0) {
+      snprintf(name, sizeof name, "K45_ds_%02d_c%d_n%d_s%d%s", bi, bl.ds.C, bl.ds.N, bl.dsl.S, bl.add_op >= 0 ? "_add" : "");
+      if (prof) prof->begin(name, st);
+      int rc = launch_ds(bin, bout, Bw, bl.ds, bl.dsl, fp.num_sms, st);
+      if (prof) prof->end(st);
+      if (rc) return rc;
+      (*launches)++;
+      bi++;
+      continue;
+    }
     {
       const DwParams& D = bl.dw;
       const int npair = ((D.ow + 1) / 2) * (D.C / 4);

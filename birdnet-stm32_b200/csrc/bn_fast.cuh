@@ -51,6 +51,7 @@ struct FastPlan {
   int wave = 0;
   int use_tc = 1;              // pointwise convs on tcgen05 (BN_OPT_TENSOR_CORE)
   int num_sms = 148;
+  int fusion = 3;              // bit 0: fused DS-block kernels, bit 1: fused frontend (BN_OPT_FUSION)
   FastImpl* impl = nullptr;
   std::string why;             // why the pattern did not match (diagnostics)
 };

@@ -74,20 +74,53 @@ def test_graph_bit_exact_default_plan(runner, oracle_model, oracle_spec):
     assert one.dtype == np.float32 and one.shape == (1, 100)
 
 
+BLOCK_OUT_TAPS = [96, 97, 99, 102, 104, 107, 110, 112, 115, 118, 121, 123, 126]
+DW_OUT_TAPS = [98, 100, 103, 105, 108, 111, 113, 116, 119, 122, 124]
+
+
 def test_fused_plan_is_active_and_its_tensors_are_bit_exact(runner, graph, oracle_model, oracle_spec):
     """The shipped graph must match the fused pattern; every tensor the fused plan materialises
-    (head output #96, stem #97, every depthwise / block output) equals the oracle's."""
+    (head output #96, stem #97, every DS-block output) equals the oracle's.  With BN_OPT_FUSION = 0 the
+    depthwise outputs are materialised too and must also match."""
+    from birdnet_stm32 import _lib as L
+
     assert runner.query().fast_path == 1
     B = oracle_spec.shape[0]
-    got = runner.predict(oracle_spec)
-    np.testing.assert_array_equal(got, oracle_model.predict(oracle_spec))
-    fused_taps = [96, 97, 98, 99, 100, 102, 103, 104, 105, 107, 108, 110, 111, 112, 113, 115, 116, 118, 119, 121, 122, 123, 124, 126]
-    for tid in fused_taps:
-        t = graph.tensor(tid)
-        nb = int(np.prod(t.shape[1:]))
-        g = runner.dump_tensor(tid, nb * B)
-        _, o = oracle_model.run(oracle_spec, tap_id=tid)
-        assert np.array_equal(g, o.reshape(-1)), f"fused tensor {tid} differs in {(g != o.reshape(-1)).sum()} of {g.size}"
+    for fusion, taps in ((3, BLOCK_OUT_TAPS), (0, BLOCK_OUT_TAPS + DW_OUT_TAPS)):
+        runner.set_option(L.BN_OPT_FUSION, fusion)
+        try:
+            got = runner.predict(oracle_spec)
+            np.testing.assert_array_equal(got, oracle_model.predict(oracle_spec))
+            for tid in taps:
+                t = graph.tensor(tid)
+                nb = int(np.prod(t.shape[1:]))
+                g = runner.dump_tensor(tid, nb * B)
+                _, o = oracle_model.run(oracle_spec, tap_id=tid)
+                assert np.array_equal(g, o.reshape(-1)), f"fusion={fusion} tensor {tid} differs in {(g != o.reshape(-1)).sum()} of {g.size}"
+        finally:
+            runner.set_option(L.BN_OPT_FUSION, 3)
+
+
+def test_fused_kernels_equal_layer_kernels_on_ragged_batches(blob, cfg, synth):
+    """Fused DS-block / frontend kernels vs one kernel per layer on batches that do not fill the last tile
+    (the 4x8 layers pack 4 chunks per MMA tile) and that span several waves: identical scores."""
+    from birdnet_stm32 import _lib as L
+    from birdnet_stm32.evaluation.gpu_runner import GpuRunner
+
+    pcm = synth.synth_pcm16(37, 66150, 22050, seed=77, edge_cases=True)
+    peak = synth.file_peaks(pcm)
+    r = GpuRunner(blob, cfg, wave=16)
+    try:
+        fused = r.predict_pcm16(pcm, peak)
+        r.set_option(L.BN_OPT_FUSION, 0)
+        layer = r.predict_pcm16(pcm, peak)
+        np.testing.assert_array_equal(fused, layer)
+        for n in (1, 2, 3, 5):
+            r.set_option(L.BN_OPT_FUSION, 3)
+            a = r.predict_pcm16(pcm[:n], peak[:n])
+            np.testing.assert_array_equal(a, layer[:n])
+    finally:
+        r.close()
 
 
 def test_full_path_same_codes_as_generic_plan(runner, pcm_batch):
