@@ -70,6 +70,27 @@ __host__ __device__ __forceinline__ int32_t clampi(int32_t v, int32_t lo, int32_
   return v < lo ? lo : (v > hi ? hi : v);
 }
 
+#ifdef __CUDACC__
+// "Saturating form" of the requantisation, for layers whose output zero point and clamp are -128 / [-128, 127]
+// (every ReLU / ReLU6 layer of the graph): with C = bias' * mult + 2^30 + (2^(n-1) + zp * 2^n) * 2^31,
+//   y = hi32(acc * mult + C) >> (n - 1)
+// equals floor((v + 2^(n-1)) / 2^n) + zp with v = SRDHM(acc + bias', mult).  gemmlowp's tie nudge (v >> 31) only
+// acts on v < 0, where both forms are <= zp = -128 and saturate to the same byte, so it is dropped.
+__device__ __forceinline__ int rq_hi(int acc, int c_lo, int c_hi, int mult) {
+  const long long c = ((long long)c_hi << 32) | (unsigned)c_lo;
+  return (int)(((long long)acc * (long long)mult + c) >> 32);
+}
+// four int32 -> four int8 with signed saturation (I2IP.S8.S32.SAT), byte 0 = a
+__device__ __forceinline__ unsigned pack4_sat(int a, int b, int c, int d) {
+  unsigned r;
+  asm("{\n\t.reg .b32 t;\n\t"
+      "cvt.pack.sat.s8.s32.b32 t, %4, %3, 0;\n\t"
+      "cvt.pack.sat.s8.s32.b32 %0, %2, %1, t;\n\t}"
+      : "=r"(r) : "r"(a), "r"(b), "r"(c), "r"(d));
+  return r;
+}
+#endif
+
 struct ConvParams {
   const int8_t* w;
   const int32_t* bias;

@@ -36,10 +36,6 @@ __device__ __forceinline__ int rq64(int acc, int c_lo, int c_hi, int mult, int r
   return (v + rz + (v >> 31)) >> n;
 }
 __device__ __forceinline__ int clamp2(int v, int lo, int hi) { return max(lo, min(v, hi)); }
-__device__ __forceinline__ unsigned pack4(int a, int b, int c, int d) {
-  return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
-}
-
 template <int S, int TR, int ADD>
 __global__ void __launch_bounds__(DS_THREADS, 2)
 k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles, DsParams P) {
@@ -89,7 +85,6 @@ k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles
   int4 drq[4];
 #pragma unroll
   for (int j = 0; j < 4; j++) drq[j] = __ldg(P.dw_rq + 4 * cg + j);
-  const int4 drz = __ldg(reinterpret_cast<const int4*>(P.dw_rz) + cg);
   // A-operand position of this thread's 4 channels: k-half, 16-byte chunk, byte in chunk
   const int k0 = 4 * cg;
   const int a_kh_off = (k0 >> P.rw_log) * (128 * RW);
@@ -155,14 +150,14 @@ k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles
           a0 = __dp4a((int)x1[fx], wb.x, a0); a1 = __dp4a((int)x1[fx], wb.y, a1); a2 = __dp4a((int)x1[fx], wb.z, a2); a3 = __dp4a((int)x1[fx], wb.w, a3);
           a0 = __dp4a((int)x2[fx], wc.x, a0); a1 = __dp4a((int)x2[fx], wc.y, a1); a2 = __dp4a((int)x2[fx], wc.z, a2); a3 = __dp4a((int)x2[fx], wc.w, a3);
         }
-        const int q0 = clamp2(rq64(a0, drq[0].x, drq[0].y, drq[0].z, drz.x, drq[0].w), P.dw_lo, P.dw_hi);
-        const int q1 = clamp2(rq64(a1, drq[1].x, drq[1].y, drq[1].z, drz.y, drq[1].w), P.dw_lo, P.dw_hi);
-        const int q2 = clamp2(rq64(a2, drq[2].x, drq[2].y, drq[2].z, drz.z, drq[2].w), P.dw_lo, P.dw_hi);
-        const int q3 = clamp2(rq64(a3, drq[3].x, drq[3].y, drq[3].z, drz.w, drq[3].w), P.dw_lo, P.dw_hi);
+        const int q0 = rq_hi(a0, drq[0].x, drq[0].y, drq[0].z) >> drq[0].w;
+        const int q1 = rq_hi(a1, drq[1].x, drq[1].y, drq[1].z) >> drq[1].w;
+        const int q2 = rq_hi(a2, drq[2].x, drq[2].y, drq[2].z) >> drq[2].w;
+        const int q3 = rq_hi(a3, drq[3].x, drq[3].y, drq[3].z) >> drq[3].w;
         const int m = mbase + (r << P.ow_log);
         const int j = m >> 7, row = m & 127;
         const int off = j * (128 * KP) + a_kh_off + row * RW + ((a_cc ^ ((row >> P.sw_sh) & P.sw_mask)) << 4) + a_b;
-        *reinterpret_cast<unsigned*>(sA + off) = pack4(q0, q1, q2, q3);
+        *reinterpret_cast<unsigned*>(sA + off) = pack4_sat(q0, q1, q2, q3);
 #pragma unroll
         for (int fx = 0; fx < 3; fx++) {
           if (S == 1) { x0[fx] = x1[fx]; x1[fx] = x2[fx]; }
@@ -204,7 +199,8 @@ k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles
         const int r = rem >> P.ow_log, ox = rem & (P.ow - 1);
         rv = *reinterpret_cast<const uint4*>(sT + ((size_t)(bb * TRIN + r + P.pt) * TW + ox + P.pl) * C + 16 * g);
       }
-      const unsigned rw[4] = {rv.x, rv.y, rv.z, rv.w};
+      // residual bytes as unsigned r - zp1 (zp1 = -128)
+      const unsigned rw[4] = {rv.x ^ 0x80808080u, rv.y ^ 0x80808080u, rv.z ^ 0x80808080u, rv.w ^ 0x80808080u};
       unsigned ow4[4];
 #pragma unroll
       for (int gg = 0; gg < 4; gg++) {
@@ -213,13 +209,15 @@ k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles
         for (int jj = 0; jj < 4; jj++) {
           const int c = 16 * g + 4 * gg + jj;
           const int4 rq = s_rq[c];
-          const int rz = s_rz[c];
-          int y = clamp2(rq64(v[4 * gg + jj], rq.x, rq.y, rq.z, rz, rq.w), P.pw_lo, P.pw_hi);
-          if (ADD) {
-            // residual term: RoundingDivideByPOT(SRDHM((r - zp1) << 20, m1), n1), zero point folded into c1
-            const int r8 = (int)(int8_t)(rw[gg] >> (8 * jj));
-            int s1 = (int)(((long long)r8 * (long long)P.a_m1 + P.a_c1) >> 11);
-            if (P.a_n1 > 0) s1 = (s1 + P.a_rz1 + (s1 >> 31)) >> P.a_n1;
+          if (!ADD) {
+            o[jj] = rq_hi(v[4 * gg + jj], rq.x, rq.y, rq.z) >> rq.w;
+          } else {
+            const int rz = s_rz[c];
+            const int y = clamp2(rq64(v[4 * gg + jj], rq.x, rq.y, rq.z, rz, rq.w), P.pw_lo, P.pw_hi);
+            // residual term RoundingDivideByPOT(SRDHM((r - zp1) << 20, m1), n1): the operand is >= 0, so both
+            // roundings are plain "add half, shift" and fold into one 64-bit multiply-add + shift
+            const unsigned u = __byte_perm(rw[gg], 0u, 0x4440 + jj);
+            const int s1 = (int)(((unsigned long long)u * (unsigned)P.a_m1 + (unsigned long long)P.a_c1) >> P.a_n1);
             int t2;
             if (ADD == 2) {
               t2 = s1 + (y << 19);                    // conv term (y - zp2) << 19, -zp2 << 19 folded into a_co
@@ -228,13 +226,11 @@ k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles
               if (P.a_n2 > 0) s2 = (s2 + P.a_rz2 + (s2 >> 31)) >> P.a_n2;
               t2 = s1 + s2;
             }
-            const int vv = (int)(((long long)t2 * (long long)P.a_mo + P.a_co) >> 31);
-            const int yo = P.a_no > 0 ? ((vv + P.a_rzo + (vv >> 31)) >> P.a_no) : vv + P.a_zpo;
-            y = clamp2(yo, P.a_lo, P.a_hi);
+            // output: saturating form (zp_out = -128, clamp [-128, 127]), a_no = right shift - 1
+            o[jj] = (int)(((long long)t2 * (long long)P.a_mo + P.a_co) >> 32) >> P.a_no;
           }
-          o[jj] = y;
         }
-        ow4[gg] = pack4(o[0], o[1], o[2], o[3]);
+        ow4[gg] = pack4_sat(o[0], o[1], o[2], o[3]);
       }
       if (ok) *reinterpret_cast<uint4*>(out + (pix0 + m) * N + 16 * g) = make_uint4(ow4[0], ow4[1], ow4[2], ow4[3]);
     }

@@ -10,12 +10,12 @@ namespace bn {
 struct DsParams {
   // depthwise 3x3
   const int4* dw_wm;      // [9][C/4] masked weight words (byte j of word j = w[tap][4*cg + j], other bytes 0)
-  const int4* dw_rq;      // [C] {mult, c_lo, c_hi, n}:  c = bias' * mult + 2^30 (64 bit), n = right shift >= 1
-  const int* dw_rz;       // [C] 2^(n-1) + out_zp * 2^n
+  const int4* dw_rq;      // [C] {c_lo, c_hi, mult, n - 1}, saturating form: c = bias' * mult + 2^30 + (2^(n-1) + zp * 2^n) * 2^31
+  const int* dw_rz;       // unused by the saturating form
   // pointwise 1x1
   const uint8_t* w_img;   // N * KP bytes: K-major swizzled shared-memory image of the weights
-  const int4* pw_rq;      // [N]
-  const int* pw_rz;       // [N]
+  const int4* pw_rq;      // [N] saturating form when there is no ADD; else {c_lo, c_hi, mult, n} with c = bias' * mult + 2^30
+  const int* pw_rz;       // [N] 2^(n-1) + out_zp * 2^n (ADD blocks: the conv output is signed, tie nudge kept)
   int C, N, KP, RW;       // depthwise channels (= GEMM K), output channels, padded K, swizzle row width
   int ih, iw, oh, ow, pt, pl;
   int NB, MT;             // chunks per CTA tile, 128-row MMA tiles per CTA tile
@@ -25,9 +25,9 @@ struct DsParams {
   int pw_lo, pw_hi;
   int tmem_cols;
   // residual ADD, input 1 = block input, input 2 = conv output
-  int a_m1, a_n1, a_rz1;  long long a_c1;   // u = (r * m1 + c1) >> 11 ; s1 = rshift_round(u, n1)
+  int a_m1, a_n1, a_rz1;  long long a_c1;   // s1 = ((r + 128) * m1 + c1) >> a_n1, a_n1 = 11 + n1, c1 = 2^10 + 2^(n1+10) (zp1 = -128)
   int a_m2, a_n2, a_rz2;  long long a_c2;   // generic conv term
-  int a_mo, a_no, a_rzo;  long long a_co;   // v = (t * mo + co) >> 31 ; y = rshift_round(v, no) (+ zp folded in rzo)
+  int a_mo, a_no, a_rzo;  long long a_co;   // y = hi32(t * mo + co) >> a_no, a_no = no - 1, rounding + zp folded into co (saturating form)
   int a_zpo;                                // used when no == 0
   int a_lo, a_hi;
 };

@@ -91,6 +91,8 @@ struct StemParams {
   const int* bias; const int* mult; const int* shift;
   int ih, iw, oh, ow, in_zp, out_zp, act_min, act_max;
   int fast;
+  const int4* pk;                 // [16][2] {w_fy0, w_fy1, w_fy2, n - 1}, {c_lo, c_hi, mult, 0}: saturating form (rq_hi)
+  int sat;                        // pk is valid (zp_out = -128, clamp [-128, 127], int32-safe)
 };
 
 struct HeadParams {
@@ -298,7 +300,10 @@ static void prep_pw_weights(const FastPlan& fp, const bn_blob_op& op, int K, int
 // -------------------------------------------------------------------------------------------------
 static int ilog2_exact(int v) { int l = 0; while ((1 << l) < v) l++; return (1 << l) == v ? l : -1; }
 
-static bool build_rq_folded(const FastPlan& fp, const bn_blob_op& op, int C, std::vector<int>& rq, std::vector<int>& rz) {
+// sat_form: constants of rq_hi() (bn_ds.cu) -- rounding term and zero point folded into the 64-bit addend, rq.w = n - 1;
+// only valid for zp_out = -128 and clamp [-128, 127] (any v < 0 saturates, so gemmlowp's tie nudge is moot).
+static bool build_rq_folded(const FastPlan& fp, const bn_blob_op& op, int C, std::vector<int>& rq, std::vector<int>& rz, bool sat_form = false) {
+  if (sat_form && (op.p[BN_CONV_OUT_ZP] != -128 || op.p[BN_CONV_ACT_MIN] != -128 || op.p[BN_CONV_ACT_MAX] != 127)) return false;
   const int32_t* mult = (const int32_t*)(fp.h_blob + op.off[2]);
   const int32_t* shift = (const int32_t*)(fp.h_blob + op.off[3]);
   const int8_t* w = (const int8_t*)(fp.h_blob + op.off[0]);
@@ -337,6 +342,15 @@ static bool build_rq_folded(const FastPlan& fp, const bn_blob_op& op, int C, std
     long long c64; int nn; long long rzv;
     if (constant) { m = 0; nn = 1; c64 = 1ll << 30; rzv = 2ll * y0; }
     else { nn = n; c64 = biasf * m + (1ll << 30); rzv = (1ll << (nn - 1)) + (long long)zp_out * (1ll << nn); }
+    if (sat_form) {
+      if (constant) { c64 = (long long)y0 * (1ll << 32); }
+      else {
+        const __int128 big = (__int128)biasf * m + (1ll << 30) + (__int128)rzv * (1ll << 31);
+        if (big >= ((__int128)1 << 62) || big <= -((__int128)1 << 62)) return false;
+        c64 = (long long)big;
+      }
+      nn -= 1;
+    }
     rq[4 * c + 0] = (int)(uint32_t)(c64 & 0xffffffffll);
     rq[4 * c + 1] = (int)(c64 >> 32);
     rq[4 * c + 2] = (int)m;
@@ -380,10 +394,10 @@ static bool prep_ds(FastPlan& fp, FastImpl* im, Block& bl) {
   if (cols > 512) { if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: reject at check 9 (line %d)\n", __LINE__); return false; }
   D.tmem_cols = cols;
   std::vector<int> rq, rz;
-  if (!build_rq_folded(fp, dw, C, rq, rz)) { if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: reject at check 10 (line %d)\n", __LINE__); return false; }
+  if (!build_rq_folded(fp, dw, C, rq, rz, true)) { if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: reject at check 10 (line %d)\n", __LINE__); return false; }
   D.dw_rq = (const int4*)upload(im, rq.data(), rq.size() * 4);
   D.dw_rz = (const int*)upload(im, rz.data(), rz.size() * 4);
-  if (!build_rq_folded(fp, pw, N, rq, rz)) { if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: reject at check 11 (line %d)\n", __LINE__); return false; }
+  if (!build_rq_folded(fp, pw, N, rq, rz, bl.add_op < 0)) { if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: reject at check 11 (line %d)\n", __LINE__); return false; }
   D.pw_rq = (const int4*)upload(im, rq.data(), rq.size() * 4);
   D.pw_rz = (const int*)upload(im, rz.data(), rz.size() * 4);
   D.dw_wm = (const int4*)bl.dw.wm;
@@ -396,14 +410,16 @@ static bool prep_ds(FastPlan& fp, FastImpl* im, Block& bl) {
     const int32_t* p = fp.ops[bl.add_op].p;
     if (p[BN_ADD_LEFT_SHIFT] != 20) { if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: reject at check 13 (line %d)\n", __LINE__); return false; }
     const int n1 = -p[BN_ADD_S1], n2 = -p[BN_ADD_S2], no = -p[BN_ADD_SO];
-    if (n1 < 0 || n1 > 30 || n2 < 0 || n2 > 30 || no < 0 || no > 30) { if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: reject at check 14 (line %d)\n", __LINE__); return false; }
+    if (n1 < 0 || n1 > 21 || n2 < 0 || n2 > 30 || no < 1 || no > 30) { if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: reject at check 14 (line %d)\n", __LINE__); return false; }
     const long long m1 = p[BN_ADD_M1], m2 = p[BN_ADD_M2], mo = p[BN_ADD_MO];
     const long long zp1 = p[BN_ADD_IN1_ZP], zp2 = p[BN_ADD_IN2_ZP], zpo = p[BN_ADD_OUT_ZP];
-    D.a_m1 = (int)m1; D.a_n1 = n1; D.a_rz1 = n1 > 0 ? (1 << (n1 - 1)) : 0; D.a_c1 = (1ll << 10) - zp1 * m1;
+    // residual term and output in the folded forms of bn_ds.cu: need r - zp1 >= 0 and a saturating -128 output
+    if (zp1 != -128 || zpo != -128 || p[BN_ADD_ACT_MIN] != -128 || p[BN_ADD_ACT_MAX] != 127) { if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: reject at check 14b (line %d)\n", __LINE__); return false; }
+    D.a_m1 = (int)m1; D.a_n1 = 11 + n1; D.a_rz1 = 0; D.a_c1 = (1ll << 10) + (n1 > 0 ? (1ll << (n1 - 1 + 11)) : 0);
     D.a_m2 = (int)m2; D.a_n2 = n2; D.a_rz2 = n2 > 0 ? (1 << (n2 - 1)) : 0; D.a_c2 = (1ll << 10) - zp2 * m2;
     L.add_mode = (m2 == (1ll << 30) && n2 == 0) ? 2 : 1;
-    D.a_mo = (int)mo; D.a_no = no;
-    D.a_co = (1ll << 30) - (L.add_mode == 2 ? zp2 * (1ll << 19) * mo : 0);
+    D.a_mo = (int)mo; D.a_no = no - 1;
+    D.a_co = (1ll << 30) - (L.add_mode == 2 ? zp2 * (1ll << 19) * mo : 0) + ((1ll << (no - 1)) + zpo * (1ll << no)) * (1ll << 31);
     // |s| <= (255 * m + 2^10) >> 11 (then shifted right) ; |t| <= |s1| + |s2| ; |v| <= (|t| * mo + 2^30) >> 31
     const long long s1max = ((255 * m1 + (1ll << 10)) >> 11 >> n1) + 1, s2max = ((255 * m2 + (1ll << 10)) >> 11 >> n2) + 1;
     const long long vmax = (long long)((((__int128)(s1max + s2max)) * mo + (1ll << 30)) >> 31) + 1;
@@ -567,6 +583,17 @@ static bool build_impl(FastPlan& fp) {
     prep_requant(fp, im, st, 16, &S.mult, &S.shift, &S.fast);
     S.ih = T[st.in[0]].dims[0]; S.iw = T[st.in[0]].dims[1]; S.oh = T[st.out].dims[0]; S.ow = T[st.out].dims[1];
     S.in_zp = st.p[BN_CONV_IN_ZP]; S.out_zp = st.p[BN_CONV_OUT_ZP]; S.act_min = st.p[BN_CONV_ACT_MIN]; S.act_max = st.p[BN_CONV_ACT_MAX];
+    std::vector<int> rq, rz;
+    S.sat = 0; S.pk = nullptr;
+    if (build_rq_folded(fp, st, 16, rq, rz, true) && S.iw % 8 == 0 && S.ow % 4 == 0) {
+      std::vector<int> pk(16 * 8);
+      for (int co = 0; co < 16; co++) {
+        pk[co * 8 + 0] = ww[co * 3 + 0]; pk[co * 8 + 1] = ww[co * 3 + 1]; pk[co * 8 + 2] = ww[co * 3 + 2]; pk[co * 8 + 3] = rq[4 * co + 3];
+        pk[co * 8 + 4] = rq[4 * co + 0]; pk[co * 8 + 5] = rq[4 * co + 1]; pk[co * 8 + 6] = rq[4 * co + 2]; pk[co * 8 + 7] = 0;
+      }
+      S.pk = (const int4*)upload(im, pk.data(), pk.size() * 4);
+      S.sat = S.pk != nullptr;
+    }
   }
   for (Block& bl : im->blocks) {
     const bn_blob_op& dw = ops[bl.dw_op];
@@ -959,6 +986,68 @@ k_stem(const int8_t* __restrict__ in, int8_t* __restrict__ out, StemParams S, in
   }
 }
 
+// Saturating-form stem (see rq_hi in bn_common.cuh): thread = 4 adjacent output pixels x 16 channels; per channel two
+// 16-byte parameter loads serve 4 pixels, the requantisation is one wide multiply-add and one shift, and int8
+// saturation happens in the pack instruction.
+__global__ void __launch_bounds__(256)
+k_stem_sat(const int8_t* __restrict__ in, int8_t* __restrict__ out, StemParams S) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int ldt = S.iw + 8;                                     // tile row stride in bytes (multiple of 8)
+  unsigned char* tile = smem;                                   // [(STEM_ROWS+2)][ldt], halo = zero point
+  int4* prm = reinterpret_cast<int4*>(smem + (((STEM_ROWS + 2) * ldt + 15) & ~15));
+  const int tid = threadIdx.x;
+  const int b = blockIdx.y;
+  const int y0 = blockIdx.x * STEM_ROWS;
+  if (tid < 32) prm[tid] = __ldg(S.pk + tid);
+  const unsigned zpw = 0x01010101u * (unsigned)(uint8_t)S.in_zp;
+  const int words = ldt / 4;
+  const int8_t* ib = in + (long)b * S.ih * S.iw;
+  for (int i = tid; i < (STEM_ROWS + 2) * words; i += 256) {
+    const int r = i / words, w = i - r * words;
+    const int iy = y0 - 1 + r;
+    unsigned v = zpw;
+    if (iy >= 0 && iy < S.ih && 4 * w < S.iw) v = __ldg(reinterpret_cast<const unsigned*>(ib + (long)iy * S.iw) + w);
+    reinterpret_cast<unsigned*>(tile)[r * words + w] = v;
+  }
+  __syncthreads();
+  const int quads = S.ow / 4;
+  for (int i = tid; i < STEM_ROWS * quads; i += 256) {
+    const int ry = i / quads, q = i - ry * quads;
+    if (y0 + ry >= S.oh) continue;
+    // output pixel x reads input bytes 2x .. 2x+2: pixels 4q..4q+3 live in words 2q, 2q+1, 2q+2
+    unsigned x[3][4];
+#pragma unroll
+    for (int fy = 0; fy < 3; fy++) {
+      const unsigned* rowp = reinterpret_cast<const unsigned*>(tile + (ry + fy) * ldt) + 2 * q;
+      const uint2 w01 = *reinterpret_cast<const uint2*>(rowp);
+      const unsigned w2 = rowp[2];
+      x[fy][0] = w01.x; x[fy][1] = __funnelshift_r(w01.x, w01.y, 16);
+      x[fy][2] = w01.y; x[fy][3] = __funnelshift_r(w01.y, w2, 16);
+    }
+    unsigned o[4][4];                                           // [pixel][channel group]
+#pragma unroll
+    for (int cg = 0; cg < 4; cg++) {
+      int v[4][4];                                              // [channel in group][pixel]
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int4 wa = prm[2 * (4 * cg + j)], rq = prm[2 * (4 * cg + j) + 1];
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+          int acc = __dp4a((int)x[0][p], wa.x, 0);
+          acc = __dp4a((int)x[1][p], wa.y, acc);
+          acc = __dp4a((int)x[2][p], wa.z, acc);
+          v[j][p] = rq_hi(acc, rq.x, rq.y, rq.z) >> wa.w;
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < 4; p++) o[p][cg] = pack4_sat(v[0][p], v[1][p], v[2][p], v[3][p]);
+    }
+    int8_t* op = out + (((long)b * S.oh + (y0 + ry)) * S.ow + 4 * q) * 16;
+#pragma unroll
+    for (int p = 0; p < 4; p++) *reinterpret_cast<uint4*>(op + 16 * p) = make_uint4(o[p][0], o[p][1], o[p][2], o[p][3]);
+  }
+}
+
 // ---- K4: depthwise 3x3 ----------------------------------------------------------------------------------
 // in int8 [B][ih][iw][C], out int8 [B][oh][ow][C].  Thread = two adjacent output columns x 4 channels; it walks
 // down a band of output rows with a 3 x (3+SH) register window.  The input words of the next output row are
@@ -1201,7 +1290,8 @@ static int run_body(FastPlan& fp, int mode, const float* src, int Bw, float* d_s
     dim3 grid((S.oh + STEM_ROWS - 1) / STEM_ROWS, Bw);
     const size_t smem = (size_t)(STEM_ROWS + 2) * (S.iw + 8) + 96 * 4;
     if (prof) prof->begin("K3_stem", st);
-    if (S.fast && R == 0) k_stem<true><<<grid, 256, smem, st>>>(head_out, stem_out, S, R);
+    if (S.sat && R == 0) k_stem_sat<<<grid, 256, smem + 32 * 16 + 16, st>>>(head_out, stem_out, S);
+    else if (S.fast && R == 0) k_stem<true><<<grid, 256, smem, st>>>(head_out, stem_out, S, R);
     else k_stem<false><<<grid, 256, smem, st>>>(head_out, stem_out, S, R);
     if (prof) prof->end(st);
     (*launches)++;

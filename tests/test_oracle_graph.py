@@ -235,3 +235,48 @@ def test_gpu_closed_form_requant_equals_gemmlowp():
                 if abs(v) + (1 << (n - 1)) >= (1 << 31):
                     continue    # outside the int32-safe domain; the engine proves |v| bounds per layer at plan build
                 assert bo.rq_fast(x, m, n) == bo.mbqm(x, m, -n, 0), (x, m, n)
+
+
+def test_saturating_requant_forms_equal_gemmlowp():
+    """The folded forms of csrc/bn_ds.cu == the gemmlowp sequence, in exact integer arithmetic.
+
+    (1) rq_hi: y = hi32(acc*m + C) >> (n-1) with C = bias*m + 2^30 + (2^(n-1) + zp*2^n)*2^31, zp = -128, then signed
+        saturation to int8  ==  clamp(MBQM(acc + bias, m, -n) + zp, -128, 127);
+    (2) residual term of ADD with zp1 = -128:  ((r+128)*m1 + 2^10 + 2^(n1+10)) >> (11+n1)
+        ==  MBQM((r - zp1) << 20, m1, -n1);
+    (3) ADD output: hi32(t*mo + 2^30 + (2^(no-1) + zp*2^no)*2^31) >> (no-1), saturated
+        ==  clamp(MBQM(t, mo, -no) + zp, -128, 127).
+    """
+    from oracle import bn_oracle as bo
+
+    rng = np.random.default_rng(5)
+    sat = lambda v: max(-128, min(127, v))
+    zp = -128
+    for n in range(1, 25):
+        for m in [1 << 30, (1 << 31) - 1, 1518500250] + rng.integers(1 << 30, 1 << 31, 6).tolist():
+            bias = int(rng.integers(-(1 << 20), 1 << 20))
+            C = bias * m + (1 << 30) + ((1 << (n - 1)) + zp * (1 << n)) * (1 << 31)
+            span = min(400 << n, 1 << 30)         # covers the whole int8 output range around both clamps (int32-safe)
+            accs = rng.integers(-span, span, 300).tolist() + [0, 1, -1, -bias, -bias + 1, -bias - 1]
+            # exact ties of the second rounding, both signs
+            accs += [(-bias) + k for k in range(-3, 4)]
+            for acc in accs:
+                want = sat(bo.mbqm(acc + bias, m, -n, 0) + zp)
+                got = sat(((acc * m + C) >> 32) >> (n - 1))
+                assert got == want, (acc, bias, m, n)
+    for n1 in range(0, 22):
+        for m1 in [1 << 30, (1 << 31) - 1] + rng.integers(1 << 30, 1 << 31, 6).tolist():
+            c1 = (1 << 10) + ((1 << (n1 - 1 + 11)) if n1 > 0 else 0)
+            for r in range(-128, 128):
+                want = bo.mbqm((r + 128) << 20, m1, -n1, 0)
+                got = ((r + 128) * m1 + c1) >> (11 + n1)
+                assert got == want, (r, m1, n1)
+    for no in range(1, 25):
+        for mo in [1 << 30, (1 << 31) - 1] + rng.integers(1 << 30, 1 << 31, 6).tolist():
+            co = (1 << 30) + ((1 << (no - 1)) + zp * (1 << no)) * (1 << 31)
+            span = 400 << no
+            ts = rng.integers(-min(span, 1 << 30), min(span, 1 << 30), 300).tolist() + list(range(-4, 5))
+            for t in ts:
+                want = sat(bo.mbqm(t, mo, -no, 0) + zp)
+                got = sat(((t * mo + co) >> 32) >> (no - 1))
+                assert got == want, (t, mo, no)
