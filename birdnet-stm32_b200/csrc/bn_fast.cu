@@ -19,6 +19,7 @@
 #include <map>
 
 #include "bn_ds.cuh"
+#include "bn_head_tc.cuh"
 #include "bn_kernels.cuh"
 #include "bn_pw_tc.cuh"
 
@@ -60,6 +61,7 @@ Profiler::~Profiler() { for (auto e : pool) cudaEventDestroy(e); for (auto& p : 
 // =================================================================================================
 // Plan data
 // =================================================================================================
+constexpr int FE_SUBWAVE = 256;  // chunks per frontend sub-wave (K1 -> K2 through an L2-resident scratch buffer)
 constexpr int HEAD_N = 64;        // mel channels handled by the head kernel
 constexpr int HEAD_M = 128;       // frames per CTA
 constexpr int GEMM_LDA = 132;     // words per k-row of the transposed A tile (128 + 4 pad, keeps 16-byte alignment)
@@ -137,6 +139,8 @@ struct FastImpl {
   int region_src = -1, region_dst = -1, head_out_slot = -1, stem_out_slot = -1;
   std::vector<Block> blocks;
   HeadParams head{};
+  HeadTcParams head_tc{};         // tensor-core head (bn_head_tc.cu)
+  bool head_tc_ok = false;
   StemParams stem{};
   TailParams tail{};
   int ldk = 264;
@@ -563,6 +567,19 @@ static bool build_impl(FastPlan& fp) {
     H.q_scale = ops[im->quant_op].f[0]; H.q_zp = ops[im->quant_op].p[0];
     H.out_zp = mel.p[BN_CONV_OUT_ZP]; H.act_min = mel.p[BN_CONV_ACT_MIN]; H.act_max = mel.p[BN_CONV_ACT_MAX];
     H.W = im->W;
+    // tensor-core variant: saturating-form requant (zp_out = -128, full int8 clamp) and K laid out as 2 x SW128 + 1 x SW32
+    std::vector<int> rq, rz;
+    if (im->bins == 257 && (K_cat == 260 || K_cat == 264) && build_rq_folded(fp, mel, HEAD_N, rq, rz, true)) {
+      std::vector<uint8_t> img;
+      head_tc_weight_image((const int8_t*)(fp.h_blob + mel.off[0]), K_cat, img);
+      HeadTcParams& Q = im->head_tc;
+      Q.w_img = (const uint8_t*)upload(im, img.data(), img.size());
+      Q.rq = (const int4*)upload(im, rq.data(), rq.size() * 4);
+      Q.lut = im->d_head_lut;
+      Q.K_real = im->bins; Q.ldk = K_cat; Q.fill = fill_val; Q.W = im->W;
+      Q.q_scale = H.q_scale; Q.q_zp = H.q_zp;
+      im->head_tc_ok = Q.w_img && Q.rq;
+    }
   }
   {  // stem: weights [16][3][3][1] -> words (w0,w1,w2,0) per (co, fy)
     const int8_t* w = (const int8_t*)(fp.h_blob + st.off[0]);
@@ -734,7 +751,7 @@ int fast_plan_alloc_workspace(FastPlan& fp, int wave, size_t* total) {
     *total += n;
     return d;
   };
-  im->d_mags = (float*)alloc(sizeof(float) * (size_t)im->W * im->ldk * wave);
+  im->d_mags = (float*)alloc(sizeof(float) * (size_t)im->W * im->ldk * (wave < FE_SUBWAVE ? wave : FE_SUBWAVE));
   im->d_mnmx = (unsigned*)alloc(sizeof(unsigned) * 2 * wave);
   if (!im->d_mags || !im->d_mnmx) return BN_ERR_CUDA;
   std::vector<int> slots = {im->head_out_slot, im->stem_out_slot};
@@ -1257,8 +1274,9 @@ static size_t pw_smem(const PwParams& P) {
   return ((size_t)KW * GEMM_LDA + (size_t)KW * NP + 3 * NP + 512) * 4;
 }
 
-static int run_body(FastPlan& fp, int mode, const float* src, int Bw, float* d_scores, int rounding, int mean_variant,
-                    cudaStream_t st, int64_t* launches, Profiler* prof) {
+// K2 for chunks [b0, b0 + nb) of the wave: src / mnmx already point at the first of them
+static int run_head(FastPlan& fp, int mode, const float* src, const unsigned* mnmx, int b0, int nb, int rounding, cudaStream_t st,
+                    int64_t* launches, Profiler* prof) {
   FastImpl* im = fp.impl;
   static bool attrs = false;
   if (!attrs) {
@@ -1271,18 +1289,31 @@ static int run_body(FastPlan& fp, int mode, const float* src, int Bw, float* d_s
     attrs = true;
   }
   const int R = rounding;
-  // K2 head
-  int8_t* head_out = (int8_t*)im->slot_buf[im->head_out_slot];
-  {
-    const int grid = Bw * (im->W / HEAD_M);
+  int8_t* head_out = (int8_t*)im->slot_buf[im->head_out_slot] + (size_t)b0 * HEAD_N * im->W;
+  int rc = 0;
+  if (mode == 0 && im->head_tc_ok && fp.use_tc && R == 0 && (fp.fusion & 2)) {
+    if (prof) prof->begin("K2tc_head", st);
+    rc = launch_head_tc(src, mnmx, head_out, nb, im->head_tc, fp.num_sms, st);
+    if (prof) prof->end(st);
+  } else {
+    const int grid = nb * (im->W / HEAD_M);
     if (prof) prof->begin("K2_head", st);
     const bool f = im->head.fast && R == 0;
     const size_t sm = head_smem(im->head);
-    if (mode == 0) { if (f) k_head<0, true><<<grid, 256, sm, st>>>(src, im->d_mnmx, head_out, im->head, im->ldk, R); else k_head<0, false><<<grid, 256, sm, st>>>(src, im->d_mnmx, head_out, im->head, im->ldk, R); }
+    if (mode == 0) { if (f) k_head<0, true><<<grid, 256, sm, st>>>(src, mnmx, head_out, im->head, im->ldk, R); else k_head<0, false><<<grid, 256, sm, st>>>(src, mnmx, head_out, im->head, im->ldk, R); }
     else { if (f) k_head<1, true><<<grid, 256, sm, st>>>(src, nullptr, head_out, im->head, im->ldk, R); else k_head<1, false><<<grid, 256, sm, st>>>(src, nullptr, head_out, im->head, im->ldk, R); }
     if (prof) prof->end(st);
-    (*launches)++;
   }
+  (*launches)++;
+  return rc;
+}
+
+// K3 .. K6 on the whole wave (the head output is in place)
+static int run_body(FastPlan& fp, int Bw, float* d_scores, int rounding, int mean_variant,
+                    cudaStream_t st, int64_t* launches, Profiler* prof) {
+  FastImpl* im = fp.impl;
+  const int R = rounding;
+  int8_t* head_out = (int8_t*)im->slot_buf[im->head_out_slot];
   // K3 stem
   int8_t* stem_out = (int8_t*)im->slot_buf[im->stem_out_slot];
   {
@@ -1353,6 +1384,10 @@ static int run_body(FastPlan& fp, int mode, const float* src, int Bw, float* d_s
   return cudaGetLastError() == cudaSuccess ? 0 : BN_ERR_CUDA;
 }
 
+// The frontend runs in sub-waves: K1 writes the float32 magnitudes of FE_SUBWAVE chunks (69 MB) into the same scratch
+// buffer each time and K2 consumes them straight away, so the 270 KB/chunk intermediate stays in the 126 MB L2
+// instead of making a round trip through HBM.
+
 int fast_run_pcm(FastPlan& fp, const int16_t* d_pcm, const float* d_peak, int Bw, float* d_scores, int rounding,
                  int mean_variant, cudaStream_t st, int64_t* launches, Profiler* prof) {
   FastImpl* im = fp.impl;
@@ -1360,12 +1395,19 @@ int fast_run_pcm(FastPlan& fp, const int16_t* d_pcm, const float* d_peak, int Bw
   int rc = prepare_rounding(fp, rounding);
   if (rc) return rc;
   const bn_blob_header* h = fp.hdr;
-  if (prof) prof->begin("K1_stft", st);
-  rc = launch_stft_mag_fm(d_pcm, d_peak, im->d_mags, im->d_mnmx, Bw, (int)h->chunk_len, (int)h->n_fft, (int)h->hop, im->W, im->ldk, st);
-  if (prof) prof->end(st);
-  if (rc) return rc;
-  *launches += 2;
-  return run_body(fp, 0, im->d_mags, Bw, d_scores, rounding, mean_variant, st, launches, prof);
+  const int T = (int)h->chunk_len;
+  for (int b0 = 0; b0 < Bw; b0 += FE_SUBWAVE) {
+    const int nb = Bw - b0 < FE_SUBWAVE ? Bw - b0 : FE_SUBWAVE;
+    if (prof) prof->begin("K1_stft", st);
+    rc = launch_stft_mag_fm(d_pcm + (size_t)b0 * T, d_peak ? d_peak + b0 : nullptr, im->d_mags, im->d_mnmx + 2 * b0, nb, T, (int)h->n_fft,
+                            (int)h->hop, im->W, im->ldk, st);
+    if (prof) prof->end(st);
+    if (rc) return rc;
+    *launches += 2;
+    rc = run_head(fp, 0, im->d_mags, im->d_mnmx + 2 * b0, b0, nb, rounding, st, launches, prof);
+    if (rc) return rc;
+  }
+  return run_body(fp, Bw, d_scores, rounding, mean_variant, st, launches, prof);
 }
 
 int fast_run_spec(FastPlan& fp, const float* d_spec, int Bw, float* d_scores, int rounding, int mean_variant,
@@ -1374,7 +1416,9 @@ int fast_run_spec(FastPlan& fp, const float* d_spec, int Bw, float* d_scores, in
   if (!im || Bw > fp.wave) return BN_ERR_STATE;
   int rc = prepare_rounding(fp, rounding);
   if (rc) return rc;
-  return run_body(fp, 1, d_spec, Bw, d_scores, rounding, mean_variant, st, launches, prof);
+  rc = run_head(fp, 1, d_spec, nullptr, 0, Bw, rounding, st, launches, prof);
+  if (rc) return rc;
+  return run_body(fp, Bw, d_scores, rounding, mean_variant, st, launches, prof);
 }
 
 }  // namespace bn

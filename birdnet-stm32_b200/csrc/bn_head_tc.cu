@@ -1,0 +1,200 @@
+// bn_head_tc.cu -- K2tc: the head of the hybrid frontend on the tensor core.
+//
+//   raw |STFT| float32 [B][W][ldk] + per-chunk {min, max}
+//     -> normalize() (audio/spectrogram.py:12-21) -> QUANTIZE -> int8 A operand in shared memory
+//     -> tcgen05.mma kind::i8 with the learned mel mixer (1x1 conv 264 -> 64, models/frontend.py:299-345)
+//     -> requant + ReLU -> the PWL magnitude chain (models/magnitude.py:179-192) folded into a per-channel LUT
+//     -> transposed store int8 [B][64][W]
+//
+// A CTA is persistent over tiles of 128 frames.  K = 264 is laid out as two 128-byte-swizzled k-blocks and one
+// 32-byte-swizzled block (K padded to 288 with zero weights): 9 MMAs of 128 x 64 x 32 per tile.
+//
+// QUANTIZE.  The reference computes round((S - min) / (max - min + 1e-10) / scale) with two IEEE divisions
+// (numpy float32) and round-half-away.  The kernel evaluates t = (S - min) * qmul with qmul = 1 / (den * scale)
+// rounded once; t and the two-division chain differ by at most 4 * 2^-24 * 255 = 6.1e-5, so whenever t is
+// farther than 2.5e-4 from a rounding tie both round to the same integer.  Rounding uses the 1.5 * 2^23 magic
+// constant; the (rare) near-tie elements take the exact two-division chain.
+#include "bn_head_tc.cuh"
+
+#include "bn_common.cuh"
+#include "bn_tc.cuh"
+
+namespace bn {
+
+constexpr int HT_THREADS = 256;
+constexpr int HT_M = 128;
+constexpr int HT_A_BYTES = HT_M * HT_KP;            // 36864
+constexpr int HT_OFF_A = HT_B_BYTES;                // 18432 (1024-aligned)
+constexpr int HT_OFF_LUT = HT_OFF_A + HT_A_BYTES;   // 55296
+constexpr int HT_OFF_OUT = HT_OFF_LUT + HT_N * 256; // 71680
+constexpr int HT_OFF_RQ = HT_OFF_OUT + HT_N * HT_M; // 79872
+constexpr int HT_OFF_BAR = HT_OFF_RQ + HT_N * 16;   // 80896
+constexpr int HT_SMEM = HT_OFF_BAR + 16 + 1024;
+
+__device__ __forceinline__ int quant_code(float f, float mn, float den, float qmul, float scale, int zp_bits, int zp) {
+  const float d = f - mn;
+  const float t = d * qmul;
+  const float tm = t + 12582912.0f;
+  const float df = t - (tm - 12582912.0f);
+  int q = __float_as_int(tm) - zp_bits;                 // RNE(t) + zp
+  if (fabsf(df) > 0.49975f) q = (int)roundf(__fdiv_rn(__fdiv_rn(d, den), scale)) + zp;
+  return q;
+}
+
+__global__ void __launch_bounds__(HT_THREADS, 2)
+k_head_tc(const float* __restrict__ mags, const unsigned* __restrict__ mnmx, int8_t* __restrict__ out, int ntiles, HeadTcParams P) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* sB = smem;
+  unsigned char* sA = smem + HT_OFF_A;
+  unsigned char* sLut = smem + HT_OFF_LUT;
+  unsigned char* sOut = smem + HT_OFF_OUT;
+  int4* s_rq = reinterpret_cast<int4*>(smem + HT_OFF_RQ);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + HT_OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 64);
+  if (tid == 32) {
+    mbar_init(smem_u32(mbar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < HT_B_BYTES / 16; i += HT_THREADS) cp_async16(smem_u32(sB + 16 * i), P.w_img + 16 * (size_t)i);
+  for (int i = tid; i < HT_N * 256 / 16; i += HT_THREADS) cp_async16(smem_u32(sLut + 16 * i), P.lut + 16 * (size_t)i);
+  cp_async_commit();
+  if (tid < HT_N) s_rq[tid] = __ldg(P.rq + tid);
+  // third k-block (k = 256 .. 287): bytes past the conv's K stay zero for the whole kernel
+  for (int i = tid; i < HT_M * 32 / 16; i += HT_THREADS) *reinterpret_cast<uint4*>(sA + 2 * HT_M * 128 + 16 * i) = make_uint4(0, 0, 0, 0);
+  cp_async_wait_all();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const uint32_t idesc = make_idesc_i8(HT_M, HT_N);
+  const int halves = P.W / HT_M;
+  const int row_w = P.ldk >> 2;                          // float4 per frame row
+  const int zp_bits = 0x4B400000 - P.q_zp;
+  const unsigned fillb = (unsigned)(uint8_t)P.fill;
+  const int q = warp & 3, hsel = warp >> 2;
+
+  int it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+    const int b = tile / halves, t0 = (tile - b * halves) * HT_M;
+    const float mn = __uint_as_float(__ldg(mnmx + 2 * b)), mx = __uint_as_float(__ldg(mnmx + 2 * b + 1));
+    const float den = (float)((double)(mx - mn) + 1e-10);   // normalize(): numpy scalar promotion (float64 add, float32 result)
+    const float qmul = (float)(1.0 / ((double)den * (double)P.q_scale));
+    const float4* s4 = reinterpret_cast<const float4*>(mags + ((size_t)b * P.W + t0) * P.ldk);
+    // ---- (1) quantise k = 0 .. 255 of 128 frames: 64 float4 per row, 8 independent loads in flight per thread ----
+    for (int base = 0; base < HT_M * 64; base += HT_THREADS * 8) {
+      float4 vv[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int i = base + u * HT_THREADS + tid;
+        vv[u] = __ldg(s4 + (i >> 6) * row_w + (i & 63));
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int i = base + u * HT_THREADS + tid;
+        const int row = i >> 6, k4 = i & 63;
+        const int q0 = quant_code(vv[u].x, mn, den, qmul, P.q_scale, zp_bits, P.q_zp);
+        const int q1 = quant_code(vv[u].y, mn, den, qmul, P.q_scale, zp_bits, P.q_zp);
+        const int q2 = quant_code(vv[u].z, mn, den, qmul, P.q_scale, zp_bits, P.q_zp);
+        const int q3 = quant_code(vv[u].w, mn, den, qmul, P.q_scale, zp_bits, P.q_zp);
+        // k = 4 k4: k-block k4 >> 5, 16-byte chunk (k4 >> 2) & 7 (XOR row & 7), word k4 & 3
+        const int off = (k4 >> 5) * (HT_M * 128) + row * 128 + (((((k4 >> 2) & 7) ^ (row & 7)) << 4)) + ((k4 & 3) << 2);
+        *reinterpret_cast<unsigned*>(sA + off) = pack4_sat(q0, q1, q2, q3);
+      }
+    }
+    // k = 256 .. 263: one real bin (K_real = 257) and the FILL columns of the CONCAT
+    if (tid < HT_M) {
+      const int row = tid;
+      const float* fr = mags + ((size_t)b * P.W + t0 + row) * P.ldk;
+      unsigned w[2] = {0, 0};
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const int k = 256 + j;
+        unsigned code = fillb;
+        if (k < P.K_real) {
+          int qv = quant_code(__ldg(fr + k), mn, den, qmul, P.q_scale, zp_bits, P.q_zp);
+          qv = max(-128, min(127, qv));
+          code = (unsigned)(uint8_t)qv;
+        }
+        if (k >= P.ldk) code = 0;
+        w[j >> 2] |= code << (8 * (j & 3));
+      }
+      // SW32 block: 16-byte chunk 0 XOR (row >> 2) & 1
+      *reinterpret_cast<uint2*>(sA + 2 * HT_M * 128 + row * 32 + ((((row >> 2) & 1)) << 4)) = make_uint2(w[0], w[1]);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    // ---- (2) 9 MMAs: D[128 frames][64 mel] ----------------------------------------------------------------
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
+#pragma unroll
+      for (int ks = 0; ks < 8; ks++) {
+        const int h = ks >> 2, kk = ks & 3;
+        umma_i8(tmem_base, make_desc(a_addr + h * (HT_M * 128) + kk * 32, 1024, 2u),
+                make_desc(b_addr + h * (HT_N * 128) + kk * 32, 1024, 2u), idesc, ks > 0 ? 1u : 0u);
+      }
+      umma_i8(tmem_base, make_desc(a_addr + 2 * HT_M * 128, 256, 6u), make_desc(b_addr + 2 * HT_N * 128, 256, 6u), idesc, 1u);
+      umma_commit(smem_u32(mbar));
+    }
+    mbar_wait(smem_u32(mbar), (uint32_t)(it & 1));
+    tc_fence_after();
+    // ---- (3) epilogue: requant + ReLU, folded PWL LUT, transpose through shared memory ---------------------
+#pragma unroll
+    for (int g = 0; g < 2; g++) {
+      const int c0 = hsel * 32 + g * 16;
+      int v[16];
+      tmem_ld16(tmem_base + (uint32_t)c0 + ((uint32_t)(32 * q) << 16), v);
+#pragma unroll
+      for (int j = 0; j < 16; j++) {
+        const int c = c0 + j;
+        const int4 rq = s_rq[c];
+        int y = rq_hi(v[j], rq.x, rq.y, rq.z) >> rq.w;
+        y = max(-128, min(127, y));
+        sOut[c * HT_M + 32 * q + lane] = sLut[c * 256 + y + 128];
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+    int8_t* ob = out + (size_t)b * HT_N * P.W + t0;
+    for (int i = tid; i < HT_N * HT_M / 16; i += HT_THREADS) {
+      const int c = i >> 3, piece = i & 7;
+      *reinterpret_cast<uint4*>(ob + (size_t)c * P.W + 16 * piece) = *reinterpret_cast<const uint4*>(sOut + c * HT_M + 16 * piece);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 64);
+}
+
+// K-major swizzled image of the mixer weights w[64][K] (K <= 288): k-blocks 0 and 1 are 64 rows x 128 bytes with the
+// 128-byte swizzle (16-byte chunk ^= row & 7), block 2 is 64 rows x 32 bytes with the 32-byte swizzle (chunk ^= (row >> 2) & 1).
+void head_tc_weight_image(const int8_t* w, int K, std::vector<uint8_t>& img) {
+  img.assign(HT_B_BYTES, 0);
+  for (int n = 0; n < HT_N; n++)
+    for (int k = 0; k < K && k < HT_KP; k++) {
+      size_t off;
+      if (k < 256) off = (size_t)(k >> 7) * (HT_N * 128) + (size_t)n * 128 + (((((k & 127) >> 4) ^ (n & 7))) << 4) + (k & 15);
+      else off = (size_t)2 * HT_N * 128 + (size_t)n * 32 + (((((k & 31) >> 4) ^ ((n >> 2) & 1))) << 4) + (k & 15);
+      img[off] = (uint8_t)w[(size_t)n * K + k];
+    }
+}
+
+int launch_head_tc(const float* mags, const unsigned* mnmx, int8_t* out, int Bw, const HeadTcParams& P, int num_sms, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(k_head_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_SMEM); attr = true; }
+  if (P.W % HT_M || (P.ldk != 260 && P.ldk != 264) || P.K_real != 257) return BN_ERR_UNSUPPORTED;
+  const int ntiles = Bw * (P.W / HT_M);
+  int grid = num_sms * 2;
+  if (grid > ntiles) grid = ntiles;
+  if (grid < 1) return 0;
+  k_head_tc<<<grid, HT_THREADS, HT_SMEM, st>>>(mags, mnmx, out, ntiles, P);
+  return 0;
+}
+
+}  // namespace bn
