@@ -70,170 +70,168 @@ __device__ __forceinline__ void fft16(float2 (&v)[16]) {
 }
 
 // dynamic smem layout:
-//   float2 tw512[512]                       4 KB   exp(-2 pi i m / 512)
-//   float  win[512]                         2 KB   periodic Hann
-//   float  xs[span]                         span = 31*hop + 512 floats
+//   float  xs[span + 16]                    span = 31*hop + 512 floats (16-byte aligned, indexed like the global buffer)
 //   float2 zbuf[16][256+16]                 per half-warp exchange buffer (padded)
-//   float  tile[257][33]                    magnitude tile
+//   float  tile[257][33]                    magnitude tile (bin-major variant only)
 //   float  red[2*8]
+//
+// The CTA is persistent over (chunk, 32-frame group) tiles.  Everything a thread needs that does not depend on the
+// data -- its 32 window samples (pre-scaled by 1/2 for the real-FFT split), the 15 inter-pass twiddles W256^(l k1) and
+// the 8 split twiddles W512^(l + 16 j) -- is loaded once into registers and reused for every frame.
 template <bool FRAME_MAJOR>
-__global__ void __launch_bounds__(FE_THREADS)
+__global__ void __launch_bounds__(FE_THREADS, 2)
 k_stft_mag(const int16_t* __restrict__ pcm, const float* __restrict__ peak, float* __restrict__ out,
-           unsigned* __restrict__ mnmx, const float4* __restrict__ tables, int T, int hop, int W, int ldk) {
+           unsigned* __restrict__ mnmx, const float4* __restrict__ tables, int T, int hop, int W, int ldk, int B) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int span = (FRAMES_PER_CTA - 1) * hop + NFFT;
-  float2* tw512 = reinterpret_cast<float2*>(smem_raw);
-  float* win = reinterpret_cast<float*>(tw512 + NFFT);
-  float* xs = win + NFFT;
-  float2* zbuf = reinterpret_cast<float2*>(xs + ((span + 3) & ~3));
+  float* xs = reinterpret_cast<float*>(smem_raw);
+  float2* zbuf = reinterpret_cast<float2*>(xs + ((span + 16 + 3) & ~3));
   float* tile = reinterpret_cast<float*>(zbuf + 16 * (NC + 16));
   float* red = FRAME_MAJOR ? tile : tile + BINS * TILE_LD;
 
   const int tid = threadIdx.x;
-  const int b = blockIdx.y;
-  const int t0 = blockIdx.x * FRAMES_PER_CTA;
-
-  // tables (computed once on the host in double precision): tw512[512] float2 followed by win[512] float
-  for (int m = tid; m < (NFFT * 2 + NFFT) / 4; m += FE_THREADS) reinterpret_cast<float4*>(smem_raw)[m] = __ldg(tables + m);
-
-  // stage samples [s0, s0 + span) of chunk b, zero outside [0, T)
-  const float pk = peak ? peak[b] : 0.0f;
-  const long chunk_base = (long)b * T;
-  const long s0 = (long)t0 * hop - NFFT / 2;           // first sample (chunk-relative), may be < 0
-  {
-    // 32-bit loads over global sample pairs; g = global sample index (even)
-    const long g_lo = chunk_base + s0;
-    const long g_first = g_lo & ~1L;                    // floor to even (g_lo may be negative only if b == 0)
-    const unsigned* p32 = reinterpret_cast<const unsigned*>(pcm);
-    const long total = (long)gridDim.y * T;             // samples in the whole buffer
-    const int npairs = (int)(((g_lo + span + 1) - g_first + 1) / 2);
-    // batches of 8 independent 32-bit loads per thread (memory-level parallelism), then decode
-    for (int base = 0; base < npairs; base += FE_THREADS * 8) {
-      unsigned wv[8];
-#pragma unroll
-      for (int u = 0; u < 8; u++) {
-        const int w = base + u * FE_THREADS + tid;
-        const long g = g_first + 2L * w;
-        unsigned word = 0;
-        if (w < npairs) {
-          if (g >= 0 && g + 1 < total) word = __ldg(p32 + (g >> 1));
-          else if (g >= 0 && g < total) word = (unsigned)(unsigned short)pcm[g];
-        }
-        wv[u] = word;
-      }
-#pragma unroll
-      for (int u = 0; u < 8; u++) {
-        const int w = base + u * FE_THREADS + tid;
-        if (w >= npairs) continue;
-        const long g = g_first + 2L * w;
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-          const long gs = g + h;
-          const long rel = gs - chunk_base;               // chunk-relative sample index
-          const long li = gs - g_lo;                      // index into xs
-          if (li >= 0 && li < span) {
-            float v = 0.0f;
-            if (rel >= 0 && rel < T) {
-              const short sv = (short)(h ? (wv[u] >> 16) : (wv[u] & 0xffffu));
-              v = (float)sv * (1.0f / 32768.0f);          // exact (power of two)
-              if (pk > 0.0f) v = __fdiv_rn(v, pk);        // y / peak, float32 (audio/io.py:124-126)
-            }
-            xs[li] = v;
-          }
-        }
-      }
-    }
-  }
-  __syncthreads();
-
   const int hw = tid >> 4;        // half-warp id 0..15
   const int l = tid & 15;         // lane within the half-warp = n2 (pass 1) / k1 (pass 2)
   float2* zb = zbuf + hw * (NC + 16);
   const unsigned hmask = 0xffffu << (16 * ((tid >> 4) & 1));
 
-  float lmin = __int_as_float(0x7f800000), lmax = 0.0f;
+  // per-thread constants (tables: tw512[512] float2 followed by win[512] float, computed on the host in double)
+  const float2* tw512 = reinterpret_cast<const float2*>(tables);
+  const float2* win2 = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(tables) + 2 * NFFT);
+  float wre[16], wim[16];
+#pragma unroll
+  for (int n1 = 0; n1 < 16; n1++) {
+    const float2 w2 = __ldg(win2 + 16 * n1 + l);
+    wre[n1] = 0.5f * w2.x; wim[n1] = 0.5f * w2.y;
+  }
+  float2 twp[16];
+#pragma unroll
+  for (int k1 = 1; k1 < 16; k1++) twp[k1] = __ldg(tw512 + ((2 * l * k1) & 511));
+  float2 tws[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) tws[j] = __ldg(tw512 + l + 16 * j);
 
-#pragma unroll 1
-  for (int round = 0; round < FRAMES_PER_CTA / 16; round++) {
-    const int f = round * 16 + hw;                      // frame within the tile
-    const float* xf = xs + f * hop;                     // 512 samples of this frame
-    // pass 1: thread n2 = l takes z[16*n1 + l], n1 = 0..15, z[n] = x[2n] + i x[2n+1] (windowed)
-    float2 v[16];
+  // the PCM pointer is only known to be 2-byte aligned: index samples relative to its 16-byte-aligned floor
+  const int a0 = (int)((reinterpret_cast<uintptr_t>(pcm) >> 1) & 7);
+  const int16_t* pcm_al = pcm - a0;
+  const long total = (long)B * T;
+  const int groups_w = W / FRAMES_PER_CTA;
+  const int ntiles = B * groups_w;
+
+  for (int tile_id = blockIdx.x; tile_id < ntiles; tile_id += gridDim.x) {
+    const int b = tile_id / groups_w;
+    const int t0 = (tile_id - b * groups_w) * FRAMES_PER_CTA;
+    // ---- stage samples [s0, s0 + span) of chunk b as float32, zero outside [0, T) -------------------------------
+    const float pk = peak ? __ldg(peak + b) : 0.0f;
+    // y = (s / 32768) / peak (audio/io.py:114-126) as one multiply by the rounded reciprocal (<= 1.5 ulp from the reference)
+    const float cs = pk > 0.0f ? __fdiv_rn(1.0f, 32768.0f * pk) : (1.0f / 32768.0f);
+    const long chunk_base = (long)b * T + a0;             // in pcm_al sample indices
+    const long g_lo = chunk_base + (long)t0 * hop - NFFT / 2;
+    const long g_first = g_lo & ~7L;
+    const int shift = (int)(g_lo - g_first);
+    const int ngroups = (shift + span + 7) >> 3;
+    for (int grp = tid; grp < ngroups; grp += FE_THREADS) {
+      const long g = g_first + 8L * grp;
+      const long rel = g - chunk_base;                    // chunk-relative index of the group's first sample
+      uint4 wv = make_uint4(0, 0, 0, 0);
+      const bool inside = rel >= 0 && rel + 8 <= T;
+      if (inside && g >= a0 && g + 8 <= a0 + total) {
+        wv = __ldg(reinterpret_cast<const uint4*>(pcm_al + g));
+      } else {
+        unsigned short sv[8];
 #pragma unroll
-    for (int n1 = 0; n1 < 16; n1++) {
-      const int n = 16 * n1 + l;
-      const float2 x2 = make_float2(xf[2 * n], xf[2 * n + 1]);
-      const float2 w2 = *reinterpret_cast<const float2*>(win + 2 * n);
-      v[n1] = make_float2(x2.x * w2.x, x2.y * w2.y);
-    }
-    fft16(v);                                           // over n1 -> k1
-    // twiddle W256^(l*k1) = tw512[2*l*k1], then transpose through smem: zb[k1*17 + n2]... use [k1][n2]
-#pragma unroll
-    for (int k1 = 0; k1 < 16; k1++) {
-      float2 t = v[k1];
-      if (k1 != 0 && l != 0) t = cmul(t, tw512[(2 * l * k1) & 511]);
-      zb[k1 * 17 + l] = t;
-    }
-    __syncwarp(hmask);
-    // pass 2: thread k1 = l reads B[n2] = zb[l][n2]
-#pragma unroll
-    for (int n2 = 0; n2 < 16; n2++) v[n2] = zb[l * 17 + n2];
-    __syncwarp(hmask);
-    fft16(v);                                           // over n2 -> k2 ; Z[k1 + 16 k2] = v[k2]
-#pragma unroll
-    for (int k2 = 0; k2 < 16; k2++) zb[l + 16 * k2] = v[k2];   // natural order Z[0..255]
-    __syncwarp(hmask);
-    // real-FFT split, two bins per step: with E = (Z[k] + conj(Z[N-k]))/2, O = (Z[k] - conj(Z[N-k]))/(2i) and
-    // T = W512^k O:   X[k] = E + T   and   X[N-k] = conj(E - T)   (N = 256), so |X[N-k]| = |E - T|.
-    const bool fok = t0 + f < W;
-    auto emit = [&](int k, float mag) {
-      if (fok) {
-        if (FRAME_MAJOR) out[((long)b * W + t0 + f) * ldk + k] = mag;   // 16 lanes -> 64 contiguous bytes
-        else tile[k * TILE_LD + f] = mag;
-        lmin = fminf(lmin, mag);
-        lmax = fmaxf(lmax, mag);
+        for (int j = 0; j < 8; j++) {
+          const long r = rel + j;
+          sv[j] = (r >= 0 && r < T) ? (unsigned short)pcm_al[g + j] : (unsigned short)0;
+        }
+        wv = make_uint4(sv[0] | ((unsigned)sv[1] << 16), sv[2] | ((unsigned)sv[3] << 16), sv[4] | ((unsigned)sv[5] << 16), sv[6] | ((unsigned)sv[7] << 16));
       }
-    };
+      const unsigned ww[4] = {wv.x, wv.y, wv.z, wv.w};
+      float fv[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-      const int k = l + 16 * j;                       // 0..127, partner bin 256 - k
-      const float2 zk = zb[k];
-      const float2 zn = zb[(NC - k) & 255];
-      const float2 e = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
-      const float2 o = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
-      const float2 t = cmul(o, tw512[k]);
-      const float ar = e.x + t.x, ai = e.y + t.y, br = e.x - t.x, bi = e.y - t.y;
-      emit(k, fast_sqrt(ar * ar + ai * ai));
-      emit(NC - k, fast_sqrt(br * br + bi * bi));
+      for (int j = 0; j < 4; j++) {
+        // int16 -> float32 through the 1.5 * 2^23 magic constant (exact), then the scale
+        const int lo = (int)(short)(ww[j] & 0xffffu), hi = (int)ww[j] >> 16;
+        fv[2 * j] = (__int_as_float(0x4B400000 + lo) - 12582912.0f) * cs;
+        fv[2 * j + 1] = (__int_as_float(0x4B400000 + hi) - 12582912.0f) * cs;
+      }
+      *reinterpret_cast<float4*>(xs + 8 * grp) = make_float4(fv[0], fv[1], fv[2], fv[3]);
+      *reinterpret_cast<float4*>(xs + 8 * grp + 4) = make_float4(fv[4], fv[5], fv[6], fv[7]);
     }
-    if (l == 0) {                                     // bin 128 pairs with itself: |X[128]| = |Z[128]|
-      const float2 z = zb[128];
-      emit(128, fast_sqrt(z.x * z.x + z.y * z.y));
-    }
-    __syncwarp(hmask);
-  }
+    __syncthreads();
 
-  // CTA reduction of min / max
+    float lmin = __int_as_float(0x7f800000), lmax = 0.0f;
+#pragma unroll 1
+    for (int round = 0; round < FRAMES_PER_CTA / 16; round++) {
+      const int f = round * 16 + hw;                      // frame within the tile
+      const float* xf = xs + shift + f * hop + 2 * l;     // sample 2 n of this frame for n = l
+      // pass 1: thread n2 = l takes z[16*n1 + l], n1 = 0..15, z[n] = x[2n] + i x[2n+1] (windowed, pre-scaled by 1/2)
+      float2 v[16];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
-    lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
-  }
-  if ((tid & 31) == 0) { red[tid >> 5] = lmin; red[8 + (tid >> 5)] = lmax; }
-  __syncthreads();
-  if (tid == 0) {
-    float mn = red[0], mx = red[8];
-    for (int i = 1; i < 8; i++) { mn = fminf(mn, red[i]); mx = fmaxf(mx, red[8 + i]); }
-    atomicMin(mnmx + 2 * b, __float_as_uint(mn));
-    atomicMax(mnmx + 2 * b + 1, __float_as_uint(mx));
-  }
+      for (int n1 = 0; n1 < 16; n1++) v[n1] = make_float2(xf[32 * n1] * wre[n1], xf[32 * n1 + 1] * wim[n1]);
+      fft16(v);                                           // over n1 -> k1
+      // twiddle W256^(l*k1), then transpose through smem
+      zb[l] = v[0];
+#pragma unroll
+      for (int k1 = 1; k1 < 16; k1++) zb[k1 * 17 + l] = cmul(v[k1], twp[k1]);
+      __syncwarp(hmask);
+      // pass 2: thread k1 = l reads B[n2] = zb[l][n2]
+#pragma unroll
+      for (int n2 = 0; n2 < 16; n2++) v[n2] = zb[l * 17 + n2];
+      __syncwarp(hmask);
+      fft16(v);                                           // over n2 -> k2 ; Z[k1 + 16 k2] = v[k2]
+#pragma unroll
+      for (int k2 = 0; k2 < 16; k2++) zb[l + 16 * k2] = v[k2];   // natural order Z[0..255]
+      __syncwarp(hmask);
+      // real-FFT split, two bins per step: with E = Z[k] + conj(Z[N-k]), O = (Z[k] - conj(Z[N-k])) / i (Z carries the
+      // factor 1/2) and T = W512^k O:   X[k] = E + T   and   X[N-k] = conj(E - T)   (N = 256), so |X[N-k]| = |E - T|.
+      float* orow = FRAME_MAJOR ? out + ((long)b * W + t0 + f) * ldk : tile + f;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const int k = l + 16 * j;                         // 0..127, partner bin 256 - k
+        const float2 zk = zb[k];
+        const float2 zn = zb[(NC - k) & 255];
+        const float2 e = make_float2(zk.x + zn.x, zk.y - zn.y);
+        const float2 o = make_float2(zk.y + zn.y, zn.x - zk.x);
+        const float2 t = cmul(o, tws[j]);
+        const float ar = e.x + t.x, ai = e.y + t.y, br = e.x - t.x, bi = e.y - t.y;
+        const float ma = fast_sqrt(ar * ar + ai * ai), mb = fast_sqrt(br * br + bi * bi);
+        if (FRAME_MAJOR) { orow[k] = ma; orow[NC - k] = mb; }   // 16 lanes -> 64 contiguous bytes each
+        else { orow[k * TILE_LD] = ma; orow[(NC - k) * TILE_LD] = mb; }
+        lmin = fminf(lmin, fminf(ma, mb));
+        lmax = fmaxf(lmax, fmaxf(ma, mb));
+      }
+      if (l == 0) {                                       // bin 128 pairs with itself: |X[128]| = 2 |Z[128]|
+        const float2 z = zb[128];
+        const float m = 2.0f * fast_sqrt(z.x * z.x + z.y * z.y);
+        if (FRAME_MAJOR) orow[128] = m; else orow[128 * TILE_LD] = m;
+        lmin = fminf(lmin, m);
+        lmax = fmaxf(lmax, m);
+      }
+      __syncwarp(hmask);
+    }
 
-  if (FRAME_MAJOR) return;
-  // write the tile bin-major: out[b][k][t0 + f], 32 consecutive floats per bin row
-  float* ob = out + (long)b * BINS * W;
-  const int lane = tid & 31, wp = tid >> 5;
-  for (int k = wp; k < BINS; k += FE_THREADS / 32) {
-    if (t0 + lane < W) ob[(long)k * W + t0 + lane] = tile[k * TILE_LD + lane];
+    // CTA reduction of min / max
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+      lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+    }
+    if ((tid & 31) == 0) { red[tid >> 5] = lmin; red[8 + (tid >> 5)] = lmax; }
+    __syncthreads();                                      // also: every warp is done with xs / zbuf / tile writes
+    if (tid == 0) {
+      float mn = red[0], mx = red[8];
+      for (int i = 1; i < 8; i++) { mn = fminf(mn, red[i]); mx = fmaxf(mx, red[8 + i]); }
+      atomicMin(mnmx + 2 * b, __float_as_uint(mn));
+      atomicMax(mnmx + 2 * b + 1, __float_as_uint(mx));
+    }
+    if (!FRAME_MAJOR) {
+      // write the tile bin-major: out[b][k][t0 + f], 32 consecutive floats per bin row
+      float* ob = out + (long)b * BINS * W;
+      const int lane = tid & 31, wp = tid >> 5;
+      for (int k = wp; k < BINS; k += FE_THREADS / 32) ob[(long)k * W + t0 + lane] = tile[k * TILE_LD + lane];
+    }
+    __syncthreads();                                      // red / tile are free for the next tile
   }
 }
 
@@ -264,10 +262,22 @@ static const float4* stft_tables() {
 
 size_t stft_smem_bytes(int hop, bool frame_major) {
   const int span = (FRAMES_PER_CTA - 1) * hop + NFFT;
-  size_t b = sizeof(float2) * NFFT + sizeof(float) * NFFT + sizeof(float) * ((span + 3) & ~3);
+  size_t b = sizeof(float) * ((span + 16 + 3) & ~3);
   b += sizeof(float2) * 16 * (NC + 16) + sizeof(float) * 16;
   b += frame_major ? 0 : sizeof(float) * BINS * TILE_LD;
   return b;
+}
+
+// persistent grid: as many CTAs as fit (2 per SM by registers, fewer if the staged span is large)
+static int stft_grid(int B, int W, size_t smem) {
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  int per = (int)((227 * 1024) / (smem + 1024));
+  if (per > 2) per = 2;
+  if (per < 1) per = 1;
+  const int ntiles = B * (W / FRAMES_PER_CTA);
+  const int g = sms * per;
+  return g < ntiles ? g : ntiles;
 }
 
 int launch_stft_mag(const int16_t* pcm, const float* peak, float* out, unsigned* mnmx, int B, int T, int n_fft,
@@ -283,9 +293,9 @@ int launch_stft_mag(const int16_t* pcm, const float* peak, float* out, unsigned*
   }
   const float4* tab = stft_tables();
   if (!tab) return BN_ERR_CUDA;
+  if (W % FRAMES_PER_CTA) return BN_ERR_UNSUPPORTED;
   k_init_minmax<<<(B + 255) / 256, 256, 0, st>>>(mnmx, B);
-  dim3 grid((W + FRAMES_PER_CTA - 1) / FRAMES_PER_CTA, B);
-  k_stft_mag<false><<<grid, FE_THREADS, smem, st>>>(pcm, peak, out, mnmx, tab, T, hop, W, 0);
+  k_stft_mag<false><<<stft_grid(B, W, smem), FE_THREADS, smem, st>>>(pcm, peak, out, mnmx, tab, T, hop, W, 0, B);
   return 0;
 }
 
@@ -303,9 +313,9 @@ int launch_stft_mag_fm(const int16_t* pcm, const float* peak, float* out, unsign
   }
   const float4* tab = stft_tables();
   if (!tab) return BN_ERR_CUDA;
+  if (W % FRAMES_PER_CTA) return BN_ERR_UNSUPPORTED;
   k_init_minmax<<<(B + 255) / 256, 256, 0, st>>>(mnmx, B);
-  dim3 grid((W + FRAMES_PER_CTA - 1) / FRAMES_PER_CTA, B);
-  k_stft_mag<true><<<grid, FE_THREADS, smem, st>>>(pcm, peak, out, mnmx, tab, T, hop, W, ldk);
+  k_stft_mag<true><<<stft_grid(B, W, smem), FE_THREADS, smem, st>>>(pcm, peak, out, mnmx, tab, T, hop, W, ldk, B);
   return 0;
 }
 
