@@ -46,35 +46,41 @@ k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles
   const int C = P.C, CG = C >> 2, N = P.N, KP = P.KP, RW = P.RW;
   const int TW = P.iw + P.pl + 1;                     // tile columns (left halo only when pad_left = 1)
   const int b_bytes = N * KP, a_bytes = P.MT * 128 * KP;
-  const int tile_bytes = P.NB * TRIN * TW * C;
+  const int tile_bytes = (P.NB * TRIN * TW * C + 15) & ~15;
+  const int NST = P.nst;                              // input-tile buffers: 1 = unpipelined, 2 / 3 = prefetch distance 1 / 2
+  const int NAB = NST > 1 ? 2 : 1;                    // A-operand and TMEM accumulator buffers
   unsigned char* sB = smem;
-  unsigned char* sA = sB + b_bytes;
-  unsigned char* sT = sA + a_bytes;
-  int4* s_rq = reinterpret_cast<int4*>(sT + ((tile_bytes + 15) & ~15));
+  unsigned char* sA0 = sB + b_bytes;
+  unsigned char* sT0 = sA0 + NAB * a_bytes;
+  int4* s_rq = reinterpret_cast<int4*>(sT0 + NST * tile_bytes);
   int* s_rz = reinterpret_cast<int*>(s_rq + N);
   uint64_t* mbar = reinterpret_cast<uint64_t*>(s_rz + ((N + 1) & ~1));
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2);
 
   // ---- one-time setup ---------------------------------------------------------------------------
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), (uint32_t)P.tmem_cols);
   if (tid == 32) {
-    mbar_init(smem_u32(mbar), 1);
+    mbar_init(smem_u32(&mbar[0]), 1);
+    mbar_init(smem_u32(&mbar[1]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = tid; i < b_bytes / 16; i += DS_THREADS) cp_async16(smem_u32(sB + 16 * i), P.w_img + 16 * (size_t)i);
   cp_async_commit();
   for (int i = tid; i < N; i += DS_THREADS) { s_rq[i] = __ldg(P.pw_rq + i); s_rz[i] = __ldg(P.pw_rz + i); }
-  if (P.C < KP) for (int i = tid; i < a_bytes / 16; i += DS_THREADS) *reinterpret_cast<uint4*>(sA + 16 * i) = make_uint4(0, 0, 0, 0);
+  if (P.C < KP) for (int i = tid; i < NAB * a_bytes / 16; i += DS_THREADS) *reinterpret_cast<uint4*>(sA0 + 16 * i) = make_uint4(0, 0, 0, 0);
   const unsigned zpw = 0x01010101u * (unsigned)(uint8_t)P.dw_in_zp;
   {  // halo columns hold the zero point for the whole kernel (cp.async never touches them)
     const int rows = P.NB * TRIN;
     const int wpc = C >> 2;                           // words per pixel
-    for (int i = tid; i < rows * wpc * 2; i += DS_THREADS) {
-      const int side = i & 1, rest = i >> 1;
-      const int row = rest / wpc, w = rest - row * wpc;
-      if (side == 0 && P.pl == 0) continue;
-      const int col = side ? TW - 1 : 0;
-      reinterpret_cast<unsigned*>(sT)[(row * TW + col) * wpc + w] = zpw;
+    for (int sb = 0; sb < NST; sb++) {
+      unsigned* tw = reinterpret_cast<unsigned*>(sT0 + sb * tile_bytes);
+      for (int i = tid; i < rows * wpc * 2; i += DS_THREADS) {
+        const int side = i & 1, rest = i >> 1;
+        const int row = rest / wpc, w = rest - row * wpc;
+        if (side == 0 && P.pl == 0) continue;
+        const int col = side ? TW - 1 : 0;
+        tw[(row * TW + col) * wpc + w] = zpw;
+      }
     }
   }
   // per-thread depthwise constants: the channel group of a thread is the same for all of its strips
@@ -107,12 +113,15 @@ k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles
   const int ppr = (P.iw * C) >> 4;                    // 16-byte pieces per input row
   const int nstrips = P.NB * P.ow * CG;
 
-  int it = 0;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
-    int b0, oy0;
+  auto tile_origin = [&](int tile, int& b0, int& oy0) {
     if (P.NB == 1) { b0 = tile / tiles_per_chunk; oy0 = (tile - b0 * tiles_per_chunk) * TR; }
     else { b0 = tile * P.NB; oy0 = 0; }
-    // ---- (1) stage input rows ------------------------------------------------------------------
+  };
+
+  // ---- (1) stage the input rows of a tile (cp.async; SAME padding rows = zero-point bytes) ---------------------
+  auto stage = [&](int tile, unsigned char* sT) {
+    int b0, oy0;
+    tile_origin(tile, b0, oy0);
     for (int row = warp; row < P.NB * TRIN; row += DS_THREADS / 32) {
       const int bb = row / TRIN, tr = row - bb * TRIN;
       const int iy = oy0 * S - P.pt + tr;
@@ -122,10 +131,10 @@ k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles
       if (ok) { for (int p = lane; p < ppr; p += 32) cp_async16(smem_u32(dst + 16 * p), src + 16 * p); }
       else { for (int p = lane; p < ppr; p += 32) *reinterpret_cast<uint4*>(dst + 16 * p) = make_uint4(zpw, zpw, zpw, zpw); }
     }
-    cp_async_commit();
-    cp_async_wait_all();
-    __syncthreads();
-    // ---- (2) depthwise 3x3 -> A operand ------------------------------------------------------------
+  };
+
+  // ---- (2) depthwise 3x3 -> swizzled A operand --------------------------------------------------------------------
+  auto depthwise = [&](const unsigned char* sT, unsigned char* sA) {
     for (int sidx = tid; sidx < nstrips; sidx += DS_THREADS) {
       const int rest = sidx >> P.cg_log;
       const int ox = rest & (P.ow - 1), bb = rest >> P.ow_log;
@@ -165,26 +174,27 @@ k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles
         }
       }
     }
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    // ---- (3) pointwise conv on the tensor core -------------------------------------------------------
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
-      for (int j = 0; j < P.MT; j++) {
-        for (int ks = 0; ks < ksteps; ks++) {
-          const int h = ks / ksteps_per_half, kk = ks - h * ksteps_per_half;
-          const uint64_t ad = make_desc(a_addr + j * (128 * KP) + h * (128 * RW) + kk * 32, sbo, lt);
-          const uint64_t bd = make_desc(b_addr + h * (N * RW) + kk * 32, sbo, lt);
-          umma_i8(tmem_base + (uint32_t)(j * N), ad, bd, idesc, ks > 0 ? 1u : 0u);
-        }
-      }
-      umma_commit(smem_u32(mbar));
-    }
-    mbar_wait(smem_u32(mbar), (uint32_t)(it & 1));
+  };
+
+  // ---- (3) pointwise conv on the tensor core (one thread) -------------------------------------------------------
+  auto issue_mma = [&](const unsigned char* sA, uint32_t tmem_d, uint64_t* bar) {
     tc_fence_after();
-    // ---- (4) epilogue ------------------------------------------------------------------------------------
+    const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
+    for (int j = 0; j < P.MT; j++) {
+      for (int ks = 0; ks < ksteps; ks++) {
+        const int h = ks / ksteps_per_half, kk = ks - h * ksteps_per_half;
+        const uint64_t ad = make_desc(a_addr + j * (128 * KP) + h * (128 * RW) + kk * 32, sbo, lt);
+        const uint64_t bd = make_desc(b_addr + h * (N * RW) + kk * 32, sbo, lt);
+        umma_i8(tmem_d + (uint32_t)(j * N), ad, bd, idesc, ks > 0 ? 1u : 0u);
+      }
+    }
+    umma_commit(smem_u32(bar));
+  };
+
+  // ---- (4) epilogue: TMEM -> requant (+ residual ADD from the shared-memory input tile) -> global ---------------
+  auto epilogue = [&](int tile, const unsigned char* sT, uint32_t tmem_d) {
+    int b0, oy0;
+    tile_origin(tile, b0, oy0);
     const size_t pix0 = ((size_t)b0 * P.oh + oy0) << P.ow_log;
     for (int t = hsel; t < P.MT * NG; t += 2) {
       const int j = t / NG, g = t - j * NG;
@@ -192,7 +202,7 @@ k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles
       const int bb = m >> P.trow_log;
       const bool ok = (b0 + bb) < Bw;
       int v[16];
-      tmem_ld16(tmem_base + (uint32_t)(j * N + 16 * g) + ((uint32_t)(32 * q) << 16), v);
+      tmem_ld16(tmem_d + (uint32_t)(j * N + 16 * g) + ((uint32_t)(32 * q) << 16), v);
       uint4 rv = make_uint4(0, 0, 0, 0);
       if (ADD) {
         const int rem = m & ((1 << P.trow_log) - 1);
@@ -234,9 +244,69 @@ k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles
       }
       if (ok) *reinterpret_cast<uint4*>(out + (pix0 + m) * N + 16 * g) = make_uint4(ow4[0], ow4[1], ow4[2], ow4[3]);
     }
-    tc_fence_before();
-    __syncthreads();                                 // TMEM drained, input tile and A operand free
+  };
+
+  if (NST == 1) {
+    // ---- unpipelined: stage -> depthwise -> MMA -> epilogue per tile --------------------------------------------
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+      stage(tile, sT0);
+      cp_async_commit();
+      cp_async_wait_all();
+      __syncthreads();
+      depthwise(sT0, sA0);
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) issue_mma(sA0, tmem_base, &mbar[0]);
+      mbar_wait(smem_u32(&mbar[0]), (uint32_t)(it & 1));
+      tc_fence_after();
+      epilogue(tile, sT0, tmem_base);
+      tc_fence_before();
+      __syncthreads();                                 // TMEM drained, input tile and A operand free
+    }
+  } else {
+    // ---- software pipeline over this CTA's tiles t_k = blockIdx.x + k * gridDim.x ------------------------------
+    //   iteration k:  cp.async(tile k + NST - 1)  |  depthwise(k + 1) -> A[(k+1)&1], MMA(k + 1) -> TMEM[(k+1)&1]  |
+    //                 wait MMA(k), epilogue(k)
+    // so the global->shared copies have NST - 1 iterations to land and every MMA runs under the next tile's depthwise.
+    const int nk = blockIdx.x < ntiles ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    const int accw = P.MT * N;                         // TMEM columns per accumulator buffer
+    auto tile_of = [&](int k) { return blockIdx.x + k * gridDim.x; };
+    for (int k = 0; k < NST - 1; k++) {
+      if (k < nk) stage(tile_of(k), sT0 + (k % NST) * tile_bytes);
+      cp_async_commit();
+    }
+    if (nk > 0) {
+      if (NST == 2) cp_async_wait_all(); else asm volatile("cp.async.wait_group 1;" ::: "memory");
+      __syncthreads();
+      depthwise(sT0, sA0);
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) issue_mma(sA0, tmem_base, &mbar[0]);
+    }
+    for (int k = 0; k < nk; k++) {
+      const int ab = k & 1;
+      if (k + NST - 1 < nk) stage(tile_of(k + NST - 1), sT0 + ((k + NST - 1) % NST) * tile_bytes);
+      cp_async_commit();
+      if (k + 1 < nk) {
+        if (NST == 2) cp_async_wait_all(); else asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();
+        depthwise(sT0 + ((k + 1) % NST) * tile_bytes, sA0 + (ab ^ 1) * a_bytes);
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) issue_mma(sA0 + (ab ^ 1) * a_bytes, tmem_base + (uint32_t)((ab ^ 1) * accw), &mbar[ab ^ 1]);
+      }
+      mbar_wait(smem_u32(&mbar[ab]), (uint32_t)((k >> 1) & 1));
+      tc_fence_after();
+      epilogue(tile_of(k), sT0 + (k % NST) * tile_bytes, tmem_base + (uint32_t)(ab * accw));
+      tc_fence_before();
+      __syncthreads();                                 // TMEM[ab] drained, sT[k % NST] free for tile k + NST
+    }
   }
+  cp_async_wait_all();
   if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
 }
 
@@ -245,9 +315,10 @@ k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles
 // ------------------------------------------------------------------------------------------------
 size_t ds_smem_bytes(const DsParams& P, int S, int TR) {
   const int trin = (TR - 1) * S + 3, tw = P.iw + P.pl + 1;
-  size_t b = (size_t)P.N * P.KP + (size_t)P.MT * 128 * P.KP;
-  b += ((size_t)P.NB * trin * tw * P.C + 15) & ~(size_t)15;
-  b += (size_t)P.N * 16 + (size_t)((P.N + 1) & ~1) * 4 + 16;
+  const int nab = P.nst > 1 ? 2 : 1;
+  size_t b = (size_t)P.N * P.KP + (size_t)nab * P.MT * 128 * P.KP;
+  b += (size_t)P.nst * (((size_t)P.NB * trin * tw * P.C + 15) & ~(size_t)15);
+  b += (size_t)P.N * 16 + (size_t)((P.N + 1) & ~1) * 4 + 32;
   return b + 1024;                                   // alignment slack
 }
 

@@ -19,6 +19,7 @@ struct DsParams {
   int C, N, KP, RW;       // depthwise channels (= GEMM K), output channels, padded K, swizzle row width
   int ih, iw, oh, ow, pt, pl;
   int NB, MT;             // chunks per CTA tile, 128-row MMA tiles per CTA tile
+  int nst;                // input-tile buffers in shared memory: 1 = unpipelined, 2 / 3 = software pipeline (bn_ds.cu)
   int ow_log, trow_log, cg_log, ppr_log;   // log2 of ow, TR*ow, C/4, iw*C/16
   int sw_sh, sw_mask, rw_log;              // swizzle: chunk ^= (row >> sw_sh) & sw_mask
   int dw_in_zp, dw_lo, dw_hi;

@@ -394,6 +394,7 @@ static bool prep_ds(FastPlan& fp, FastImpl* im, Block& bl) {
   D.rw_log = ilog2_exact(D.RW);
   D.sw_sh = D.RW == 128 ? 0 : (D.RW == 64 ? 1 : 2);
   D.sw_mask = D.RW == 128 ? 7 : (D.RW == 64 ? 3 : 1);
+  D.nst = 1;
   int cols = 32; while (cols < D.MT * N) cols <<= 1;
   if (cols > 512) { if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: reject at check 9 (line %d)\n", __LINE__); return false; }
   D.tmem_cols = cols;
@@ -432,12 +433,40 @@ static bool prep_ds(FastPlan& fp, FastImpl* im, Block& bl) {
     D.a_rzo = (int)rzo; D.a_zpo = (int)zpo;
     D.a_lo = p[BN_ADD_ACT_MIN]; D.a_hi = p[BN_ADD_ACT_MAX];
   }
-  L.smem = ds_smem_bytes(D, S, TR);
-  if (L.smem > 225 * 1024) { if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: reject at check 16 (line %d)\n", __LINE__); return false; }
-  int per = (int)((225 * 1024) / L.smem);
-  if (per > 512 / cols) per = 512 / cols;
-  if (per > 2) per = 2;                          // 128 registers x 256 threads
-  L.ctas_per_sm = per < 1 ? 1 : per;
+  // pick the pipeline depth: score = resident CTAs per SM x (pipelined ? 1.5 : 1); deeper prefetch wins ties
+  {
+    const int limit = 225 * 1024;
+    const int ds_cta_cap = getenv("BN_DS_CTAS") ? atoi(getenv("BN_DS_CTAS")) : 2;
+    double best = -1.0;
+    for (int nst = 1; nst <= 3; nst++) {
+      DsParams Q = D;
+      Q.nst = nst;
+      int c2 = 32; while (c2 < (nst > 1 ? 2 : 1) * D.MT * N) c2 <<= 1;
+      if (c2 > 512) continue;
+      const size_t sm = ds_smem_bytes(Q, S, TR);
+      if ((int)sm > limit) continue;
+      int per = (int)(limit / sm);
+      if (per > 512 / c2) per = 512 / c2;
+      if (per > ds_cta_cap) per = ds_cta_cap;      // registers x 256 threads
+      if (per < 1) continue;
+      // measured: with 2-3 co-resident CTAs per SM the software pipeline adds nothing (the other CTAs already fill the
+      // stalls), so the unpipelined loop is preferred unless it would leave the SM with a single CTA
+      const double score = per >= 2 ? per - 0.01 * nst : (nst > 1 ? 1.5 : 1.0) + 0.01 * nst;
+      if (score > best) { best = score; D.nst = nst; D.tmem_cols = c2; L.smem = sm; L.ctas_per_sm = per; }
+    }
+    if (best < 0) { if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: reject at check 16 (line %d)\n", __LINE__); return false; }
+    if (getenv("BN_FORCE_NST")) {
+      const int f = atoi(getenv("BN_FORCE_NST"));
+      DsParams Q = D; Q.nst = f;
+      int c2 = 32; while (c2 < (f > 1 ? 2 : 1) * D.MT * N) c2 <<= 1;
+      const size_t sm = ds_smem_bytes(Q, S, TR);
+      if (f >= 1 && f <= 3 && c2 <= 512 && (int)sm <= limit) {
+        int per = (int)(limit / sm); if (per > 512 / c2) per = 512 / c2; if (per > ds_cta_cap) per = ds_cta_cap;
+        D.nst = f; D.tmem_cols = c2; L.smem = sm; L.ctas_per_sm = per;
+      }
+    }
+    if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: C=%d N=%d S=%d nst=%d smem=%zu ctas/SM=%d tmem=%d\n", C, N, S, D.nst, L.smem, L.ctas_per_sm, D.tmem_cols);
+  }
   return D.dw_rq && D.dw_rz && D.pw_rq && D.pw_rz;
 }
 

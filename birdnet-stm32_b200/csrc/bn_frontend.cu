@@ -34,6 +34,10 @@ __device__ __forceinline__ float fast_sqrt(float x) {
   return r;
 }
 
+__device__ __forceinline__ void cp_async16_fe(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
@@ -71,6 +75,7 @@ __device__ __forceinline__ void fft16(float2 (&v)[16]) {
 
 // dynamic smem layout:
 //   float  xs[span + 16]                    span = 31*hop + 512 floats (16-byte aligned, indexed like the global buffer)
+//   uint4  sraw[(span + 16) / 8]            raw int16 samples of the NEXT tile (cp.async prefetch)
 //   float2 zbuf[16][256+16]                 per half-warp exchange buffer (padded)
 //   float  tile[257][33]                    magnitude tile (bin-major variant only)
 //   float  red[2*8]
@@ -85,7 +90,8 @@ k_stft_mag(const int16_t* __restrict__ pcm, const float* __restrict__ peak, floa
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int span = (FRAMES_PER_CTA - 1) * hop + NFFT;
   float* xs = reinterpret_cast<float*>(smem_raw);
-  float2* zbuf = reinterpret_cast<float2*>(xs + ((span + 16 + 3) & ~3));
+  uint4* sraw = reinterpret_cast<uint4*>(xs + ((span + 16 + 3) & ~3));      // (span + 16) / 8 groups of 8 int16
+  float2* zbuf = reinterpret_cast<float2*>(sraw + ((span + 16 + 7) >> 3));
   float* tile = reinterpret_cast<float*>(zbuf + 16 * (NC + 16));
   float* red = FRAME_MAJOR ? tile : tile + BINS * TILE_LD;
 
@@ -118,35 +124,56 @@ k_stft_mag(const int16_t* __restrict__ pcm, const float* __restrict__ peak, floa
   const int groups_w = W / FRAMES_PER_CTA;
   const int ntiles = B * groups_w;
 
+  // Raw int16 samples of a tile arrive through cp.async one tile ahead (group grp of 8 samples is always handled by
+  // thread grp % FE_THREADS, so a thread only ever touches its own slots of sraw and no barrier is needed for them).
+  auto tile_geom = [&](int tile_id, int& b, int& t0, long& chunk_base, long& g_first, int& shift, int& ngroups) {
+    b = tile_id / groups_w;
+    t0 = (tile_id - b * groups_w) * FRAMES_PER_CTA;
+    chunk_base = (long)b * T + a0;                        // in pcm_al sample indices
+    const long g_lo = chunk_base + (long)t0 * hop - NFFT / 2;
+    g_first = g_lo & ~7L;
+    shift = (int)(g_lo - g_first);
+    ngroups = (shift + span + 7) >> 3;
+  };
+  auto prefetch = [&](int tile_id) {
+    int b, t0, shift, ngroups; long chunk_base, g_first;
+    tile_geom(tile_id, b, t0, chunk_base, g_first, shift, ngroups);
+    for (int grp = tid; grp < ngroups; grp += FE_THREADS) {
+      const long g = g_first + 8L * grp;
+      if (g >= a0 && g + 8 <= a0 + total) {
+        cp_async16_fe(sraw + grp, pcm_al + g);
+      } else {                                            // first / last samples of the whole buffer
+        unsigned short sv[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) sv[j] = (g + j >= a0 && g + j < a0 + total) ? (unsigned short)pcm_al[g + j] : (unsigned short)0;
+        sraw[grp] = make_uint4(sv[0] | ((unsigned)sv[1] << 16), sv[2] | ((unsigned)sv[3] << 16), sv[4] | ((unsigned)sv[5] << 16), sv[6] | ((unsigned)sv[7] << 16));
+      }
+    }
+  };
+
+  if ((int)blockIdx.x < ntiles) prefetch(blockIdx.x);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+
   for (int tile_id = blockIdx.x; tile_id < ntiles; tile_id += gridDim.x) {
-    const int b = tile_id / groups_w;
-    const int t0 = (tile_id - b * groups_w) * FRAMES_PER_CTA;
-    // ---- stage samples [s0, s0 + span) of chunk b as float32, zero outside [0, T) -------------------------------
+    int b, t0, shift, ngroups; long chunk_base, g_first;
+    tile_geom(tile_id, b, t0, chunk_base, g_first, shift, ngroups);
+    // ---- samples [s0, s0 + span) of chunk b as float32, zero outside [0, T) -------------------------------------
     const float pk = peak ? __ldg(peak + b) : 0.0f;
     // y = (s / 32768) / peak (audio/io.py:114-126) as one multiply by the rounded reciprocal (<= 1.5 ulp from the reference)
     const float cs = pk > 0.0f ? __fdiv_rn(1.0f, 32768.0f * pk) : (1.0f / 32768.0f);
-    const long chunk_base = (long)b * T + a0;             // in pcm_al sample indices
-    const long g_lo = chunk_base + (long)t0 * hop - NFFT / 2;
-    const long g_first = g_lo & ~7L;
-    const int shift = (int)(g_lo - g_first);
-    const int ngroups = (shift + span + 7) >> 3;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     for (int grp = tid; grp < ngroups; grp += FE_THREADS) {
-      const long g = g_first + 8L * grp;
-      const long rel = g - chunk_base;                    // chunk-relative index of the group's first sample
-      uint4 wv = make_uint4(0, 0, 0, 0);
-      const bool inside = rel >= 0 && rel + 8 <= T;
-      if (inside && g >= a0 && g + 8 <= a0 + total) {
-        wv = __ldg(reinterpret_cast<const uint4*>(pcm_al + g));
-      } else {
-        unsigned short sv[8];
+      const long rel = g_first + 8L * grp - chunk_base;   // chunk-relative index of the group's first sample
+      const uint4 wv = sraw[grp];
+      unsigned ww[4] = {wv.x, wv.y, wv.z, wv.w};
+      if (rel < 0 || rel + 8 > T) {                       // chunk edge: samples outside [0, T) are zero padding
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-          const long r = rel + j;
-          sv[j] = (r >= 0 && r < T) ? (unsigned short)pcm_al[g + j] : (unsigned short)0;
+        for (int j = 0; j < 4; j++) {
+          const long r0 = rel + 2 * j, r1 = r0 + 1;
+          if (!(r0 >= 0 && r0 < T)) ww[j] &= 0xffff0000u;
+          if (!(r1 >= 0 && r1 < T)) ww[j] &= 0x0000ffffu;
         }
-        wv = make_uint4(sv[0] | ((unsigned)sv[1] << 16), sv[2] | ((unsigned)sv[3] << 16), sv[4] | ((unsigned)sv[5] << 16), sv[6] | ((unsigned)sv[7] << 16));
       }
-      const unsigned ww[4] = {wv.x, wv.y, wv.z, wv.w};
       float fv[8];
 #pragma unroll
       for (int j = 0; j < 4; j++) {
@@ -158,6 +185,8 @@ k_stft_mag(const int16_t* __restrict__ pcm, const float* __restrict__ peak, floa
       *reinterpret_cast<float4*>(xs + 8 * grp) = make_float4(fv[0], fv[1], fv[2], fv[3]);
       *reinterpret_cast<float4*>(xs + 8 * grp + 4) = make_float4(fv[4], fv[5], fv[6], fv[7]);
     }
+    if (tile_id + (int)gridDim.x < ntiles) prefetch(tile_id + gridDim.x);
+    asm volatile("cp.async.commit_group;" ::: "memory");
     __syncthreads();
 
     float lmin = __int_as_float(0x7f800000), lmax = 0.0f;
@@ -262,7 +291,7 @@ static const float4* stft_tables() {
 
 size_t stft_smem_bytes(int hop, bool frame_major) {
   const int span = (FRAMES_PER_CTA - 1) * hop + NFFT;
-  size_t b = sizeof(float) * ((span + 16 + 3) & ~3);
+  size_t b = sizeof(float) * ((span + 16 + 3) & ~3) + 16 * (size_t)((span + 16 + 7) >> 3);
   b += sizeof(float2) * 16 * (NC + 16) + sizeof(float) * 16;
   b += frame_major ? 0 : sizeof(float) * BINS * TILE_LD;
   return b;

@@ -1,6 +1,6 @@
 set -x
 cd /root/repo
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:^k_ -s 16 -c 16 -o /tmp/r1_full python profiles/run_wave.py 2048 2 > gpurun_out/r1_ncu_full.log 2>&1; tail -2 gpurun_out/r1_ncu_full.log
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:^k_ -s 30 -c 30 -o /tmp/r1_full python profiles/run_wave.py 2048 2 > gpurun_out/r1_ncu_full.log 2>&1; tail -2 gpurun_out/r1_ncu_full.log
 ncu -i /tmp/r1_full.ncu-rep --page raw --csv > gpurun_out/r1_full_raw.csv
 ncu -i /tmp/r1_full.ncu-rep --page details --csv > gpurun_out/r1_full_details.csv
 for k in k_stft_mag k_head k_stem k_tail; do
