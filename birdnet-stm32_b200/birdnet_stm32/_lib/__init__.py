@@ -18,6 +18,8 @@ EXPORTS = (
     "bn_create", "bn_destroy", "bn_query", "bn_set_option", "bn_infer_spec_f32", "bn_frontend_pcm16",
     "bn_infer_pcm16", "bn_infer_pool", "bn_pool_scores", "bn_dump_tensor", "bn_launch_count",
     "bn_profile_read", "bn_host_alloc", "bn_host_free", "bn_last_error", "bn_version",
+    # include/bn_features.h
+    "bn_features_create", "bn_features_destroy", "bn_features_rows", "bn_features_pcm16",
 )
 
 BN_POOL = {"avg": 0, "mean": 0, "average": 0, "max": 1, "lme": 2, "log_mean_exp": 2, "log_mean_exponential": 2}
@@ -32,6 +34,20 @@ class BnInfo(C.Structure):
         ("input_elems", C.c_int64), ("n_ops", C.c_int32), ("n_tensors", C.c_int32), ("device", C.c_int32),
         ("wave", C.c_int32), ("workspace_bytes", C.c_int64), ("fast_path", C.c_int32), ("reserved", C.c_int32 * 7),
     ]
+
+
+class BnFeatParams(C.Structure):
+    """`bn_feat_params` of include/bn_features.h"""
+
+    _fields_ = [
+        ("sample_rate", C.c_int32), ("chunk_len", C.c_int32), ("n_fft", C.c_int32), ("spec_width", C.c_int32),
+        ("n_mels", C.c_int32), ("mode", C.c_int32), ("mag_scale", C.c_int32), ("n_mfcc", C.c_int32),
+        ("pcen_b", C.c_float), ("reserved", C.c_int32 * 7),
+    ]
+
+
+BN_FEAT_MODE = {"mel": 0, "log_mel": 1, "mfcc": 2}
+BN_MAG_SCALE = {"none": 0, "pwl": 1, "pcen": 2, "db": 3}
 
 
 class EngineError(RuntimeError):
@@ -77,6 +93,11 @@ def load():
     L.bn_host_free.restype = None
     L.bn_last_error.restype = C.c_char_p
     L.bn_version.restype = C.c_char_p
+    L.bn_features_create.argtypes = [C.POINTER(BnFeatParams), vp, vp, i32, C.POINTER(vp)]
+    L.bn_features_destroy.argtypes = [vp]
+    L.bn_features_destroy.restype = None
+    L.bn_features_rows.argtypes = [vp]
+    L.bn_features_pcm16.argtypes = [vp, vp, vp, i32, vp, vp]
     _lib = L
     return L
 

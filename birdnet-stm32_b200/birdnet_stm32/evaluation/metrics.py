@@ -51,6 +51,20 @@ def make_chunks_for_file(path: str, cfg: dict, frontend: str, mag_scale: str, n_
                                "(this package has no CPU spectrogram path)")
         spec = frontend_runner.frontend(pcm, np.full((pcm.shape[0],), peak, dtype=np.float32))
         return [s for s in spec]
+    if frontend == "librosa":
+        # precomputed mel spectrograms (reference `metrics.py:49-54`): computed for all chunks of the file in one
+        # call by the CUDA feature kernels; `frontend_runner` may carry a cached FeatureExtractor
+        from birdnet_stm32.audio.spectrogram import FeatureExtractor
+
+        key = (sr, pcm.shape[1], n_fft, int(cfg["num_mels"]), int(cfg["spec_width"]), mag_scale)
+        cache = getattr(make_chunks_for_file, "_fx", None)
+        if cache is None or cache[0] != key:
+            if cache is not None:
+                cache[1].close()
+            cache = (key, FeatureExtractor(sr, pcm.shape[1], n_fft, int(cfg["num_mels"]), int(cfg["spec_width"]), mag_scale))
+            make_chunks_for_file._fx = cache
+        S = cache[1](pcm, np.full((pcm.shape[0],), peak, dtype=np.float32))
+        return [s[:, :, None] for s in S]
     raise ValueError(f"Invalid audio_frontend for the B200 path: {frontend}")
 
 

@@ -27,6 +27,11 @@ static int set_err(int code, const char* fmt, ...) {
   return code;
 }
 
+namespace bn {
+// shared with the other translation units of the library (bn_features.cu): same thread-local message
+int set_error(int code, const char* msg) { return set_err(code, "%s", msg); }
+}  // namespace bn
+
 #define CU(call)                                                                                   \
   do {                                                                                             \
     cudaError_t _e = (call);                                                                       \

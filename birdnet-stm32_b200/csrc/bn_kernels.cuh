@@ -7,6 +7,8 @@
 
 namespace bn {
 
+int set_error(int code, const char* msg);   // bn_engine.cu: sets bn_last_error() for this thread, returns code
+
 // ---- generic plan (bn_generic.cu) -------------------------------------------------------
 void launch_quantize(const float* x, int8_t* y, long n, float scale, int zp, cudaStream_t st);
 void launch_dequantize(const int8_t* x, float* y, long n, float scale, int zp, cudaStream_t st);

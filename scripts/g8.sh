@@ -1,0 +1,2 @@
+cd /root/repo
+timeout 900 python -m pytest tests/test_features.py -m gpu -q 2>&1 | tail -25

@@ -1,0 +1,169 @@
+"""Precomputed-spectrogram frontends (BASELINE config 2): mel / log-mel / MFCC features with
+none | pwl | pcen | db scaling.  CPU tests pin the oracle and the host tables; GPU tests compare the CUDA feature
+kernels (through the C ABI of include/bn_features.h) with the oracle on the same seeded PCM.
+
+Mirrors reference tests/test_spectrogram.py:11-35 (shapes, silence, dtype) on both implementations.
+"""
+
+import numpy as np
+import pytest
+import scipy.fftpack
+
+from birdnet_stm32.audio import mel as melmod
+from oracle import bn_features_oracle as fo
+
+MODES = [("mel", "none"), ("mel", "pwl"), ("mel", "pcen"), ("mel", "db"), ("log_mel", "none"), ("mfcc", "none")]
+# float32 CUDA pipeline vs the float64-FFT / float64-PCEN oracle, on min-max normalised features in [0, 1]
+TOL = 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU: host tables and oracle behaviour
+# ---------------------------------------------------------------------------------------------------------------
+def test_mel_filterbank_matches_oracle_and_slaney_properties():
+    for sr, n_mels in ((24000, 64), (22050, 64), (24000, 32)):
+        a = melmod.mel_filterbank(sr, 512, n_mels, 150.0, float(sr // 2))
+        b = fo.mel_basis(sr, 512, n_mels, 150, sr // 2)
+        assert a.dtype == np.float32 and a.shape == (n_mels, 257)
+        assert np.array_equal(a, b)                      # two independent restatements of librosa.filters.mel
+        assert (a >= 0).all() and (a.max(axis=1) > 0).all()
+        # triangles: one contiguous run of non-zeros per filter, centres increasing
+        bands = melmod.filter_bands(a)
+        assert (np.diff(bands[:, 0]) >= 0).all() and (bands[:, 1] > bands[:, 0]).all()
+        for m in range(n_mels):
+            assert (a[m, bands[m, 0]:bands[m, 1]] > 0).all()
+        # Slaney area normalisation: each continuous triangle integrates to 1 over Hz; sampled on the FFT grid the
+        # wide (high) filters come close
+        area = a[-8:].sum(axis=1) * (sr / 512)
+        assert np.allclose(area, 1.0, atol=0.05)
+    # the mel scale itself: linear below 1 kHz, log above, inverse consistent
+    f = np.array([0.0, 150.0, 999.0, 1000.0, 4000.0, 12000.0])
+    assert np.allclose(melmod.mel_to_hz(melmod.hz_to_mel(f)), f)
+    assert np.isclose(melmod.hz_to_mel(1000.0), 15.0)
+
+
+def test_dct_matrix_matches_scipy():
+    x = np.random.default_rng(0).normal(size=(64, 7))
+    want = scipy.fftpack.dct(x, axis=0, type=2, norm="ortho")[:20]
+    got = melmod.dct_matrix(20, 64).astype(np.float64) @ x
+    assert np.abs(got - want).max() < 1e-6
+
+
+def test_pcen_coefficient_matches_filter_design():
+    # b solves the librosa design equation  b^2 T^2 + b - 1 = 0  for T = time_constant * sr / hop frames
+    for sr, hop in ((24000, 281), (22050, 258)):
+        b = melmod.pcen_coefficient(sr, hop)
+        T = 0.4 * sr / hop
+        assert abs(b * b * T * T + b - 1.0) < 1e-12 and 0 < b < 1
+
+
+@pytest.mark.parametrize("mode,mag", MODES)
+def test_oracle_shapes_range_dtype(mode, mag):
+    sr, T = 24000, 72000
+    t = np.arange(T) / sr
+    sine = (0.5 * np.sin(2 * np.pi * 1000.0 * t)).astype(np.float32)
+    S = fo.get_spectrogram_from_audio(sine, sr, 512, 64, 256, mag, mode, 20)
+    rows = 20 if mode == "mfcc" else 64
+    assert S.shape == (rows, 256)
+    assert np.isfinite(S).all() and S.min() >= 0.0 and S.max() <= 1.0 + 1e-6
+    assert abs(float(S.max()) - 1.0) < 1e-5 and float(S.min()) == 0.0
+
+
+def test_oracle_linear_and_silence():
+    sr, T = 22050, 66150
+    S = fo.get_spectrogram_from_audio(np.zeros(T, np.float32), sr, 512, 64, 256)
+    assert S.shape == (64, 256) and np.max(np.abs(S)) < 1e-3           # reference test_silence_low_energy
+    L = fo.get_spectrogram_from_audio(np.zeros(T, np.float32), sr, 512, -1, 256)
+    assert L.shape == (257, 256)                                          # reference test_output_shape_linear
+    x = np.random.default_rng(1).normal(size=T).astype(np.float32) * 0.1
+    assert fo.get_spectrogram_from_audio(x, sr, 512, 32, 64).astype(np.float32).dtype == np.float32
+
+
+def test_oracle_linear_matches_c_oracle_frontend(pcm_batch):
+    """The numpy STFT of this oracle == the C oracle's hybrid frontend (float64 FFT stored as complex64)."""
+    from oracle import bn_oracle
+
+    pcm, peak = pcm_batch
+    want = bn_oracle.frontend_hybrid(pcm[:3], peak[:3], 512, 66150 // 256, 256)[..., 0]
+    got = fo.features_from_pcm16(pcm[:3], peak[:3], sample_rate=22050, n_fft=512, mel_bins=-1, spec_width=256)
+    assert np.abs(got - want).max() < 2e-6
+
+
+def test_feature_abi_symbols_declared_and_exported():
+    import ctypes
+    import os
+    import re
+
+    from birdnet_stm32 import _lib
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "bn_features.h")).read()
+    declared = set(re.findall(r"BN_API\s+[\w\s\*]+?\b(bn_\w+)\s*\(", hdr))
+    assert declared == {"bn_features_create", "bn_features_destroy", "bn_features_rows", "bn_features_pcm16"}
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name)
+    assert declared <= set(_lib.EXPORTS)
+
+
+def test_feature_extractor_argument_errors():
+    from birdnet_stm32.audio.spectrogram import FeatureExtractor
+
+    with pytest.raises(ValueError):
+        FeatureExtractor(mode="nope")
+    with pytest.raises(ValueError):
+        FeatureExtractor(mag_scale="nope")
+    with pytest.raises(ValueError):
+        FeatureExtractor(mel_bins=-1)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPU: CUDA kernels vs oracle
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("sr,T", [(24000, 72000), (22050, 66150)])
+@pytest.mark.parametrize("mode,mag", MODES)
+def test_gpu_features_match_oracle(synth, sr, T, mode, mag):
+    from birdnet_stm32.audio.spectrogram import FeatureExtractor
+
+    pcm = synth.synth_pcm16(6, T, sr, seed=77, edge_cases=True)        # chirps + 1 kHz sine, impulse, square, silence
+    peak = synth.file_peaks(pcm)
+    fx = FeatureExtractor(sr, T, 512, 64, 256, mag, mode, 20)
+    got = fx(pcm, peak)
+    fx.close()
+    want = fo.features_from_pcm16(pcm, peak, sample_rate=sr, n_fft=512, mel_bins=64, spec_width=256, mag_scale=mag,
+                                  mode=mode, n_mfcc=20)
+    assert got.shape == want.shape and got.dtype == np.float32
+    assert np.isfinite(got).all()
+    err = np.abs(got.astype(np.float64) - want.astype(np.float64)).reshape(got.shape[0], -1).max(axis=1)
+    # the silent chunk is 0/1e-10 everywhere on both sides; every other chunk within TOL of the oracle
+    tol = np.full(err.shape, TOL)
+    if mag == "pcen":
+        # PCEN divides every band by its own smoothed energy.  For the noiseless digital 1 kHz sine (chunk 2) most
+        # bands hold nothing but FFT round-off (float32 on the GPU, float64 in the oracle, ~1e-7 of the peak), and
+        # the gain control amplifies exactly that difference; any signal with a noise floor is unaffected.
+        tol[2] = 1e-2
+    assert (err <= tol).all(), (mode, mag, err)
+
+
+@pytest.mark.gpu
+def test_gpu_features_device_pointers_and_batches(synth):
+    """Device-pointer entry, B > one sub-wave, 32 mel bands: same numbers as the host-pointer entry."""
+    import torch
+
+    from birdnet_stm32.audio.spectrogram import FeatureExtractor
+
+    sr, T, B = 24000, 72000, 300
+    base = synth.synth_pcm16(10, T, sr, seed=5)
+    pcm = np.ascontiguousarray(base[np.arange(B) % 10])
+    peak = synth.file_peaks(pcm)
+    fx = FeatureExtractor(sr, T, 512, 32, 256, "pwl", "mel")
+    host = fx(pcm, peak)
+    dp = torch.from_numpy(pcm).cuda()
+    dk = torch.from_numpy(peak).cuda()
+    do = torch.empty((B, 32, 256), dtype=torch.float32, device="cuda")
+    fx.run_device(dp.data_ptr(), dk.data_ptr(), B, do.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    fx.close()
+    assert np.array_equal(do.cpu().numpy(), host)
+    assert np.array_equal(host[:10], host[290:300])
