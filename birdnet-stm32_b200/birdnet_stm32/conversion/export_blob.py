@@ -236,6 +236,12 @@ class Lowering:
         if depthwise:
             weights = weights.reshape(kh, kw, cout)
         kind = "FC" if fc else ("DWCONV2D" if depthwise else "CONV2D")
+        if fc and int(np.prod(_dims3(x.shape)[1])) != cin:
+            # Dense applied to every position of [B, ..., K] (keep_num_dims, e.g. the attention-pooling score of
+            # models/blocks.py:151-156): the same arithmetic as a 1x1 convolution over the leading dims
+            if _dims3(x.shape)[1][2] != cin:
+                raise ValueError(f"op {op.index}: FULLY_CONNECTED input {x.shape} does not end in K={cin}")
+            kind = "CONV2D"
         self.emit(kind, op, [op.inputs[0]], op.outputs[0],
                   p=[kh, kw, sh, sw, pt, pl, x.zp(), y.zp(), amin, amax, cin, cout],
                   arrays=[weights, bias, mult, shift])
@@ -259,6 +265,8 @@ class Lowering:
             _, db = _dims3(b.shape)
             if db[0] == 1 and db[1] == 1 and db[2] == da[2]:
                 bcast = 2   # per-item [1,1,C] activation broadcast over H,W (SE gate)
+            elif db[2] == 1 and db[:2] == da[:2] and op.kind == "MUL":
+                bcast = 3   # per-position [H,W,1] activation broadcast over C (attention weights, blocks.py:157)
             else:
                 raise ValueError(f"op {op.index}: unsupported broadcast {a.shape} vs {b.shape}")
         amin, amax = activation_range(op.options.get("act", "NONE"), y.s(), y.zp())
@@ -368,6 +376,33 @@ class Lowering:
                 self.emit("LOGISTIC", op, [op.inputs[0]], outs[0], arrays=[logistic_lut(x.s(), x.zp(), y.s(), y.zp())])
             elif k == "RESHAPE":
                 self.emit("RESHAPE", op, [op.inputs[0]], outs[0])
+            elif k == "PAD":
+                x, y = g.tensor(op.inputs[0]), g.tensor(outs[0])
+                pads = g.tensor(op.inputs[1]).data.reshape(-1, 2).astype(int)
+                if x.s() != y.s() or x.zp() != y.zp():
+                    raise ValueError(f"op {op.index}: PAD must keep the quantisation parameters")
+                if pads.shape[0] != len(x.shape) or pads[0].any():
+                    raise ValueError(f"op {op.index}: PAD must not touch the batch dim")
+                rows = [(0, 0)] * (4 - len(x.shape)) + [tuple(r) for r in pads[1:]]
+                self.emit("PAD", op, [op.inputs[0]], outs[0], p=[v for r in rows[-3:] for v in r] + [x.zp()])
+            elif k == "SOFTMAX":
+                x, y = g.tensor(op.inputs[0]), g.tensor(outs[0])
+                beta = float(op.options.get("beta", 1.0)) or 1.0
+                # optimized_ops::PopulateSoftmaxLookupTable: table[255 - v] = expf(-input_scale * beta * v), float32
+                sc = np.float32(-np.float32(x.s()) * np.float32(beta))
+                table = np.exp((sc * np.arange(256, dtype=np.float32)).astype(np.float32)).astype(np.float32)[::-1].copy()
+                self.emit("SOFTMAX", op, [op.inputs[0]], outs[0], p=[y.zp()], f=[float(np.float32(x.s()) * np.float32(beta)), y.s()],
+                          arrays=[table])
+            elif k == "SUM":
+                x, ax, y = g.tensor(op.inputs[0]), g.tensor(op.inputs[1]), g.tensor(outs[0])
+                axes = [int(v) % len(x.shape) for v in ax.data.reshape(-1)]
+                if len(axes) != 1 or axes[0] == 0:
+                    raise ValueError(f"op {op.index}: SUM over exactly one non-batch axis is supported")
+                axis3 = axes[0] - 1 + (3 - (len(x.shape) - 1))
+                count = int(x.shape[axes[0]])
+                scale = np.float32(np.float32(x.s()) / np.float32(y.s()))
+                bias = np.float32(np.float32(np.float32(-x.zp()) * scale) * np.float32(count))
+                self.emit("SUM", op, [op.inputs[0]], outs[0], p=[axis3, count, x.zp(), y.zp()], f=[float(scale), float(bias)])
             else:
                 raise ValueError(f"op {op.index}: unsupported operator {k}")
         return self

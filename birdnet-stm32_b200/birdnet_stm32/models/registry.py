@@ -21,8 +21,9 @@ class FrontendInfo:
 
 _REGISTRY: dict[str, FrontendInfo] = {}
 
-# frontends whose host-side work has a CUDA kernel in libbn_b200.so (bn_frontend_pcm16)
-GPU_FRONTENDS = frozenset({"hybrid"})
+# frontends whose host-side work has a CUDA kernel in libbn_b200.so: bn_frontend_pcm16 (hybrid) and
+# bn_features_pcm16 (librosa / log_mel / mfcc); "raw" only needs x / (max|x| + 1e-6) on the host
+GPU_FRONTENDS = frozenset({"hybrid", "librosa", "log_mel", "mfcc"})
 
 
 def register_frontend(info: FrontendInfo) -> None:

@@ -91,7 +91,7 @@ static int validate_blob(const bn_engine* e) {
     switch (op.kind) {
       case BN_OP_QUANTIZE: case BN_OP_DEQUANTIZE: case BN_OP_REQUANT: case BN_OP_TRANSPOSE: case BN_OP_SLICE:
       case BN_OP_FILL: case BN_OP_CONCAT: case BN_OP_CONV2D: case BN_OP_DWCONV2D: case BN_OP_FC: case BN_OP_ADD:
-      case BN_OP_MUL: case BN_OP_MEAN: case BN_OP_LOGISTIC: case BN_OP_RESHAPE:
+      case BN_OP_MUL: case BN_OP_MEAN: case BN_OP_LOGISTIC: case BN_OP_RESHAPE: case BN_OP_PAD: case BN_OP_SOFTMAX: case BN_OP_SUM:
         break;
       default:
         return set_err(BN_ERR_UNSUPPORTED, "op %u (tflite op %d): kind %d has no CUDA kernel", i, op.tfl_index, op.kind);
@@ -312,6 +312,17 @@ static int run_generic(bn_engine* e, std::vector<void*>& ptr, int Bw, cudaStream
         launch_mean((const int8_t*)x, (int8_t*)y, n_out, op.p[BN_MEAN_COUNT], ti->dims[2], op.p, ti->scale, to.scale, variant, R, st);
       } break;
       case BN_OP_LOGISTIC: launch_logistic((const int8_t*)x, (int8_t*)y, n_out, (const int8_t*)(e->d_blob + op.off[0]), st); break;
+      case BN_OP_PAD: launch_pad((const int8_t*)x, (int8_t*)y, n_out, ti->dims, to.dims, op.p, st); break;
+      case BN_OP_SOFTMAX:
+        launch_softmax((const int8_t*)x, (int8_t*)y, n_out / to.dims[2], to.dims[2], (const float*)(e->d_blob + op.off[0]), op.f[1], op.p[0], st);
+        break;
+      case BN_OP_SUM: {
+        const int axis = op.p[0];
+        int outer = 1, inner = 1;
+        for (int d = 0; d < axis; d++) outer *= ti->dims[d];
+        for (int d = axis + 1; d < 3; d++) inner *= ti->dims[d];
+        launch_sum((const int8_t*)x, (int8_t*)y, n_out, outer, ti->dims[axis], inner, op.f[0], op.f[1], op.p[3], st);
+      } break;
       default: return set_err(BN_ERR_UNSUPPORTED, "op kind %d", op.kind);
     }
     if (e->prof.on) e->prof.end(st);

@@ -193,10 +193,62 @@ __global__ void k_mul(const int8_t* __restrict__ a, const int8_t* __restrict__ b
                       long per_chunk, int in1_zp, int in2_zp, int out_zp, int mult, int shift, int act_min,
                       int act_max, int bcast, int C, int R) {
   GRID_STRIDE(i, n) {
-    long bi = bcast == 0 ? i : (bcast == 1 ? (i % C) : ((i / per_chunk) * C + (i % C)));
+    // bcast: 0 none, 1 const [C], 2 per-chunk [1,1,C] over H,W (SE gate), 3 per-position [H,W,1] over C (attention weights)
+    long bi = bcast == 0 ? i : (bcast == 1 ? (i % C) : (bcast == 2 ? ((i / per_chunk) * C + (i % C)) : (i / C)));
     int v = ((int)a[i] - in1_zp) * ((int)b[bi] - in2_zp);
     int o = mbqm(v, mult, shift, R) + out_zp;
     y[i] = (int8_t)clampi(o, act_min, act_max);
+  }
+}
+
+// PAD with the zero point: x [B][d0][d1][d2] -> y [B][o0][o1][o2], o = d + before + after
+__global__ void k_pad(const int8_t* __restrict__ x, int8_t* __restrict__ y, long n, int d0, int d1, int d2, int o0, int o1, int o2,
+                      int b0, int b1, int b2, int val) {
+  GRID_STRIDE(i, n) {
+    long r = i;
+    const int c = (int)(r % o2); r /= o2;
+    const int w = (int)(r % o1); r /= o1;
+    const int h = (int)(r % o0); r /= o0;
+    const int sh = h - b0, sw = w - b1, sc = c - b2;
+    int v = val;
+    if (sh >= 0 && sh < d0 && sw >= 0 && sw < d1 && sc >= 0 && sc < d2) v = x[((r * d0 + sh) * d1 + sw) * (long)d2 + sc];
+    y[i] = (int8_t)v;
+  }
+}
+
+// SOFTMAX over the last dim, int8 -> int8: the float-LUT kernel of tflite::optimized_ops::Softmax
+// (table[255 - v] = expf(-in_scale * beta * v) comes with the blob; sums run left to right in float32).
+__global__ void k_softmax(const int8_t* __restrict__ x, int8_t* __restrict__ y, long rows, int L, const float* __restrict__ table,
+                          float out_scale, int out_zp) {
+  GRID_STRIDE(r, rows) {
+    const int8_t* xp = x + r * (long)L;
+    int mx = -128;
+    for (int j = 0; j < L; j++) mx = max(mx, (int)xp[j]);
+    const float* toff = table + (255 - mx);
+    float sum = 0.0f;
+    for (int j = 0; j < L; j++) sum = __fadd_rn(sum, toff[xp[j]]);
+    const float inv = __fdiv_rn(1.0f, __fmul_rn(sum, out_scale));
+    for (int j = 0; j < L; j++) {
+      const float pr = __fmul_rn(toff[xp[j]], inv);
+      const int q = (int)__fadd_rn(pr, 0.5f) + out_zp;
+      y[r * (long)L + j] = (int8_t)max(-128, min(127, q));
+    }
+  }
+}
+
+// SUM over one non-batch axis, int8 -> int8: tflite::reference_ops::QuantizedMeanOrSum(compute_sum = true):
+// round(float(sum) * scale + bias) + out_zp with scale = in_scale / out_scale, bias = -in_zp * scale * count.
+__global__ void k_sum(const int8_t* __restrict__ x, int8_t* __restrict__ y, long n, int outer, int count, int inner, float scale,
+                      float bias, int out_zp) {
+  GRID_STRIDE(i, n) {
+    const long in_ = i % inner;
+    const long ob = i / inner;                       // (batch * outer) index
+    const int8_t* xp = x + (ob * count) * inner + in_;
+    int sum = 0;
+    for (int j = 0; j < count; j++) sum += xp[(long)j * inner];
+    const float v = __fadd_rn(__fmul_rn((float)sum, scale), bias);
+    const int q = (int)roundf(v) + out_zp;
+    y[i] = (int8_t)max(-128, min(127, q));
   }
 }
 
@@ -302,6 +354,15 @@ void launch_mean(const int8_t* x, int8_t* y, long n, int N, int C, const int* p,
          p[BN_MEAN_MULT_N], p[BN_MEAN_SHIFT_N], in_scale, out_scale, variant, R);
 }
 void launch_logistic(const int8_t* x, int8_t* y, long n, const int8_t* lut, cudaStream_t st) { LAUNCH(k_logistic, n, st, x, y, n, lut); }
+void launch_pad(const int8_t* x, int8_t* y, long n, const int* id, const int* od, const int* p, cudaStream_t st) {
+  LAUNCH(k_pad, n, st, x, y, n, id[0], id[1], id[2], od[0], od[1], od[2], p[0], p[2], p[4], p[6]);
+}
+void launch_softmax(const int8_t* x, int8_t* y, long rows, int L, const float* table, float out_scale, int out_zp, cudaStream_t st) {
+  LAUNCH(k_softmax, rows, st, x, y, rows, L, table, out_scale, out_zp);
+}
+void launch_sum(const int8_t* x, int8_t* y, long n, int outer, int count, int inner, float scale, float bias, int out_zp, cudaStream_t st) {
+  LAUNCH(k_sum, n, st, x, y, n, outer, count, inner, scale, bias, out_zp);
+}
 void launch_minmax_normalize(float* s, long per_chunk, long n, const unsigned* mnmx, cudaStream_t st) { LAUNCH(k_minmax_normalize, n, st, s, per_chunk, n, mnmx); }
 void launch_pool(const float* scores, const int* offs, float* out, int F, int C, int method, float beta, cudaStream_t st) {
   if (F <= 0) return;

@@ -24,6 +24,9 @@ void launch_add(const int8_t* a, const int8_t* b, int8_t* y, long n, long per_ch
 void launch_mul(const int8_t* a, const int8_t* b, int8_t* y, long n, long per_chunk, const int* p, int C, int R, cudaStream_t st);
 void launch_mean(const int8_t* x, int8_t* y, long n, int N, int C, const int* p, float in_scale, float out_scale, int variant, int R, cudaStream_t st);
 void launch_logistic(const int8_t* x, int8_t* y, long n, const int8_t* lut, cudaStream_t st);
+void launch_pad(const int8_t* x, int8_t* y, long n, const int* id, const int* od, const int* p, cudaStream_t st);
+void launch_softmax(const int8_t* x, int8_t* y, long rows, int L, const float* table, float out_scale, int out_zp, cudaStream_t st);
+void launch_sum(const int8_t* x, int8_t* y, long n, int outer, int count, int inner, float scale, float bias, int out_zp, cudaStream_t st);
 void launch_minmax_normalize(float* s, long per_chunk, long n, const unsigned* mnmx, cudaStream_t st);
 void launch_pool(const float* scores, const int* offs, float* out, int F, int C, int method, float beta, cudaStream_t st);
 

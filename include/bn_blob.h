@@ -49,13 +49,16 @@ enum {
   BN_OP_DWCONV2D = 8,    /* same slots, weights [kh,kw,C]                                        */
   BN_OP_FC = 9,          /* same slots with kh=kw=1, in [K] out [N]                              */
   BN_OP_ADD = 10,        /* see BN_ADD_* slots; in[1] may be a const broadcast over last dim     */
-  BN_OP_MUL = 11,        /* p: in1_off,in2_off,out_zp,mult,shift,act_min,act_max                 */
+  BN_OP_MUL = 11,        /* p: in1_zp,in2_zp,out_zp,mult,shift,act_min,act_max,bcast (0 none, 1 const [C],
+                            2 per-chunk [1,1,C] over H,W, 3 per-position [H,W,1] over C)                   */
   BN_OP_MEAN = 12,       /* mean over H,W : see BN_MEAN_* slots                                  */
   BN_OP_LOGISTIC = 13,   /* off[0] = 256-byte LUT indexed by (uint8)(q+128)                      */
   BN_OP_RESHAPE = 14,    /* pure re-interpretation (copy)                                        */
-  BN_OP_SOFTMAX = 15,    /* over last dim; f[0] = in_scale*beta; out scale 1/256 zp -128         */
+  BN_OP_SOFTMAX = 15,    /* over last dim; p[0]=out_zp f[0]=in_scale*beta f[1]=out_scale off[0]=float table[256],
+                            table[255-v] = expf(-in_scale*beta*v)                                   */
   BN_OP_PAD = 16,        /* p[0..5] = before/after per non-batch dim, p[6] = pad value           */
-  BN_OP_SUM = 17,        /* sum over axis p[0] (non-batch), requant p[1]=mult p[2]=shift         */
+  BN_OP_SUM = 17,        /* sum over axis p[0] (non-batch): p[1]=count p[2]=in_zp p[3]=out_zp f[0]=in/out scale
+                            f[1]=bias = -in_zp*scale*count                                         */
   BN_OP_REDUCE_MAX = 18, /* max over axes bitmask p[0]                                           */
   BN_OP_REQUANT = 19     /* i8 -> i8 QUANTIZE: p[0]=in_zp p[1]=out_zp p[2]=mult p[3]=shift       */
 };

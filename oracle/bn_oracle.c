@@ -315,7 +315,8 @@ static int run_one(const bno_model* m, const float* input, float* output, void**
         const int bc = p[7];
         for (long i = 0; i < (long)to->nbytes; i++) {
           int32_t v1 = (int32_t)a[i] - p[0];
-          int32_t v2 = (int32_t)b[bc ? (i % C) : i] - p[1];
+          /* bcast: 0 none, 1 const [C], 2 per-chunk [1,1,C] (SE gate), 3 per-position [H,W,1] (attention weights) */
+          int32_t v2 = (int32_t)b[bc == 3 ? (i / C) : (bc ? (i % C) : i)] - p[1];
           int32_t o = mbqm(v1 * v2, p[3], p[4], R) + p[2];
           y[i] = (int8_t)clampi(o, p[5], p[6]);
         }
@@ -354,6 +355,62 @@ static int run_one(const bno_model* m, const float* input, float* output, void**
         int8_t* y = (int8_t*)buf[op->out];
         const int8_t* lut = (const int8_t*)(m->blob + op->off[0]);
         for (long i = 0; i < (long)to->nbytes; i++) y[i] = lut[(uint8_t)(x[i] + 128)];
+      } break;
+      case BN_OP_PAD: {
+        /* reference_ops::Pad on int8: the pad value is the tensor's zero point (p[6]) */
+        const int8_t* x = (const int8_t*)buf[op->in[0]];
+        int8_t* y = (int8_t*)buf[op->out];
+        const int d0 = ti->dims[0], d1 = ti->dims[1], d2 = ti->dims[2];
+        const int o0 = to->dims[0], o1 = to->dims[1], o2 = to->dims[2];
+        for (int h = 0; h < o0; h++)
+          for (int w = 0; w < o1; w++)
+            for (int c = 0; c < o2; c++) {
+              const int sh = h - p[0], sw = w - p[2], sc = c - p[4];
+              int v = p[6];
+              if (sh >= 0 && sh < d0 && sw >= 0 && sw < d1 && sc >= 0 && sc < d2) v = x[((long)sh * d1 + sw) * d2 + sc];
+              y[((long)h * o1 + w) * o2 + c] = (int8_t)v;
+            }
+      } break;
+      case BN_OP_SOFTMAX: {
+        /* tflite::optimized_ops::Softmax (int8 in/out, float LUT): the kernel BuiltinOpResolver registers on x86.
+         * table[255 - v] = expf(-in_scale * beta * v) is precomputed by the exporter (off[0]); f[1] = output scale. */
+        const int8_t* x = (const int8_t*)buf[op->in[0]];
+        int8_t* y = (int8_t*)buf[op->out];
+        const float* table = (const float*)(m->blob + op->off[0]);
+        const int L = to->dims[2];
+        const long rows = (long)to->dims[0] * to->dims[1];
+        for (long r = 0; r < rows; r++) {
+          const int8_t* xp = x + r * L;
+          int32_t mx = -128;
+          for (int j = 0; j < L; j++) if (xp[j] > mx) mx = xp[j];
+          const float* toff = table + (255 - mx);
+          volatile float sum = 0.0f;
+          for (int j = 0; j < L; j++) sum = sum + toff[xp[j]];
+          const float inv = 1.0f / (float)(sum * op->f[1]);
+          for (int j = 0; j < L; j++) {
+            const float pr = toff[xp[j]] * inv;
+            const int32_t q = (int32_t)(float)(pr + 0.5f) + p[0];
+            y[r * L + j] = (int8_t)clampi(q, -128, 127);
+          }
+        }
+      } break;
+      case BN_OP_SUM: {
+        /* reference_ops::QuantizedMeanOrSum(compute_sum = true): p = axis, count, in_zp, out_zp; f = scale, bias */
+        const int8_t* x = (const int8_t*)buf[op->in[0]];
+        int8_t* y = (int8_t*)buf[op->out];
+        const int axis = p[0];
+        long outer = 1, inner = 1;
+        for (int d = 0; d < axis; d++) outer *= ti->dims[d];
+        for (int d = axis + 1; d < 3; d++) inner *= ti->dims[d];
+        const int count = ti->dims[axis];
+        for (long o = 0; o < outer; o++)
+          for (long in_ = 0; in_ < inner; in_++) {
+            int32_t sum = 0;
+            for (int j = 0; j < count; j++) sum += x[(o * count + j) * inner + in_];
+            const float prod = (float)sum * op->f[0];
+            const float v = prod + op->f[1];
+            y[o * inner + in_] = (int8_t)clampi((int32_t)roundf(v) + p[3], -128, 127);
+          }
       } break;
       default:
         snprintf(g_err, sizeof g_err, "oracle: unsupported op kind %d (tflite op %d)", op->kind, op->tfl_index);

@@ -80,7 +80,7 @@ def test_frontend_registry_and_names():
     assert registry.list_frontends() == ["hybrid", "librosa", "log_mel", "mfcc", "raw"]
     assert registry.get_frontend_info("hybrid").mode == "hybrid" and not registry.is_precomputed("hybrid")
     assert registry.is_precomputed("librosa") and registry.is_n6_compatible("raw")
-    assert registry.has_gpu_frontend("hybrid") and not registry.has_gpu_frontend("mfcc")
+    assert registry.has_gpu_frontend("hybrid") and registry.has_gpu_frontend("mfcc") and not registry.has_gpu_frontend("raw")
     with pytest.raises(KeyError, match="not registered"):
         registry.get_frontend_info("nope")
     with pytest.raises(ValueError, match="already registered"):
@@ -116,12 +116,12 @@ def test_blob_layout_and_exporter_errors(graph, blob, cfg):
 
 
 def test_c_abi_library_loads_and_exports_every_declared_symbol():
-    """No compute calls here (no GPU): the .so loads, exports what include/bn_engine.h declares, and
+    """No compute calls here (no GPU): the .so loads, exports what include/*.h declare, and
     creating an engine without a CUDA device fails loudly instead of falling back to the CPU."""
     from birdnet_stm32 import _lib as L
 
     lib = L.load()
-    header = open(os.path.join(ROOT, "include", "bn_engine.h")).read()
+    header = open(os.path.join(ROOT, "include", "bn_engine.h")).read() + open(os.path.join(ROOT, "include", "bn_features.h")).read()
     declared = set(re.findall(r"BN_API\s+[\w\s\*]+?\b(bn_\w+)\s*\(", header))
     assert declared == set(L.EXPORTS), declared ^ set(L.EXPORTS)
     for name in declared:
