@@ -220,6 +220,9 @@ def run_b200(args):
         import torch.distributed as dist_
 
         dist = dist_
+        # stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) off it
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     cfg = load_cfg_24k()
@@ -322,10 +325,20 @@ def run_b200(args):
     tot_ms = sum(v[0] for v in prof.values()) or 1.0
     dom = max(prof.items(), key=lambda kv: kv[1][0]) if prof else ("none", (1.0, 1))
     dom_ms_per_launch = dom[1][0] / max(dom[1][1], 1)
-    chunks_per_launch = min(runner.query().wave, n_chunks)
+    # chunks one launch of that kernel processes (the frontend kernels run in sub-waves, the body in whole waves)
+    chunks_per_launch = n_chunks * args.steps / max(dom[1][1], 1)
     achieved = BYTES_PER_CHUNK_ALG * chunks_per_launch / (dom_ms_per_launch / 1e3) / 1e9
+    # DRAM bytes per launch of the same kernel from the committed `ncu --set full` capture (profiles/r1/ncu_traffic.json)
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1", "ncu_traffic.json")))
+        ent = tr.get(dom[0])
+        if ent and abs(ent["chunks_per_launch"] - chunks_per_launch) < 1:
+            traffic = ent["dram_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {
-        "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+        "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
         "peak_source": peak_src, "kernel": dom[0], "kernel_share_of_step": dom[1][0] / tot_ms,
         "kernel_ms_per_launch": dom_ms_per_launch, "chunks_per_launch": chunks_per_launch,
         "path_achieved_gbs": value / world * BYTES_PER_CHUNK_ALG / 1e9,
