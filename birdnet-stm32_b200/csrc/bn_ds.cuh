@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 namespace bn {
 
 // One DS block of models/dscnn.py:28-84 (ds_conv_block): DEPTHWISE_CONV_2D 3x3 (+ReLU6) -> CONV_2D 1x1
@@ -20,6 +22,11 @@ struct DsParams {
   int ih, iw, oh, ow, pt, pl;
   int NB, MT;             // chunks per CTA tile, 128-row MMA tiles per CTA tile
   int nst;                // input-tile buffers in shared memory: 1 = unpipelined, 2 / 3 = software pipeline (bn_ds.cu)
+  // tensor-core depthwise variant (bn_ds_tc.cu, stride 1): diag(w[tap]) 32x32 blocks, no-swizzle K-major, [C/32][9][1024 B]
+  const uint8_t* dw_img;
+  int MTd;                // 128-row M tiles of the depthwise GEMM over padded pixel indices
+  int plane_px;           // pixels per channel-chunk plane in shared memory (odd, covers the last tap of the last M tile)
+  int TRr;                // output rows per tile (runtime copy of the TR template parameter of k_ds)
   int ow_log, trow_log, cg_log, ppr_log;   // log2 of ow, TR*ow, C/4, iw*C/16
   int sw_sh, sw_mask, rw_log;              // swizzle: chunk ^= (row >> sw_sh) & sw_mask
   int dw_in_zp, dw_lo, dw_hi;
@@ -37,9 +44,14 @@ struct DsLaunch {
   int S, TR, add_mode;    // stride, output rows per tile, 0 none / 1 generic / 2 conv term = (o - zp2) << 19
   size_t smem;
   int ctas_per_sm;
+  int tcdw;               // 1 = run bn_ds_tc.cu (both convolutions on the tensor core)
 };
 
 int launch_ds(const int8_t* in, int8_t* out, int Bw, const DsParams& P, const DsLaunch& L, int num_sms, cudaStream_t st);
 size_t ds_smem_bytes(const DsParams& P, int S, int TR);
+
+int launch_dst(const int8_t* in, int8_t* out, int Bw, const DsParams& P, const DsLaunch& L, int num_sms, cudaStream_t st);
+size_t dst_smem_bytes(const DsParams& P);
+void dst_weight_image(const int8_t* w, int C, std::vector<uint8_t>& img);
 
 }  // namespace bn

@@ -130,6 +130,9 @@ struct Block {
   DsParams ds{};                  // fused depthwise + pointwise (+ADD) kernel
   DsLaunch dsl{};
   bool ds_ok = false;
+  DsParams dst{};                 // same block with the depthwise conv on the tensor core too (bn_ds_tc.cu)
+  DsLaunch dstl{};
+  bool dst_ok = false;
 };
 
 struct FastImpl {
@@ -466,6 +469,56 @@ static bool prep_ds(FastPlan& fp, FastImpl* im, Block& bl) {
       }
     }
     if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: C=%d N=%d S=%d nst=%d smem=%zu ctas/SM=%d tmem=%d\n", C, N, S, D.nst, L.smem, L.ctas_per_sm, D.tmem_cols);
+  }
+  // Variant with both convolutions on the tensor core (bn_ds_tc.cu) for stride-1 blocks whose diagonal depthwise
+  // operand fits.  It is prepared next to the default kernel and selected at run time by BN_OPT_FUSION bit 2: measured
+  // on B200 it is bit-exact but latency-bound (two MMA round trips per tile) and 1 - 8 % slower per layer than the
+  // CUDA-core depthwise, so it is off by default.  The tile height is re-chosen for it (fewer TMEM columns -> more CTAs).
+  L.tcdw = 0;
+  D.dw_img = nullptr; D.MTd = 0; D.plane_px = 0; D.TRr = TR;
+  bl.dst_ok = false;
+  if (S == 1 && C % 32 == 0 && C <= 128 && D.KP == C && D.pt == 1 && D.pl == 1) {
+    const int limit = 225 * 1024;
+    const int tc_cap = getenv("BN_DST_CTAS") ? atoi(getenv("BN_DST_CTAS")) : 3;   // 80 registers x 256 threads
+    const int min_ctas = 1;
+    int best_per = 0, best_tr = 0;
+    DsParams bestQ = D;
+    size_t best_sm = 0;
+    int best_cols = 0;
+    for (int cand = 0; cand < 2; cand++) {
+      int tr = TR;
+      if (cand == 1) { tr = 128 / D.ow; if (NB != 1 || tr < 1 || tr >= TR || D.oh % tr) continue; }
+      const int TWp = D.ow + 2, TRINp = tr + 2;
+      const int qtot = ((NB - 1) * TRINp + tr - 1) * TWp + D.ow;
+      const int MTd = (qtot + 127) / 128;
+      int ppx = MTd * 128 + 2 * TWp + 2;
+      if (ppx < NB * TRINp * TWp) ppx = NB * TRINp * TWp;
+      ppx |= 1;
+      DsParams Q = D;
+      Q.MTd = MTd; Q.plane_px = ppx; Q.TRr = tr;
+      Q.MT = tr * D.ow * NB / 128;
+      Q.trow_log = ilog2_exact(tr * D.ow);
+      if (Q.MT < 1 || Q.trow_log < 0) continue;
+      int c2 = 32;
+      while (c2 < MTd * C || c2 < Q.MT * N) c2 <<= 1;
+      const size_t sm = dst_smem_bytes(Q);
+      if (c2 > 512 || (int)sm > limit || ppx >= 16384) continue;
+      int per = (int)(limit / sm);
+      if (per > 512 / c2) per = 512 / c2;
+      if (per > tc_cap) per = tc_cap;
+      if (per > best_per) { best_per = per; best_tr = tr; bestQ = Q; best_sm = sm; best_cols = c2; }
+    }
+    if (best_per >= min_ctas) {
+      std::vector<uint8_t> img;
+      dst_weight_image((const int8_t*)(fp.h_blob + dw.off[0]), C, img);
+      bestQ.dw_img = (const uint8_t*)upload(im, img.data(), img.size());
+      if (bestQ.dw_img) {
+        bl.dst = bestQ; bl.dst.tmem_cols = best_cols; bl.dst.nst = 1;
+        bl.dstl = L; bl.dstl.smem = best_sm; bl.dstl.ctas_per_sm = best_per; bl.dstl.tcdw = 1; bl.dstl.TR = best_tr;
+        bl.dst_ok = true;
+        if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: tensor-core depthwise C=%d TR=%d MTd=%d plane_px=%d smem=%zu ctas/SM=%d tmem=%d\n", C, best_tr, bl.dst.MTd, bl.dst.plane_px, best_sm, best_per, best_cols);
+      }
+    }
   }
   return D.dw_rq && D.dw_rz && D.pw_rq && D.pw_rz;
 }
@@ -1364,9 +1417,10 @@ static int run_body(FastPlan& fp, int Bw, float* d_scores, int rounding, int mea
     int8_t* dwo = (int8_t*)im->slot_buf[bl.dw_slot];
     int8_t* bout = (int8_t*)im->slot_buf[bl.out_slot];
     if ((fp.fusion & 1) && bl.ds_ok && fp.use_tc && R == 0) {
-      snprintf(name, sizeof name, "K45_ds_%02d_c%d_n%d_s%d%s", bi, bl.ds.C, bl.ds.N, bl.dsl.S, bl.add_op >= 0 ? "_add" : "");
+      const bool tcdw = (fp.fusion & 4) && bl.dst_ok;
+      snprintf(name, sizeof name, "%s_%02d_c%d_n%d_s%d%s", tcdw ? "K45t_ds" : "K45_ds", bi, bl.ds.C, bl.ds.N, bl.dsl.S, bl.add_op >= 0 ? "_add" : "");
       if (prof) prof->begin(name, st);
-      int rc = launch_ds(bin, bout, Bw, bl.ds, bl.dsl, fp.num_sms, st);
+      int rc = tcdw ? launch_dst(bin, bout, Bw, bl.dst, bl.dstl, fp.num_sms, st) : launch_ds(bin, bout, Bw, bl.ds, bl.dsl, fp.num_sms, st);
       if (prof) prof->end(st);
       if (rc) return rc;
       (*launches)++;

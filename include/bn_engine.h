@@ -61,8 +61,9 @@ enum {
   BN_OPT_WAVE = 4,          /* chunks processed per internal wave (workspace is sized for it)           */
   BN_OPT_PROFILE = 5,       /* 1 = time every kernel with CUDA events, 0 = off, 2 = on + reset counters  */
   BN_OPT_TENSOR_CORE = 6,   /* 1 (default) = pointwise convs on tcgen05.mma kind::i8, 0 = dp4a CUDA-core GEMM */
-  BN_OPT_FUSION = 7         /* bit 0: depthwise + pointwise (+ADD) fused per DS block, bit 1: STFT + quantise +
-                               mel mixer fused per chunk (cluster kernel); default 3, 0 = one kernel per layer */
+  BN_OPT_FUSION = 7         /* bit 0: depthwise + pointwise (+ADD) fused per DS block, bit 1: tensor-core head (quantise +
+                               mel mixer + PWL LUT), bit 2: depthwise conv of stride-1 blocks on the tensor core too
+                               (shifted no-swizzle descriptors; bit-exact, measured slower, off); default 3 */
 };
 
 typedef struct bn_info {

@@ -86,7 +86,8 @@ def test_fused_plan_is_active_and_its_tensors_are_bit_exact(runner, graph, oracl
 
     assert runner.query().fast_path == 1
     B = oracle_spec.shape[0]
-    for fusion, taps in ((3, BLOCK_OUT_TAPS), (0, BLOCK_OUT_TAPS + DW_OUT_TAPS)):
+    # fusion 7 = the variant with the depthwise convs of the stride-1 blocks on the tensor core as well (bn_ds_tc.cu)
+    for fusion, taps in ((3, BLOCK_OUT_TAPS), (7, BLOCK_OUT_TAPS), (0, BLOCK_OUT_TAPS + DW_OUT_TAPS)):
         runner.set_option(L.BN_OPT_FUSION, fusion)
         try:
             got = runner.predict(oracle_spec)
@@ -112,6 +113,8 @@ def test_fused_kernels_equal_layer_kernels_on_ragged_batches(blob, cfg, synth):
     r = GpuRunner(blob, cfg, wave=16)
     try:
         fused = r.predict_pcm16(pcm, peak)
+        r.set_option(L.BN_OPT_FUSION, 7)            # tensor-core depthwise variant, ragged last tile
+        np.testing.assert_array_equal(fused, r.predict_pcm16(pcm, peak))
         r.set_option(L.BN_OPT_FUSION, 0)
         layer = r.predict_pcm16(pcm, peak)
         np.testing.assert_array_equal(fused, layer)
