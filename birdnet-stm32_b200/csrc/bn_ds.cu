@@ -36,7 +36,7 @@ __device__ __forceinline__ int rq64(int acc, int c_lo, int c_hi, int mult, int r
   return (v + rz + (v >> 31)) >> n;
 }
 __device__ __forceinline__ int clamp2(int v, int lo, int hi) { return max(lo, min(v, hi)); }
-template <int S, int TR, int ADD>
+template <int S, int TR, int ADD, int DWT>
 __global__ void __launch_bounds__(DS_THREADS, 2)
 k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles, DsParams P) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -85,9 +85,18 @@ k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles
   }
   // per-thread depthwise constants: the channel group of a thread is the same for all of its strips
   const int cg = tid & (CG - 1);
-  int4 w[9];
+  int4 w[DWT ? 1 : 9];                                // DWT 0: masked words, one tap of 4 channels each
+  int4 wl[DWT ? 3 : 1], wr[(DWT && S == 1) ? 3 : 1];   // DWT 1: per filter row, word j = (w[ky][0], w[ky][1], w[ky][2], 0) of channel 4 cg + j
+  if (DWT == 0) {
 #pragma unroll
-  for (int t = 0; t < 9; t++) w[t] = __ldg(P.dw_wm + t * CG + cg);
+    for (int t = 0; t < 9; t++) w[t] = __ldg(P.dw_wm + t * CG + cg);
+  } else {
+#pragma unroll
+    for (int ky = 0; ky < 3; ky++) {
+      wl[ky] = __ldg(P.dw_wt + (2 * ky) * CG + cg);
+      if (S == 1) wr[ky] = __ldg(P.dw_wt + (2 * ky + 1) * CG + cg);   // same taps one byte up: the right output column of a pair
+    }
+  }
   int4 drq[4];
 #pragma unroll
   for (int j = 0; j < 4; j++) drq[j] = __ldg(P.dw_rq + 4 * cg + j);
@@ -176,6 +185,82 @@ k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles
     }
   };
 
+  // ---- (2') depthwise 3x3 with the taps of a filter row along the dp4a axis ------------------------------------
+  // The pixel words of an input row (4 channels each) are byte-transposed with PRMT into one word per channel that
+  // holds 4 (stride 1) or 3 (stride 2) horizontally adjacent pixels; one dp4a against (w0, w1, w2, 0) then covers a
+  // whole filter row of one channel: 3 dp4a per output instead of 9 masked ones.  With stride 1 a thread produces two
+  // adjacent output columns from the same transposed words (second weight word = (0, w0, w1, w2)).
+  // A-operand byte offset of output pixel m for this thread's 4 channels: [m / 128][k-half][m % 128][RW] with the
+  // 16-byte chunk index XOR-swizzled by the row.  All swizzle periods are 8 rows and ow is a multiple of 8, so the
+  // swizzle term of a strip does not change from row to row, and the right pixel of an even / odd pair only flips
+  // chunk bit 0 when the swizzle uses row bit 0 (RW = 128).
+  const int a_jhop = 128 * (KP - RW);
+  const unsigned a_pairx = P.sw_sh == 0 ? 16u : 0u;
+  auto depthwise_t = [&](const unsigned char* sT, unsigned char* sA) {
+    constexpr int NCOL = S == 1 ? 2 : 1;              // output columns per thread
+    const int owp_log = P.ow_log - (S == 1 ? 1 : 0);
+    const int nst = nstrips >> (S == 1 ? 1 : 0);
+    for (int sidx = tid; sidx < nst; sidx += DS_THREADS) {
+      const int rest = sidx >> P.cg_log;
+      const int oxp = rest & ((1 << owp_log) - 1), bb = rest >> owp_log;
+      const int ox = oxp * NCOL;
+      const unsigned* tp = reinterpret_cast<const unsigned*>(sT) + ((size_t)(bb * TRIN) * TW + ox * S) * CG + cg;
+      const int mbase = ((bb * TR) << P.ow_log) + ox;
+      const int a_thr = a_kh_off + (((a_cc ^ ((mbase >> P.sw_sh) & P.sw_mask)) << 4) | a_b);
+      auto load_row = [&](int ir, unsigned (&t)[4]) {   // transposed words of input row ir of the tile
+        const unsigned* rp = tp + (size_t)ir * TW * CG;
+        const unsigned x0 = rp[0], x1 = rp[CG], x2 = rp[2 * CG];
+        const unsigned a = __byte_perm(x0, x1, 0x5140), b = __byte_perm(x0, x1, 0x7362);
+        if (S == 1) {
+          const unsigned x3 = rp[3 * CG];
+          const unsigned c = __byte_perm(x2, x3, 0x5140), d = __byte_perm(x2, x3, 0x7362);
+          t[0] = __byte_perm(a, c, 0x5410); t[1] = __byte_perm(a, c, 0x7632);
+          t[2] = __byte_perm(b, d, 0x5410); t[3] = __byte_perm(b, d, 0x7632);
+        } else {                                        // byte 3 meets a zero weight byte: any value will do
+          t[0] = __byte_perm(a, x2, 0x4410); t[1] = __byte_perm(a, x2, 0x5532);
+          t[2] = __byte_perm(b, x2, 0x6610); t[3] = __byte_perm(b, x2, 0x7732);
+        }
+      };
+      unsigned t0[4], t1[4], t2[4];
+      load_row(0, t0);
+      if (S == 1) load_row(1, t1);
+#pragma unroll
+      for (int r = 0; r < TR; r++) {
+        if (S == 2) load_row(2 * r + 1, t1);
+        load_row(r * S + 2, t2);
+        int aL[4], aR[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          const int w0 = c == 0 ? wl[0].x : c == 1 ? wl[0].y : c == 2 ? wl[0].z : wl[0].w;
+          const int w1 = c == 0 ? wl[1].x : c == 1 ? wl[1].y : c == 2 ? wl[1].z : wl[1].w;
+          const int w2 = c == 0 ? wl[2].x : c == 1 ? wl[2].y : c == 2 ? wl[2].z : wl[2].w;
+          aL[c] = __dp4a((int)t2[c], w2, __dp4a((int)t1[c], w1, __dp4a((int)t0[c], w0, 0)));
+          if (S == 1) {
+            const int v0 = c == 0 ? wr[0].x : c == 1 ? wr[0].y : c == 2 ? wr[0].z : wr[0].w;
+            const int v1 = c == 0 ? wr[1].x : c == 1 ? wr[1].y : c == 2 ? wr[1].z : wr[1].w;
+            const int v2 = c == 0 ? wr[2].x : c == 1 ? wr[2].y : c == 2 ? wr[2].z : wr[2].w;
+            aR[c] = __dp4a((int)t2[c], v2, __dp4a((int)t1[c], v1, __dp4a((int)t0[c], v0, 0)));
+          }
+        }
+        const int m = mbase + (r << P.ow_log);
+        const unsigned off = (unsigned)((m << P.rw_log) + (m >> 7) * a_jhop + a_thr);
+        *reinterpret_cast<unsigned*>(sA + off) = (pack4_sat(rq_hi(aL[0], drq[0].x, drq[0].y, drq[0].z) >> drq[0].w, rq_hi(aL[1], drq[1].x, drq[1].y, drq[1].z) >> drq[1].w,
+                                 rq_hi(aL[2], drq[2].x, drq[2].y, drq[2].z) >> drq[2].w, rq_hi(aL[3], drq[3].x, drq[3].y, drq[3].z) >> drq[3].w));
+        if (S == 1)
+          *reinterpret_cast<unsigned*>(sA + ((off + RW) ^ a_pairx)) = (pack4_sat(rq_hi(aR[0], drq[0].x, drq[0].y, drq[0].z) >> drq[0].w, rq_hi(aR[1], drq[1].x, drq[1].y, drq[1].z) >> drq[1].w,
+                                       rq_hi(aR[2], drq[2].x, drq[2].y, drq[2].z) >> drq[2].w, rq_hi(aR[3], drq[3].x, drq[3].y, drq[3].z) >> drq[3].w));
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          if (S == 1) { t0[c] = t1[c]; t1[c] = t2[c]; }
+          else t0[c] = t2[c];
+        }
+      }
+    }
+  };
+  auto run_dw = [&](const unsigned char* sT, unsigned char* sA) {
+    if (DWT) depthwise_t(sT, sA); else depthwise(sT, sA);
+  };
+
   // ---- (3) pointwise conv on the tensor core (one thread) -------------------------------------------------------
   auto issue_mma = [&](const unsigned char* sA, uint32_t tmem_d, uint64_t* bar) {
     tc_fence_after();
@@ -254,7 +339,7 @@ k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles
       cp_async_commit();
       cp_async_wait_all();
       __syncthreads();
-      depthwise(sT0, sA0);
+      run_dw(sT0, sA0);
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();
@@ -280,7 +365,7 @@ k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles
     if (nk > 0) {
       if (NST == 2) cp_async_wait_all(); else asm volatile("cp.async.wait_group 1;" ::: "memory");
       __syncthreads();
-      depthwise(sT0, sA0);
+      run_dw(sT0, sA0);
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();
@@ -293,7 +378,7 @@ k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles
       if (k + 1 < nk) {
         if (NST == 2) cp_async_wait_all(); else asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncthreads();
-        depthwise(sT0 + ((k + 1) % NST) * tile_bytes, sA0 + (ab ^ 1) * a_bytes);
+        run_dw(sT0 + ((k + 1) % NST) * tile_bytes, sA0 + (ab ^ 1) * a_bytes);
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
@@ -322,11 +407,11 @@ size_t ds_smem_bytes(const DsParams& P, int S, int TR) {
   return b + 1024;                                   // alignment slack
 }
 
-template <int S, int TR, int ADD>
+template <int S, int TR, int ADD, int DWT>
 static int launch_one(const int8_t* in, int8_t* out, int Bw, int ntiles, int grid, size_t smem, const DsParams& P, cudaStream_t st) {
   static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(k_ds<S, TR, ADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; }
-  k_ds<S, TR, ADD><<<grid, DS_THREADS, smem, st>>>(in, out, Bw, ntiles, P);
+  if (!attr) { cudaFuncSetAttribute(k_ds<S, TR, ADD, DWT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; }
+  k_ds<S, TR, ADD, DWT><<<grid, DS_THREADS, smem, st>>>(in, out, Bw, ntiles, P);
   return 0;
 }
 
@@ -335,7 +420,10 @@ int launch_ds(const int8_t* in, int8_t* out, int Bw, const DsParams& P, const Ds
   int grid = num_sms * L.ctas_per_sm;
   if (grid > ntiles) grid = ntiles;
   if (grid < 1) return 0;
-#define DS_CASE(s, tr, add) if (L.S == s && L.TR == tr && L.add_mode == add) return launch_one<s, tr, add>(in, out, Bw, ntiles, grid, L.smem, P, st)
+#define DS_CASE(s, tr, add)                                                                                         \
+  if (L.S == s && L.TR == tr && L.add_mode == add)                                                                  \
+    return L.dwt ? launch_one<s, tr, add, 1>(in, out, Bw, ntiles, grid, L.smem, P, st)                              \
+                 : launch_one<s, tr, add, 0>(in, out, Bw, ntiles, grid, L.smem, P, st)
   DS_CASE(1, 4, 0); DS_CASE(1, 4, 1); DS_CASE(1, 4, 2);
   DS_CASE(1, 8, 0); DS_CASE(1, 8, 1); DS_CASE(1, 8, 2);
   DS_CASE(2, 4, 0); DS_CASE(2, 8, 0);

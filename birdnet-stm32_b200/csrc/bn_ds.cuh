@@ -12,6 +12,8 @@ namespace bn {
 struct DsParams {
   // depthwise 3x3
   const int4* dw_wm;      // [9][C/4] masked weight words (byte j of word j = w[tap][4*cg + j], other bytes 0)
+  const int4* dw_wt;      // [3][2][C/4] filter-row words for the transposed depthwise (DsLaunch::dwt): word j of entry (ky, 0) =
+                          //   (w[ky][0], w[ky][1], w[ky][2], 0) of channel 4 cg + j, entry (ky, 1) = the same taps one byte up
   const int4* dw_rq;      // [C] {c_lo, c_hi, mult, n - 1}, saturating form: c = bias' * mult + 2^30 + (2^(n-1) + zp * 2^n) * 2^31
   const int* dw_rz;       // unused by the saturating form
   // pointwise 1x1
@@ -45,6 +47,7 @@ struct DsLaunch {
   size_t smem;
   int ctas_per_sm;
   int tcdw;               // 1 = run bn_ds_tc.cu (both convolutions on the tensor core)
+  int dwt;                // 1 = depthwise with filter rows along the dp4a axis (PRMT transpose, 3 dp4a per output), 0 = masked words (9)
 };
 
 int launch_ds(const int8_t* in, int8_t* out, int Bw, const DsParams& P, const DsLaunch& L, int num_sms, cudaStream_t st);

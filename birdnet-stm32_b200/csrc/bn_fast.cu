@@ -409,6 +409,20 @@ static bool prep_ds(FastPlan& fp, FastImpl* im, Block& bl) {
   D.pw_rq = (const int4*)upload(im, rq.data(), rq.size() * 4);
   D.pw_rz = (const int*)upload(im, rz.data(), rz.size() * 4);
   D.dw_wm = (const int4*)bl.dw.wm;
+  {  // filter-row words of the transposed depthwise: [ky][side][cg] int4, component j = channel 4 cg + j
+    const int8_t* w = (const int8_t*)(fp.h_blob + dw.off[0]);   // [3][3][C]
+    std::vector<int> wt((size_t)6 * C);
+    for (int ky = 0; ky < 3; ky++)
+      for (int c = 0; c < C; c++) {
+        const unsigned b0 = (uint8_t)w[(ky * 3 + 0) * C + c], b1 = (uint8_t)w[(ky * 3 + 1) * C + c], b2 = (uint8_t)w[(ky * 3 + 2) * C + c];
+        const unsigned left = b0 | (b1 << 8) | (b2 << 16);
+        wt[((size_t)(2 * ky) * (C / 4) + c / 4) * 4 + (c & 3)] = (int)left;
+        wt[((size_t)(2 * ky + 1) * (C / 4) + c / 4) * 4 + (c & 3)] = (int)(left << 8);
+      }
+    D.dw_wt = (const int4*)upload(im, wt.data(), wt.size() * 4);
+  }
+  L.dwt = getenv("BN_DW_MODE") ? atoi(getenv("BN_DW_MODE")) : 1;
+  if (D.ow % 8) L.dwt = 0;                       // row-invariant swizzle term and even/odd output pairs (bn_ds.cu)
   D.w_img = bl.tc.w_img;
   D.dw_in_zp = dw.p[BN_CONV_IN_ZP]; D.dw_lo = dw.p[BN_CONV_ACT_MIN]; D.dw_hi = dw.p[BN_CONV_ACT_MAX];
   D.pw_lo = pw.p[BN_CONV_ACT_MIN]; D.pw_hi = pw.p[BN_CONV_ACT_MAX];
