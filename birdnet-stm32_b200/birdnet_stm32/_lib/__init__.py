@@ -18,9 +18,15 @@ EXPORTS = (
     "bn_create", "bn_destroy", "bn_query", "bn_set_option", "bn_infer_spec_f32", "bn_frontend_pcm16",
     "bn_infer_pcm16", "bn_infer_pool", "bn_pool_scores", "bn_dump_tensor", "bn_launch_count",
     "bn_profile_read", "bn_host_alloc", "bn_host_free", "bn_last_error", "bn_version",
+    "bn_infer_wave_f32", "bn_infer_pool_wave_f32", "bn_frontend_wave_f32",
     # include/bn_features.h
     "bn_features_create", "bn_features_destroy", "bn_features_rows", "bn_features_pcm16",
+    # include/bn_ingest.h
+    "bn_ingest_create", "bn_ingest_destroy", "bn_ingest_out_len", "bn_ingest_num_chunks", "bn_ingest_filter",
+    "bn_ingest_window", "bn_ingest_chunks", "bn_ingest_launch_count",
 )
+
+BN_SAMPLE_FORMAT = {"s16": 0, "s24": 1, "s32": 2, "f32": 3, "u8": 4}
 
 BN_POOL = {"avg": 0, "mean": 0, "average": 0, "max": 1, "lme": 2, "log_mean_exp": 2, "log_mean_exponential": 2}
 BN_OPT_ROUNDING, BN_OPT_MEAN_VARIANT, BN_OPT_FORCE_GENERIC, BN_OPT_WAVE, BN_OPT_PROFILE, BN_OPT_TENSOR_CORE = 1, 2, 3, 4, 5, 6
@@ -98,6 +104,21 @@ def load():
     L.bn_features_destroy.restype = None
     L.bn_features_rows.argtypes = [vp]
     L.bn_features_pcm16.argtypes = [vp, vp, vp, i32, vp, vp]
+    L.bn_infer_wave_f32.argtypes = [vp, vp, vp, i32, vp, vp]
+    L.bn_infer_pool_wave_f32.argtypes = [vp, vp, vp, vp, i32, i32, f32, vp, vp]
+    L.bn_frontend_wave_f32.argtypes = [vp, vp, vp, i32, vp, vp]
+    i64 = C.c_int64
+    L.bn_ingest_create.argtypes = [i32, C.POINTER(vp)]
+    L.bn_ingest_destroy.argtypes = [vp]
+    L.bn_ingest_destroy.restype = None
+    L.bn_ingest_out_len.argtypes = [i64, i32, i32]
+    L.bn_ingest_out_len.restype = i64
+    L.bn_ingest_num_chunks.argtypes = [i64, i32, i32]
+    L.bn_ingest_filter.argtypes = [i32, i32, vp, i32, C.POINTER(i32), C.POINTER(i32)]
+    L.bn_ingest_window.argtypes = [vp, vp, i32, i64, i32, i32, i32, i32, vp, vp, vp]
+    L.bn_ingest_chunks.argtypes = [vp, vp, i32, i64, i32, i32, i32, i32, i32, vp, i32, C.POINTER(i32), vp, vp]
+    L.bn_ingest_launch_count.argtypes = [vp]
+    L.bn_ingest_launch_count.restype = i64
     _lib = L
     return L
 

@@ -10,14 +10,19 @@ Semantics follow the reference `birdnet_stm32/audio/io.py`:
     step = int(sr * (cd - overlap)) with overlap clamped to [0, cd - 0.1], plus an end-anchored
     tail chunk when samples remain.
 
-Decoding uses the stdlib `wave` module (soundfile/libsndfile are not part of this image).  Files
-that would need the reference's host-side resampling or channel averaging (sample rate different from
-the model's, multi-channel, non-16-bit) are reported with `UnsupportedAudio`; `evaluate()` skips them
-the way the reference skips unreadable files (`metrics.py:125-126`) and counts them.
+Container parsing is done here (RIFF/WAVE: PCM 8/16/24/32-bit and IEEE float32, any channel count;
+soundfile/libsndfile are not part of this image).  Mono 16-bit files at the model rate take the PCM16 path
+above.  Everything else -- other sample rates, several channels, other sample formats -- is what the
+reference handles with `y.mean(axis=1)` + `scipy.signal.resample_poly` on the host (`io.py:118-120`); here
+the raw interleaved samples go to the device once and `bn_ingest_*` (`audio/ingest.py`, `csrc/bn_ingest.cu`)
+decodes, mixes, resamples, peak-normalises and chunks them on the GPU.  Non-WAV containers raise
+`UnsupportedAudio`; `evaluate()` skips them the way the reference skips unreadable files
+(`metrics.py:125-126`) and counts them.
 """
 
 from __future__ import annotations
 
+import struct
 import wave
 
 import numpy as np
@@ -80,6 +85,49 @@ def read_wav_pcm16(path: str, max_frames: int | None = None) -> tuple[np.ndarray
         raise UnsupportedAudio(f"{path}: {exc}") from exc
 
 
+def read_wav_frames(path: str, max_seconds: float | None = None) -> tuple[np.ndarray, str, int, int]:
+    """RIFF/WAVE -> (interleaved raw samples, format, channels, sample_rate) without converting anything.
+
+    format is one of `s16 | s24 | s32 | f32 | u8` (`_lib.BN_SAMPLE_FORMAT`); the array is int16 / uint8 (3 bytes per
+    sample, packed) / int32 / float32 / uint8 with `frames * channels` samples.  `max_seconds` limits the read to
+    `int(min(frames, max_seconds * sr))` frames from the start, the window `load_audio_window` reads (`io.py:97-109`).
+    """
+    with open(path, "rb") as fh:
+        head = fh.read(12)
+        if len(head) < 12 or head[:4] != b"RIFF" or head[8:12] != b"WAVE":
+            raise UnsupportedAudio(f"{path}: not a RIFF/WAVE file")
+        fmt = None
+        while True:
+            hdr = fh.read(8)
+            if len(hdr) < 8:
+                raise UnsupportedAudio(f"{path}: no data chunk")
+            cid, size = hdr[:4], struct.unpack("<I", hdr[4:])[0]
+            if cid == b"fmt ":
+                body = fh.read(size + (size & 1))
+                tag, ch, sr, _, _, bits = struct.unpack("<HHIIHH", body[:16])
+                if tag == 0xFFFE and len(body) >= 26:
+                    tag = struct.unpack("<H", body[24:26])[0]
+                fmt = (tag, ch, sr, bits)
+            elif cid == b"data":
+                if fmt is None:
+                    raise UnsupportedAudio(f"{path}: data chunk before fmt chunk")
+                tag, ch, sr, bits = fmt
+                kind = {(1, 8): "u8", (1, 16): "s16", (1, 24): "s24", (1, 32): "s32", (3, 32): "f32"}.get((tag, bits))
+                if kind is None or ch < 1 or sr <= 0:
+                    raise UnsupportedAudio(f"{path}: WAVE format tag {tag} with {bits} bits is not decoded on this path")
+                bps = bits // 8
+                frames = size // (bps * ch)
+                if max_seconds and max_seconds > 0:
+                    frames = int(min(frames, float(max_seconds) * sr))
+                raw = fh.read(frames * bps * ch)
+                frames = len(raw) // (bps * ch)
+                raw = raw[: frames * bps * ch]
+                dt = {"u8": np.uint8, "s16": "<i2", "s24": np.uint8, "s32": "<i4", "f32": "<f4"}[kind]
+                return np.frombuffer(raw, dtype=dt), kind, ch, sr
+            else:
+                fh.seek(size + (size & 1), 1)
+
+
 def load_pcm16_window(path: str, sample_rate: int, max_duration: float | None = 60) -> tuple[np.ndarray, np.float32]:
     """(int16 mono window, file peak) -- the device-path twin of `load_audio_window`.
 
@@ -98,6 +146,15 @@ def load_audio_window(path: str, sample_rate: int = 24000, max_duration: float |
     """Reference-compatible float view: mono float32 in [-1, 1], peak normalised; empty on error."""
     try:
         pcm, peak = load_pcm16_window(path, sample_rate, max_duration)
+    except UnsupportedAudio:
+        # other rate / channels / sample format: decode + mix + resample + normalise on the device (no host resampler here)
+        try:
+            raw, kind, ch, sr0 = read_wav_frames(path, max_duration)
+        except Exception:
+            return np.empty((0,), dtype=np.float32)
+        from birdnet_stm32.audio.ingest import shared_ingest
+
+        return shared_ingest().window(raw, kind, ch, sr0, sample_rate, normalize=True)
     except Exception:
         return np.empty((0,), dtype=np.float32)
     y = pcm.astype(np.float32) / np.float32(32768.0)

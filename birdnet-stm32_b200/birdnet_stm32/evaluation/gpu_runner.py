@@ -179,6 +179,60 @@ class GpuRunner:
                                         L.BN_POOL[method], float(beta), _vp(out), None))
         return out
 
+    # -- float32 waveform chunks (files the device ingest resampled / mixed, audio/ingest.py) --------
+    def _wave_args(self, wave, peak):
+        w = np.ascontiguousarray(wave, dtype=np.float32)
+        if w.ndim != 2 or w.shape[1] != self.info.chunk_len:
+            raise ValueError(f"wave must be float32 [B, {self.info.chunk_len}], got {w.shape}")
+        pk = None
+        if peak is not None:
+            pk = np.ascontiguousarray(peak, dtype=np.float32)
+            if pk.shape != (w.shape[0],):
+                raise ValueError("peak must be float32 [B]")
+        return w, pk
+
+    def frontend_wave(self, wave: np.ndarray, peak: np.ndarray | None = None) -> np.ndarray:
+        """float32 chunks `[B, T]` -> the model's float input; what `make_chunks_for_file` computes per chunk."""
+        w, pk = self._wave_args(wave, peak)
+        B = w.shape[0]
+        out = np.empty((B, self.info.fft_bins, self.info.spec_width, 1), dtype=np.float32)
+        if B:
+            L.check(self._lib.bn_frontend_wave_f32(self._h, _vp(w), _vp(pk) if pk is not None else None, B, _vp(out), None))
+        return out
+
+    def predict_wave(self, wave: np.ndarray, peak: np.ndarray | None = None) -> np.ndarray:
+        """float32 chunks `[B, T]` -> chunk scores float32 `[B, C]`."""
+        w, pk = self._wave_args(wave, peak)
+        B = w.shape[0]
+        out = np.empty((B, self.num_classes), dtype=np.float32)
+        if B:
+            L.check(self._lib.bn_infer_wave_f32(self._h, _vp(w), _vp(pk) if pk is not None else None, B, _vp(out), None))
+        return out
+
+    def predict_pooled_wave(self, wave: np.ndarray, peak, file_offsets, pooling: str = "average", beta: float = 10.0) -> np.ndarray:
+        method = pooling.lower()
+        if method not in L.BN_POOL:
+            raise ValueError(f"Unsupported pooling method: {pooling}")
+        w, pk = self._wave_args(wave, peak)
+        offs = np.ascontiguousarray(file_offsets, dtype=np.int32)
+        F = offs.size - 1
+        if F < 0 or int(offs[-1]) != w.shape[0]:
+            raise ValueError("file_offsets must be [F+1] with file_offsets[F] == number of chunks")
+        out = np.empty((F, self.num_classes), dtype=np.float32)
+        L.check(self._lib.bn_infer_pool_wave_f32(self._h, _vp(w), _vp(pk) if pk is not None else None, _vp(offs), F,
+                                                 L.BN_POOL[method], float(beta), _vp(out), None))
+        return out
+
+    def infer_pool_wave_ptr(self, wave_ptr: int, peak_ptr: int | None, offs_ptr: int, F: int, pooling: str, beta: float,
+                            out_ptr: int, stream: int | None = None):
+        L.check(self._lib.bn_infer_pool_wave_f32(self._h, C.c_void_p(wave_ptr), C.c_void_p(peak_ptr) if peak_ptr else None,
+                                                 C.c_void_p(offs_ptr), F, L.BN_POOL[pooling.lower()], float(beta),
+                                                 C.c_void_p(out_ptr), C.c_void_p(stream) if stream else None))
+
+    def infer_wave_ptr(self, wave_ptr: int, peak_ptr: int | None, B: int, scores_ptr: int, stream: int | None = None):
+        L.check(self._lib.bn_infer_wave_f32(self._h, C.c_void_p(wave_ptr), C.c_void_p(peak_ptr) if peak_ptr else None, B,
+                                            C.c_void_p(scores_ptr), C.c_void_p(stream) if stream else None))
+
     def pool_scores(self, chunk_scores: np.ndarray, file_offsets, pooling: str = "average", beta: float = 10.0) -> np.ndarray:
         method = pooling.lower()
         if method not in L.BN_POOL:

@@ -17,7 +17,7 @@ import time
 
 import numpy as np
 
-from birdnet_stm32.audio.io import load_pcm16_chunks
+from birdnet_stm32.audio.io import UnsupportedAudio, load_pcm16_chunks, read_wav_frames
 from birdnet_stm32.evaluation.pooling import pool_scores
 from birdnet_stm32.models.frontend import normalize_frontend_name
 
@@ -33,6 +33,21 @@ def make_chunks_for_file(path: str, cfg: dict, frontend: str, mag_scale: str, n_
     sr, cd = int(cfg["sample_rate"]), float(cfg["chunk_duration"])
     try:
         pcm, peak = load_pcm16_chunks(path, sr, cd, chunk_overlap, max_duration=60)
+    except UnsupportedAudio:
+        # other rate / channels / sample format: float32 chunks from the device ingest (audio/ingest.py)
+        if frontend != "hybrid":
+            return []
+        if frontend_runner is None or not hasattr(frontend_runner, "frontend_wave"):
+            raise RuntimeError("this file needs the device ingest and frontend: pass frontend_runner=GpuRunner(...)")
+        try:
+            raw, kind, ch, sr0 = read_wav_frames(path, 60)
+        except Exception:
+            return []
+        from birdnet_stm32.audio.ingest import chunk_step, shared_ingest
+
+        T, step = chunk_step(sr, cd, chunk_overlap)
+        chunks = shared_ingest(int(getattr(frontend_runner, "device", 0))).chunks(raw, kind, ch, sr0, sr, T, step)
+        return [s for s in frontend_runner.frontend_wave(chunks)] if chunks.shape[0] else []
     except Exception:
         return []
     if pcm.shape[0] == 0:
@@ -129,30 +144,63 @@ def evaluate(model_runner, files: list[str], classes: list[str], cfg: dict, pool
 
     device_path = hasattr(model_runner, "predict_pooled") and frontend == "hybrid"
     if device_path:
-        pend_pcm: list[np.ndarray] = []
-        pend_peak: list[np.ndarray] = []
-        pend_meta: list[tuple[str, str]] = []
-        pend_counts: list[int] = []
+        # Files are batched across file boundaries.  Mono 16-bit files at the model rate travel as PCM16; every other
+        # WAV (other rate, several channels, other sample format) is decoded / mixed / resampled / peak-normalised /
+        # chunked on the device by bn_ingest_chunks straight into a float32 chunk buffer in HBM (reference: the host
+        # side of load_audio_window, audio/io.py:112-128) and classified from there.
+        pend: list[dict] = []          # {"path", "label", "kind": "pcm" | "wave", "n", ...} in file order
+        wave_state: dict = {}
+
+        def wave_buffer():
+            if not wave_state:
+                import torch
+
+                from birdnet_stm32.audio.ingest import GpuIngest, chunk_step
+
+                dev = torch.device("cuda", int(getattr(model_runner, "device", 0)))
+                T, step = chunk_step(sr, cd, overlap)
+                cap = int(device_batch_chunks) + int(60 * sr / step) + 8
+                wave_state.update(torch=torch, ingest=GpuIngest(dev.index), T=T, step=step, cap=cap, used=0,
+                                  buf=torch.empty((cap, T), dtype=torch.float32, device=dev), dev=dev)
+            return wave_state
 
         def flush():
             nonlocal total_chunks
-            if not pend_meta:
+            if not pend:
                 return
-            pcm = np.concatenate(pend_pcm, axis=0)
-            peak = np.concatenate(pend_peak, axis=0)
-            offs = np.zeros(len(pend_counts) + 1, dtype=np.int32)
-            offs[1:] = np.cumsum(pend_counts)
+            rows: dict[int, np.ndarray] = {}
             t0 = time.perf_counter()
-            pooled = model_runner.predict_pooled(pcm, peak, offs, pooling=pooling, beta=mep_beta)
+            pcm_ids = [i for i, f in enumerate(pend) if f["kind"] == "pcm"]
+            if pcm_ids:
+                pcm = np.concatenate([pend[i]["pcm"] for i in pcm_ids], axis=0)
+                peak = np.concatenate([pend[i]["peak"] for i in pcm_ids], axis=0)
+                offs = np.zeros(len(pcm_ids) + 1, dtype=np.int32)
+                offs[1:] = np.cumsum([pend[i]["n"] for i in pcm_ids])
+                pooled = model_runner.predict_pooled(pcm, peak, offs, pooling=pooling, beta=mep_beta)
+                rows.update(zip(pcm_ids, pooled))
+            wav_ids = [i for i, f in enumerate(pend) if f["kind"] == "wave"]
+            if wav_ids:
+                ws = wave_state
+                torch = ws["torch"]
+                offs = np.zeros(len(wav_ids) + 1, dtype=np.int32)
+                offs[1:] = np.cumsum([pend[i]["n"] for i in wav_ids])
+                d_offs = torch.from_numpy(offs).to(ws["dev"])
+                d_out = torch.empty((len(wav_ids), num_classes), dtype=torch.float32, device=ws["dev"])
+                torch.cuda.synchronize(ws["dev"])
+                model_runner.infer_pool_wave_ptr(ws["buf"].data_ptr(), None, d_offs.data_ptr(), len(wav_ids), pooling, mep_beta,
+                                                 d_out.data_ptr(), None)
+                rows.update(zip(wav_ids, d_out.cpu().numpy()))
+                ws["used"] = 0
+            n_all = sum(f["n"] for f in pend)
             if measure_latency:
-                per = (time.perf_counter() - t0) * 1000 / max(pcm.shape[0], 1)
-                latencies_ms.extend([per] * pcm.shape[0])
-            total_chunks += pcm.shape[0]
-            for (path, label), row in zip(pend_meta, pooled):
-                y_true.append(target_for(label))
-                y_scores.append(row)
-                per_file.append({"file": path, "label": label, "scores": row.tolist()})
-            pend_pcm.clear(); pend_peak.clear(); pend_meta.clear(); pend_counts.clear()
+                per = (time.perf_counter() - t0) * 1000 / max(n_all, 1)
+                latencies_ms.extend([per] * n_all)
+            total_chunks += n_all
+            for i, f in enumerate(pend):
+                y_true.append(target_for(f["label"]))
+                y_scores.append(rows[i])
+                per_file.append({"file": f["path"], "label": f["label"], "scores": rows[i].tolist()})
+            pend.clear()
 
         for path in files:
             label = os.path.basename(os.path.dirname(path))
@@ -160,19 +208,33 @@ def evaluate(model_runner, files: list[str], classes: list[str], cfg: dict, pool
                 continue
             try:
                 pcm, peak = load_pcm16_chunks(path, sr, cd, overlap, max_duration=60)
+                if pcm.shape[0] == 0:
+                    skipped += 1
+                    continue
+                pend.append({"path": path, "label": label, "kind": "pcm", "n": pcm.shape[0], "pcm": pcm,
+                             "peak": np.full((pcm.shape[0],), peak, dtype=np.float32)})
+            except UnsupportedAudio:
+                try:
+                    raw, kind, ch, sr0 = read_wav_frames(path, 60)
+                except Exception:
+                    skipped += 1
+                    continue
+                ws = wave_buffer()
+                n = ws["ingest"].chunks_to_ptr(raw, kind, ch, sr0, sr, ws["T"], ws["step"],
+                                               ws["buf"].data_ptr() + 4 * ws["used"] * ws["T"], ws["cap"] - ws["used"])
+                if n == 0:
+                    skipped += 1
+                    continue
+                ws["used"] += n
+                pend.append({"path": path, "label": label, "kind": "wave", "n": n})
             except Exception:
                 skipped += 1
                 continue
-            if pcm.shape[0] == 0:
-                skipped += 1
-                continue
-            pend_pcm.append(pcm)
-            pend_peak.append(np.full((pcm.shape[0],), peak, dtype=np.float32))
-            pend_meta.append((path, label))
-            pend_counts.append(pcm.shape[0])
-            if sum(pend_counts) >= device_batch_chunks:
+            if sum(f["n"] for f in pend) >= device_batch_chunks:
                 flush()
         flush()
+        if wave_state:
+            wave_state["ingest"].close()
     else:
         fr = frontend_runner if frontend_runner is not None else (model_runner if hasattr(model_runner, "frontend") else None)
         for path in files:

@@ -334,12 +334,12 @@ static int run_generic(bn_engine* e, std::vector<void*>& ptr, int Bw, cudaStream
 }
 
 // frontend for one wave: pcm (device) -> float32 graph input (device)
-static int run_frontend(bn_engine* e, const int16_t* d_pcm, const float* d_peak, int Bw, float* d_spec, cudaStream_t st) {
+static int run_frontend(bn_engine* e, const void* d_pcm, int f32, const float* d_peak, int Bw, float* d_spec, cudaStream_t st) {
   const bn_blob_header* h = e->hdr;
   if (h->frontend_kind != BN_FE_HYBRID)
     return set_err(BN_ERR_UNSUPPORTED, "frontend kind %u has no CUDA kernel yet", h->frontend_kind);
   if (e->prof.on) e->prof.begin("K1_stft_binmajor", st);
-  int rc = launch_stft_mag(d_pcm, d_peak, d_spec, e->d_mnmx, Bw, (int)h->chunk_len, (int)h->n_fft, (int)h->hop, (int)h->spec_width, st);
+  int rc = launch_stft_mag(d_pcm, f32, d_peak, d_spec, e->d_mnmx, Bw, (int)h->chunk_len, (int)h->n_fft, (int)h->hop, (int)h->spec_width, st);
   if (e->prof.on) e->prof.end(st);
   if (rc) return set_err(rc, "stft launch rejected (n_fft %u hop %u)", h->n_fft, h->hop);
   const long per = (long)(h->n_fft / 2 + 1) * h->spec_width;
@@ -353,13 +353,13 @@ static int run_frontend(bn_engine* e, const int16_t* d_pcm, const float* d_peak,
 }
 
 // One wave of the whole path on device data.  d_pcm may be NULL (then d_spec is the input).
-static int run_wave(bn_engine* e, const int16_t* d_pcm, const float* d_peak, const float* d_spec_in, int Bw,
+static int run_wave(bn_engine* e, const void* d_pcm, int f32, const float* d_peak, const float* d_spec_in, int Bw,
                     float* d_scores_out, cudaStream_t st) {
   const bn_blob_header* h = e->hdr;
   if (use_fast(e)) {
     int rc;
     Profiler* pr = e->prof.on ? &e->prof : nullptr;
-    if (d_pcm) rc = fast_run_pcm(e->fast, d_pcm, d_peak, Bw, d_scores_out, e->rounding, e->mean_variant, st, &e->launches, pr);
+    if (d_pcm) rc = fast_run_pcm(e->fast, d_pcm, f32, d_peak, Bw, d_scores_out, e->rounding, e->mean_variant, st, &e->launches, pr);
     else rc = fast_run_spec(e->fast, d_spec_in, Bw, d_scores_out, e->rounding, e->mean_variant, st, &e->launches, pr);
     if (rc) return set_err(rc, "fused plan failed: %s", cudaGetErrorString(cudaGetLastError()));
     e->last_wave_B = Bw;
@@ -367,7 +367,7 @@ static int run_wave(bn_engine* e, const int16_t* d_pcm, const float* d_peak, con
   }
   std::vector<void*> ptr = e->buf;
   if (d_pcm) {
-    int rc = run_frontend(e, d_pcm, d_peak, Bw, (float*)ptr[h->input_tensor], st);
+    int rc = run_frontend(e, d_pcm, f32, d_peak, Bw, (float*)ptr[h->input_tensor], st);
     if (rc) return rc;
   } else {
     ptr[h->input_tensor] = (void*)d_spec_in;
@@ -393,8 +393,11 @@ static int pick_wave(const bn_engine* e, int B) { return B < e->wave_opt ? B : e
 
 // Shared implementation.  Exactly one of (pcm, spec) is non-NULL.  If offs != NULL pooled file
 // scores are produced instead of chunk scores.
-static int infer_impl(bn_engine* e, const int16_t* pcm, const float* peak, const float* spec, int B,
+// `pcm` holds int16 samples (sbytes = 2) or float32 waveform samples (sbytes = 4).
+static int infer_impl(bn_engine* e, const void* pcm_v, int sbytes, const float* peak, const float* spec, int B,
                       const int32_t* offs, int F, int pooling, float beta, float* out, cudaStream_t user_stream) {
+  const char* pcm = (const char*)pcm_v;
+  const int f32 = sbytes == 4;
   int rc = check_engine(e);
   if (rc) return rc;
   if (B < 0 || (!pcm && !spec) || !out) return set_err(BN_ERR_ARG, "bad arguments");
@@ -420,7 +423,7 @@ static int infer_impl(bn_engine* e, const int16_t* pcm, const float* peak, const
   const bool pooled = offs != nullptr;
   // chunk scores live on the device when pooling or when the caller's buffers are host memory
   const bool scores_internal = pooled || !dev_out;
-  rc = ensure_io(e, dev_in ? 0 : wave, scores_internal ? (size_t)B * C + 1 : 0);
+  rc = ensure_io(e, dev_in ? 0 : wave * (sbytes / 2), scores_internal ? (size_t)B * C + 1 : 0);
   if (rc) return rc;
   float* d_scores = scores_internal ? e->d_scores : out;
 
@@ -429,18 +432,18 @@ static int infer_impl(bn_engine* e, const int16_t* pcm, const float* peak, const
   for (int w = 0; w < nw; w++) {
     const int b0 = w * wave;
     const int Bw = (B - b0) < wave ? (B - b0) : wave;
-    const int16_t* d_pcm = nullptr;
+    const void* d_pcm = nullptr;
     const float* d_peak = nullptr;
     const float* d_spec = nullptr;
     if (dev_in) {
-      if (pcm) { d_pcm = pcm + (long)b0 * h->chunk_len; d_peak = peak ? peak + b0 : nullptr; }
+      if (pcm) { d_pcm = pcm + (size_t)b0 * h->chunk_len * sbytes; d_peak = peak ? peak + b0 : nullptr; }
       else d_spec = spec + (long)b0 * in_elems;
     } else {
       const int slot = w & 1;
       // the compute of wave w-2 must have consumed this slot before it is overwritten
       CU(cudaStreamWaitEvent(e->s_copy, e->ev_comp[slot], 0));
       if (pcm) {
-        CU(cudaMemcpyAsync(e->d_pcm[slot], pcm + (long)b0 * h->chunk_len, sizeof(int16_t) * (size_t)h->chunk_len * Bw, cudaMemcpyHostToDevice, e->s_copy));
+        CU(cudaMemcpyAsync(e->d_pcm[slot], pcm + (size_t)b0 * h->chunk_len * sbytes, (size_t)sbytes * h->chunk_len * Bw, cudaMemcpyHostToDevice, e->s_copy));
         if (peak) CU(cudaMemcpyAsync(e->d_peak[slot], peak + b0, sizeof(float) * Bw, cudaMemcpyHostToDevice, e->s_copy));
         d_pcm = e->d_pcm[slot];
         d_peak = peak ? e->d_peak[slot] : nullptr;
@@ -453,7 +456,7 @@ static int infer_impl(bn_engine* e, const int16_t* pcm, const float* peak, const
       CU(cudaEventRecord(e->ev_h2d[slot], e->s_copy));
       CU(cudaStreamWaitEvent(st, e->ev_h2d[slot], 0));
     }
-    rc = run_wave(e, d_pcm, d_peak, d_spec, Bw, d_scores + (long)b0 * C, st);
+    rc = run_wave(e, d_pcm, f32, d_peak, d_spec, Bw, d_scores + (long)b0 * C, st);
     if (rc) return rc;
     if (!dev_in) CU(cudaEventRecord(e->ev_comp[w & 1], st));
   }
@@ -495,16 +498,21 @@ static int infer_impl(bn_engine* e, const int16_t* pcm, const float* peak, const
 }
 
 extern "C" int bn_infer_spec_f32(bn_engine* e, const float* spec, int B, float* scores, void* stream) {
-  return infer_impl(e, nullptr, nullptr, spec, B, nullptr, 0, 0, 0.f, scores, (cudaStream_t)stream);
+  return infer_impl(e, nullptr, 2, nullptr, spec, B, nullptr, 0, 0, 0.f, scores, (cudaStream_t)stream);
 }
 
 extern "C" int bn_infer_pcm16(bn_engine* e, const int16_t* pcm, const float* peak, int B, float* scores, void* stream) {
   if (!pcm) return set_err(BN_ERR_ARG, "pcm is NULL");
-  return infer_impl(e, pcm, peak, nullptr, B, nullptr, 0, 0, 0.f, scores, (cudaStream_t)stream);
+  return infer_impl(e, pcm, 2, peak, nullptr, B, nullptr, 0, 0, 0.f, scores, (cudaStream_t)stream);
 }
 
-extern "C" int bn_infer_pool(bn_engine* e, const int16_t* pcm, const float* peak, const int32_t* file_offsets, int F,
-                             int pooling, float beta, float* file_scores, void* stream) {
+extern "C" int bn_infer_wave_f32(bn_engine* e, const float* wave, const float* peak, int B, float* scores, void* stream) {
+  if (!wave) return set_err(BN_ERR_ARG, "wave is NULL");
+  return infer_impl(e, wave, 4, peak, nullptr, B, nullptr, 0, 0, 0.f, scores, (cudaStream_t)stream);
+}
+
+static int infer_pool_any(bn_engine* e, const void* pcm, int sbytes, const float* peak, const int32_t* file_offsets, int F,
+                          int pooling, float beta, float* file_scores, void* stream) {
   if (!pcm && F > 0) return set_err(BN_ERR_ARG, "pcm is NULL");
   if (!file_offsets) return set_err(BN_ERR_ARG, "file_offsets is NULL");
   int B = 0;
@@ -516,11 +524,22 @@ extern "C" int bn_infer_pool(bn_engine* e, const int16_t* pcm, const float* peak
     for (int f = 0; f < F; f++)
       if (file_offsets[f] > file_offsets[f + 1] || file_offsets[f] < 0) return set_err(BN_ERR_ARG, "file_offsets must be non-decreasing");
   }
-  static const int16_t dummy[2] = {0, 0};
-  return infer_impl(e, pcm ? pcm : dummy, peak, nullptr, B, file_offsets, F, pooling, beta, file_scores, (cudaStream_t)stream);
+  static const float dummy[1] = {0.f};
+  return infer_impl(e, pcm ? pcm : (const void*)dummy, sbytes, peak, nullptr, B, file_offsets, F, pooling, beta, file_scores, (cudaStream_t)stream);
 }
 
-extern "C" int bn_frontend_pcm16(bn_engine* e, const int16_t* pcm, const float* peak, int B, float* spec_out, void* stream) {
+extern "C" int bn_infer_pool(bn_engine* e, const int16_t* pcm, const float* peak, const int32_t* file_offsets, int F,
+                             int pooling, float beta, float* file_scores, void* stream) {
+  return infer_pool_any(e, pcm, 2, peak, file_offsets, F, pooling, beta, file_scores, stream);
+}
+
+extern "C" int bn_infer_pool_wave_f32(bn_engine* e, const float* wave, const float* peak, const int32_t* file_offsets, int F,
+                                      int pooling, float beta, float* file_scores, void* stream) {
+  return infer_pool_any(e, wave, 4, peak, file_offsets, F, pooling, beta, file_scores, stream);
+}
+
+static int frontend_any(bn_engine* e, const void* pcm_v, int sbytes, const float* peak, int B, float* spec_out, void* stream) {
+  const char* pcm = (const char*)pcm_v;
   int rc = check_engine(e);
   if (rc) return rc;
   if (!pcm || !spec_out || B < 0) return set_err(BN_ERR_ARG, "bad arguments");
@@ -533,27 +552,35 @@ extern "C" int bn_frontend_pcm16(bn_engine* e, const int16_t* pcm, const float* 
   const int wave = pick_wave(e, B);
   rc = ensure_workspace(e, wave);
   if (rc) return rc;
-  rc = ensure_io(e, dev_in ? 0 : wave, 0);
+  rc = ensure_io(e, dev_in ? 0 : wave * (sbytes / 2), 0);
   if (rc) return rc;
   cudaStream_t st = dev_in ? (cudaStream_t)stream : e->s_comp;
   for (int b0 = 0; b0 < B; b0 += wave) {
     const int Bw = (B - b0) < wave ? (B - b0) : wave;
-    const int16_t* d_pcm = pcm + (long)b0 * h->chunk_len;
+    const void* d_pcm = pcm + (size_t)b0 * h->chunk_len * sbytes;
     const float* d_peak = peak ? peak + b0 : nullptr;
     float* d_spec = spec_out + (long)b0 * in_elems;
     if (!dev_in) {
-      CU(cudaMemcpyAsync(e->d_pcm[0], d_pcm, sizeof(int16_t) * (size_t)h->chunk_len * Bw, cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(e->d_pcm[0], d_pcm, (size_t)sbytes * h->chunk_len * Bw, cudaMemcpyHostToDevice, st));
       if (peak) CU(cudaMemcpyAsync(e->d_peak[0], d_peak, sizeof(float) * Bw, cudaMemcpyHostToDevice, st));
       d_pcm = e->d_pcm[0];
       d_peak = peak ? e->d_peak[0] : nullptr;
       d_spec = (float*)e->buf[h->input_tensor];
     }
-    rc = run_frontend(e, d_pcm, d_peak, Bw, d_spec, st);
+    rc = run_frontend(e, d_pcm, sbytes == 4, d_peak, Bw, d_spec, st);
     if (rc) return rc;
     if (!dev_in) CU(cudaMemcpyAsync(spec_out + (long)b0 * in_elems, d_spec, sizeof(float) * (size_t)in_elems * Bw, cudaMemcpyDeviceToHost, st));
   }
   if (!dev_in) CU(cudaStreamSynchronize(st));
   return BN_OK;
+}
+
+extern "C" int bn_frontend_pcm16(bn_engine* e, const int16_t* pcm, const float* peak, int B, float* spec_out, void* stream) {
+  return frontend_any(e, pcm, 2, peak, B, spec_out, stream);
+}
+
+extern "C" int bn_frontend_wave_f32(bn_engine* e, const float* wave, const float* peak, int B, float* spec_out, void* stream) {
+  return frontend_any(e, wave, 4, peak, B, spec_out, stream);
 }
 
 extern "C" int bn_pool_scores(bn_engine* e, const float* chunk_scores, const int32_t* file_offsets, int F, int C,

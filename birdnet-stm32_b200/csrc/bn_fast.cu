@@ -1485,7 +1485,7 @@ static int run_body(FastPlan& fp, int Bw, float* d_scores, int rounding, int mea
 // buffer each time and K2 consumes them straight away, so the 270 KB/chunk intermediate stays in the 126 MB L2
 // instead of making a round trip through HBM.
 
-int fast_run_pcm(FastPlan& fp, const int16_t* d_pcm, const float* d_peak, int Bw, float* d_scores, int rounding,
+int fast_run_pcm(FastPlan& fp, const void* d_pcm, int f32, const float* d_peak, int Bw, float* d_scores, int rounding,
                  int mean_variant, cudaStream_t st, int64_t* launches, Profiler* prof) {
   FastImpl* im = fp.impl;
   if (!im || Bw > fp.wave) return BN_ERR_STATE;
@@ -1496,7 +1496,7 @@ int fast_run_pcm(FastPlan& fp, const int16_t* d_pcm, const float* d_peak, int Bw
   for (int b0 = 0; b0 < Bw; b0 += FE_SUBWAVE) {
     const int nb = Bw - b0 < FE_SUBWAVE ? Bw - b0 : FE_SUBWAVE;
     if (prof) prof->begin("K1_stft", st);
-    rc = launch_stft_mag_fm(d_pcm + (size_t)b0 * T, d_peak ? d_peak + b0 : nullptr, im->d_mags, im->d_mnmx + 2 * b0, nb, T, (int)h->n_fft,
+    rc = launch_stft_mag_fm((const char*)d_pcm + (size_t)b0 * T * (f32 ? 4 : 2), f32, d_peak ? d_peak + b0 : nullptr, im->d_mags, im->d_mnmx + 2 * b0, nb, T, (int)h->n_fft,
                             (int)h->hop, im->W, im->ldk, st);
     if (prof) prof->end(st);
     if (rc) return rc;

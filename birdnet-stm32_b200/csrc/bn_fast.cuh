@@ -61,7 +61,8 @@ void fast_plan_build(FastPlan& fp, const uint8_t* h_blob, const bn_blob_header* 
 void fast_plan_destroy(FastPlan& fp);
 int fast_plan_alloc_workspace(FastPlan& fp, int wave, size_t* total_bytes);
 void fast_plan_free_workspace(FastPlan& fp);
-int fast_run_pcm(FastPlan& fp, const int16_t* d_pcm, const float* d_peak, int Bw, float* d_scores, int rounding,
+// d_pcm: int16 [Bw, T] (f32 = 0) or float32 waveform chunks (f32 = 1)
+int fast_run_pcm(FastPlan& fp, const void* d_pcm, int f32, const float* d_peak, int Bw, float* d_scores, int rounding,
                  int mean_variant, cudaStream_t st, int64_t* launches, Profiler* prof);
 int fast_run_spec(FastPlan& fp, const float* d_spec, int Bw, float* d_scores, int rounding, int mean_variant,
                   cudaStream_t st, int64_t* launches, Profiler* prof);

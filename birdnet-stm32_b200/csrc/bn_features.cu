@@ -337,7 +337,7 @@ extern "C" int bn_features_pcm16(bn_features* f, const int16_t* pcm, const float
       d_peak = peak ? f->d_peak : nullptr;
       d_out = f->d_out;
     }
-    int rc = launch_stft_mag_fm(d_pcm, d_peak, f->d_mags, f->d_mnmx, nb, T, f->p.n_fft, f->hop, f->Wk, KF_LDK, st);
+    int rc = launch_stft_mag_fm(d_pcm, 0, d_peak, f->d_mags, f->d_mnmx, nb, T, f->p.n_fft, f->hop, f->Wk, KF_LDK, st);
     if (rc) return set_error(rc, "STFT kernel launch failed");
     k_feat<<<nb, KF_THREADS, f->smem, st>>>(f->d_mags, d_out, f->dev);
     FCU(cudaGetLastError());

@@ -15,6 +15,7 @@
 // (magnitudes are >= +0, so their IEEE bit patterns order like unsigned integers).
 #include "bn_common.cuh"
 #include <cmath>
+#include <type_traits>
 
 #include "bn_kernels.cuh"
 
@@ -75,7 +76,7 @@ __device__ __forceinline__ void fft16(float2 (&v)[16]) {
 
 // dynamic smem layout:
 //   float  xs[span + 16]                    span = 31*hop + 512 floats (16-byte aligned, indexed like the global buffer)
-//   uint4  sraw[(span + 16) / 8]            raw int16 samples of the NEXT tile (cp.async prefetch)
+//   uint4  sraw[(span + 16) / G]            raw samples of the NEXT tile (cp.async prefetch), G = 8 int16 or 4 float32 per 16 bytes
 //   float2 zbuf[16][256+16]                 per half-warp exchange buffer (padded)
 //   float  tile[257][33]                    magnitude tile (bin-major variant only)
 //   float  red[2*8]
@@ -83,15 +84,22 @@ __device__ __forceinline__ void fft16(float2 (&v)[16]) {
 // The CTA is persistent over (chunk, 32-frame group) tiles.  Everything a thread needs that does not depend on the
 // data -- its 32 window samples (pre-scaled by 1/2 for the real-FFT split), the 15 inter-pass twiddles W256^(l k1) and
 // the 8 split twiddles W512^(l + 16 j) -- is loaded once into registers and reused for every frame.
-template <bool FRAME_MAJOR>
+//
+// F32IN: the chunks are float32 waveforms (what the reference's make_chunks_for_file hands to the frontend after
+// load_audio_window resampled / mixed the file, audio/io.py:118-128); the scale is then 1 / peak, or exactly 1 without a peak.
+template <bool FRAME_MAJOR, bool F32IN>
 __global__ void __launch_bounds__(FE_THREADS, 2)
-k_stft_mag(const int16_t* __restrict__ pcm, const float* __restrict__ peak, float* __restrict__ out,
+k_stft_mag(const void* __restrict__ pcm_v, const float* __restrict__ peak, float* __restrict__ out,
            unsigned* __restrict__ mnmx, const float4* __restrict__ tables, int T, int hop, int W, int ldk, int B) {
+  using raw_t = typename std::conditional<F32IN, float, int16_t>::type;
+  constexpr int G = F32IN ? 4 : 8;                    // samples per 16-byte group
+  constexpr int GL = F32IN ? 2 : 3;
+  const raw_t* pcm = reinterpret_cast<const raw_t*>(pcm_v);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int span = (FRAMES_PER_CTA - 1) * hop + NFFT;
   float* xs = reinterpret_cast<float*>(smem_raw);
-  uint4* sraw = reinterpret_cast<uint4*>(xs + ((span + 16 + 3) & ~3));      // (span + 16) / 8 groups of 8 int16
-  float2* zbuf = reinterpret_cast<float2*>(sraw + ((span + 16 + 7) >> 3));
+  uint4* sraw = reinterpret_cast<uint4*>(xs + ((span + 16 + 3) & ~3));      // (span + 16) / G groups of G samples
+  float2* zbuf = reinterpret_cast<float2*>(sraw + ((span + 16 + G - 1) >> GL));
   float* tile = reinterpret_cast<float*>(zbuf + 16 * (NC + 16));
   float* red = FRAME_MAJOR ? tile : tile + BINS * TILE_LD;
 
@@ -117,9 +125,9 @@ k_stft_mag(const int16_t* __restrict__ pcm, const float* __restrict__ peak, floa
 #pragma unroll
   for (int j = 0; j < 8; j++) tws[j] = __ldg(tw512 + l + 16 * j);
 
-  // the PCM pointer is only known to be 2-byte aligned: index samples relative to its 16-byte-aligned floor
-  const int a0 = (int)((reinterpret_cast<uintptr_t>(pcm) >> 1) & 7);
-  const int16_t* pcm_al = pcm - a0;
+  // the sample pointer is only known to be element aligned: index samples relative to its 16-byte-aligned floor
+  const int a0 = (int)((reinterpret_cast<uintptr_t>(pcm) / sizeof(raw_t)) & (G - 1));
+  const raw_t* pcm_al = pcm - a0;
   const long total = (long)B * T;
   const int groups_w = W / FRAMES_PER_CTA;
   const int ntiles = B * groups_w;
@@ -131,18 +139,23 @@ k_stft_mag(const int16_t* __restrict__ pcm, const float* __restrict__ peak, floa
     t0 = (tile_id - b * groups_w) * FRAMES_PER_CTA;
     chunk_base = (long)b * T + a0;                        // in pcm_al sample indices
     const long g_lo = chunk_base + (long)t0 * hop - NFFT / 2;
-    g_first = g_lo & ~7L;
+    g_first = g_lo & ~(long)(G - 1);
     shift = (int)(g_lo - g_first);
-    ngroups = (shift + span + 7) >> 3;
+    ngroups = (shift + span + G - 1) >> GL;
   };
   auto prefetch = [&](int tile_id) {
     int b, t0, shift, ngroups; long chunk_base, g_first;
     tile_geom(tile_id, b, t0, chunk_base, g_first, shift, ngroups);
     for (int grp = tid; grp < ngroups; grp += FE_THREADS) {
-      const long g = g_first + 8L * grp;
-      if (g >= a0 && g + 8 <= a0 + total) {
+      const long g = g_first + (long)G * grp;
+      if (g >= a0 && g + G <= a0 + total) {
         cp_async16_fe(sraw + grp, pcm_al + g);
-      } else {                                            // first / last samples of the whole buffer
+      } else if (F32IN) {                                 // first / last samples of the whole buffer
+        unsigned fv[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) fv[j] = (g + j >= a0 && g + j < a0 + total) ? __float_as_uint((float)pcm_al[g + j]) : 0u;
+        sraw[grp] = make_uint4(fv[0], fv[1], fv[2], fv[3]);
+      } else {
         unsigned short sv[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) sv[j] = (g + j >= a0 && g + j < a0 + total) ? (unsigned short)pcm_al[g + j] : (unsigned short)0;
@@ -160,11 +173,18 @@ k_stft_mag(const int16_t* __restrict__ pcm, const float* __restrict__ peak, floa
     // ---- samples [s0, s0 + span) of chunk b as float32, zero outside [0, T) -------------------------------------
     const float pk = peak ? __ldg(peak + b) : 0.0f;
     // y = (s / 32768) / peak (audio/io.py:114-126) as one multiply by the rounded reciprocal (<= 1.5 ulp from the reference)
-    const float cs = pk > 0.0f ? __fdiv_rn(1.0f, 32768.0f * pk) : (1.0f / 32768.0f);
+    const float cs = F32IN ? (pk > 0.0f ? __fdiv_rn(1.0f, pk) : 1.0f) : (pk > 0.0f ? __fdiv_rn(1.0f, 32768.0f * pk) : (1.0f / 32768.0f));
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     for (int grp = tid; grp < ngroups; grp += FE_THREADS) {
-      const long rel = g_first + 8L * grp - chunk_base;   // chunk-relative index of the group's first sample
+      const long rel = g_first + (long)G * grp - chunk_base;   // chunk-relative index of the group's first sample
       const uint4 wv = sraw[grp];
+      if (F32IN) {
+        float f4[4] = {__uint_as_float(wv.x), __uint_as_float(wv.y), __uint_as_float(wv.z), __uint_as_float(wv.w)};
+#pragma unroll
+        for (int j = 0; j < 4; j++) f4[j] = (rel + j >= 0 && rel + j < T) ? f4[j] * cs : 0.0f;   // zero padding outside [0, T)
+        *reinterpret_cast<float4*>(xs + 4 * grp) = make_float4(f4[0], f4[1], f4[2], f4[3]);
+        continue;
+      }
       unsigned ww[4] = {wv.x, wv.y, wv.z, wv.w};
       if (rel < 0 || rel + 8 > T) {                       // chunk edge: samples outside [0, T) are zero padding
 #pragma unroll
@@ -289,9 +309,9 @@ static const float4* stft_tables() {
   return d_tab;
 }
 
-size_t stft_smem_bytes(int hop, bool frame_major) {
+size_t stft_smem_bytes(int hop, bool frame_major, bool f32) {
   const int span = (FRAMES_PER_CTA - 1) * hop + NFFT;
-  size_t b = sizeof(float) * ((span + 16 + 3) & ~3) + 16 * (size_t)((span + 16 + 7) >> 3);
+  size_t b = sizeof(float) * ((span + 16 + 3) & ~3) + 16 * (size_t)(f32 ? ((span + 16 + 3) >> 2) : ((span + 16 + 7) >> 3));
   b += sizeof(float2) * 16 * (NC + 16) + sizeof(float) * 16;
   b += frame_major ? 0 : sizeof(float) * BINS * TILE_LD;
   return b;
@@ -309,42 +329,50 @@ static int stft_grid(int B, int W, size_t smem) {
   return g < ntiles ? g : ntiles;
 }
 
-int launch_stft_mag(const int16_t* pcm, const float* peak, float* out, unsigned* mnmx, int B, int T, int n_fft,
+static void set_stft_attrs() {
+  cudaFuncSetAttribute(k_stft_mag<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(k_stft_mag<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(k_stft_mag<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(k_stft_mag<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+
+int launch_stft_mag(const void* pcm, int f32, const float* peak, float* out, unsigned* mnmx, int B, int T, int n_fft,
                     int hop, int W, cudaStream_t st) {
   if (n_fft != NFFT) return BN_ERR_UNSUPPORTED;
-  const size_t smem = stft_smem_bytes(hop, false);
+  const size_t smem = stft_smem_bytes(hop, false, f32 != 0);
   if (smem > 227 * 1024) return BN_ERR_UNSUPPORTED;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(k_stft_mag<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(k_stft_mag<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    set_stft_attrs();
     attr_done = true;
   }
   const float4* tab = stft_tables();
   if (!tab) return BN_ERR_CUDA;
   if (W % FRAMES_PER_CTA) return BN_ERR_UNSUPPORTED;
   k_init_minmax<<<(B + 255) / 256, 256, 0, st>>>(mnmx, B);
-  k_stft_mag<false><<<stft_grid(B, W, smem), FE_THREADS, smem, st>>>(pcm, peak, out, mnmx, tab, T, hop, W, 0, B);
+  if (f32) k_stft_mag<false, true><<<stft_grid(B, W, smem), FE_THREADS, smem, st>>>(pcm, peak, out, mnmx, tab, T, hop, W, 0, B);
+  else k_stft_mag<false, false><<<stft_grid(B, W, smem), FE_THREADS, smem, st>>>(pcm, peak, out, mnmx, tab, T, hop, W, 0, B);
   return 0;
 }
 
 // Frame-major variant for the fused plan: out float32 [B, W, ldk] (raw magnitudes, bins 0..256 of
 // each frame contiguous; columns >= 257 are left untouched).
-int launch_stft_mag_fm(const int16_t* pcm, const float* peak, float* out, unsigned* mnmx, int B, int T, int n_fft,
+int launch_stft_mag_fm(const void* pcm, int f32, const float* peak, float* out, unsigned* mnmx, int B, int T, int n_fft,
                        int hop, int W, int ldk, cudaStream_t st) {
   if (n_fft != NFFT || ldk < BINS) return BN_ERR_UNSUPPORTED;
-  const size_t smem = stft_smem_bytes(hop, true);
+  const size_t smem = stft_smem_bytes(hop, true, f32 != 0);
   if (smem > 227 * 1024) return BN_ERR_UNSUPPORTED;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(k_stft_mag<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    set_stft_attrs();
     attr_done = true;
   }
   const float4* tab = stft_tables();
   if (!tab) return BN_ERR_CUDA;
   if (W % FRAMES_PER_CTA) return BN_ERR_UNSUPPORTED;
   k_init_minmax<<<(B + 255) / 256, 256, 0, st>>>(mnmx, B);
-  k_stft_mag<true><<<stft_grid(B, W, smem), FE_THREADS, smem, st>>>(pcm, peak, out, mnmx, tab, T, hop, W, ldk, B);
+  if (f32) k_stft_mag<true, true><<<stft_grid(B, W, smem), FE_THREADS, smem, st>>>(pcm, peak, out, mnmx, tab, T, hop, W, ldk, B);
+  else k_stft_mag<true, false><<<stft_grid(B, W, smem), FE_THREADS, smem, st>>>(pcm, peak, out, mnmx, tab, T, hop, W, ldk, B);
   return 0;
 }
 

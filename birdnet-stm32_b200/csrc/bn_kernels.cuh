@@ -33,10 +33,11 @@ void launch_pool(const float* scores, const int* offs, float* out, int F, int C,
 // ---- frontend (bn_frontend.cu) -----------------------------------------------------------
 // |STFT| of B chunks -> out float32 [B, 257, W] (un-normalised) and per-chunk {min,max} bit patterns.
 // Launches 2 kernels.  Returns 0 or a bn_status.
-int launch_stft_mag(const int16_t* pcm, const float* peak, float* out, unsigned* mnmx, int B, int T, int n_fft,
+// pcm: int16 [B, T] (f32 = 0) or float32 waveform chunks [B, T] (f32 = 1).
+int launch_stft_mag(const void* pcm, int f32, const float* peak, float* out, unsigned* mnmx, int B, int T, int n_fft,
                     int hop, int W, cudaStream_t st);
 
-int launch_stft_mag_fm(const int16_t* pcm, const float* peak, float* out, unsigned* mnmx, int B, int T, int n_fft,
+int launch_stft_mag_fm(const void* pcm, int f32, const float* peak, float* out, unsigned* mnmx, int B, int T, int n_fft,
                        int hop, int W, int ldk, cudaStream_t st);
 
 }  // namespace bn

@@ -105,6 +105,14 @@ BN_API int bn_frontend_pcm16(bn_engine* e, const int16_t* pcm, const float* peak
 BN_API int bn_infer_pcm16(bn_engine* e, const int16_t* pcm, const float* peak, int B,
                           float* scores, void* stream);
 
+/* The same with float32 waveform chunks [B, chunk_len] -- what the reference's make_chunks_for_file holds after
+ * load_audio_window resampled / mixed / peak-normalised a file (audio/io.py:118-128, evaluation/metrics.py:39-61); produced
+ * on the device by bn_ingest_chunks (bn_ingest.h).  peak: optional extra divisor per chunk (NULL = samples used as they are). */
+BN_API int bn_infer_wave_f32(bn_engine* e, const float* wave, const float* peak, int B, float* scores, void* stream);
+BN_API int bn_frontend_wave_f32(bn_engine* e, const float* wave, const float* peak, int B, float* spec_out, void* stream);
+BN_API int bn_infer_pool_wave_f32(bn_engine* e, const float* wave, const float* peak, const int32_t* file_offsets, int F,
+                                  int pooling, float beta, float* file_scores, void* stream);
+
 /* Full hot path with per-file pooling on the device.  file_offsets: int32 [F+1], chunk index
  * ranges per file (file f owns chunks [off[f], off[f+1]) ; empty files give zeros);
  * file_scores: float32 [F, num_classes].  B = file_offsets[F]. */

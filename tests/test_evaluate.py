@@ -163,3 +163,72 @@ def test_gpu_evaluate_matches_oracle_path(tmp_path, blob, cfg, oracle_model):
         np.testing.assert_allclose(ys2, y_scores, rtol=0, atol=3e-6)
     finally:
         runner.close()
+
+
+@pytest.mark.gpu
+def test_gpu_evaluate_mixed_rates_and_formats(tmp_path, blob, cfg, oracle_model):
+    """Files the reference would resample / mix on the host (48 kHz stereo, 44.1 kHz float32, 32 kHz 24-bit) next to
+    native 22.05 kHz PCM16 files: device ingest + float32 waveform entry vs the oracle (real scipy resample_poly +
+    numpy + C frontend + int8 graph).  Same bars as the PCM16 path: scores within 1 LSB, top-1 identical."""
+    from test_ingest import write_wav
+
+    from birdnet_stm32.audio import io
+    from birdnet_stm32.evaluation.gpu_runner import GpuRunner
+    from birdnet_stm32.evaluation.metrics import evaluate
+    from oracle import bn_ingest_oracle as O
+    from oracle import bn_oracle
+
+    classes = cfg["class_names"]
+    rng = np.random.default_rng(77)
+    specs = [(48000, 2, "s16", 7.0), (22050, 1, "s16", 4.1), (44100, 1, "f32", 3.0), (32000, 3, "s24", 9.5), (22050, 2, "s16", 2.0),
+             (48000, 1, "s16", 61.5)]
+    files, raws = [], []
+    for i, (sr0, ch, kind, secs) in enumerate(specs):
+        n = int(sr0 * secs)
+        t = np.arange(n) / sr0
+        x = np.stack([0.35 * np.sin(2 * np.pi * (600 + 450 * i + 200 * c) * t) for c in range(ch)], axis=1) + 0.08 * rng.standard_normal((n, ch))
+        x = x.clip(-1, 1)
+        if kind == "s16":
+            raw = np.round(32767 * x).astype("<i2").reshape(-1)
+        elif kind == "f32":
+            raw = x.astype("<f4").reshape(-1)
+        else:
+            v = np.round(8388607 * x).astype(np.int32).reshape(-1)
+            raw = np.stack([v & 0xFF, (v >> 8) & 0xFF, (v >> 16) & 0xFF], axis=1).astype(np.uint8).reshape(-1)
+        d = tmp_path / classes[i]
+        d.mkdir()
+        path = str(d / "f.wav")
+        write_wav(path, raw, kind, ch, sr0)
+        files.append(path)
+        raws.append((raw, kind, ch, sr0))
+    runner = GpuRunner(blob, cfg)
+    try:
+        metrics, per_file, y_true, y_scores = evaluate(runner, files, classes, cfg, pooling="lme", device_batch_chunks=9)
+        assert y_scores.shape == (len(files), 100) and "skipped_files" not in metrics
+        assert [f["file"] for f in per_file] == files
+        ref = []
+        for raw, kind, ch, sr0 in raws:
+            per = (3 if kind == "s24" else 1) * ch
+            nfr = int(min(raw.size // per, 60 * sr0))
+            wave, _ = O.load_window(raw[: nfr * per], kind, ch, sr0, 22050)
+            chunks = O.split_chunks(wave, 22050, 3.0, 0.0)
+            spec = bn_oracle.frontend_hybrid_f32(chunks, 512, 66150 // 256, 256)
+            ref.append(bn_oracle.pool_scores(oracle_model.predict(spec), "lme", 10.0))
+        ref = np.asarray(ref, dtype=np.float32)
+        np.testing.assert_array_equal(y_scores.argmax(1), ref.argmax(1))
+        assert np.abs(y_scores - ref).max() <= 1 / 256 + 1e-5
+        # the reference-compatible float view of a non-native file comes from the device too
+        y = io.load_audio_window(files[0], sample_rate=22050, max_duration=60)
+        want, _ = O.load_window(raws[0][0], "s16", 2, 48000, 22050)
+        assert y.shape == want.shape and np.abs(y - want).max() <= 2e-6
+        # protocol path (make_chunks_for_file + predict + host pooling)
+        class ProtocolOnly:
+            predict = staticmethod(runner.predict)
+            frontend = staticmethod(runner.frontend)
+            frontend_wave = staticmethod(runner.frontend_wave)
+            device = 0
+
+        _, _, _, ys2 = evaluate(ProtocolOnly(), files, classes, cfg, pooling="lme", batch_size=4)
+        np.testing.assert_allclose(ys2, y_scores, rtol=0, atol=3e-6)
+    finally:
+        runner.close()

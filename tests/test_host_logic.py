@@ -121,7 +121,7 @@ def test_c_abi_library_loads_and_exports_every_declared_symbol():
     from birdnet_stm32 import _lib as L
 
     lib = L.load()
-    header = open(os.path.join(ROOT, "include", "bn_engine.h")).read() + open(os.path.join(ROOT, "include", "bn_features.h")).read()
+    header = "".join(open(os.path.join(ROOT, "include", h)).read() for h in ("bn_engine.h", "bn_features.h", "bn_ingest.h"))
     declared = set(re.findall(r"BN_API\s+[\w\s\*]+?\b(bn_\w+)\s*\(", header))
     assert declared == set(L.EXPORTS), declared ^ set(L.EXPORTS)
     for name in declared:
@@ -141,6 +141,10 @@ def test_c_abi_library_loads_and_exports_every_declared_symbol():
 
         with pytest.raises(L.EngineError, match="no CPU fallback"):
             GpuRunner(export_blob(TFLITE, {}))
+        from birdnet_stm32.audio.ingest import GpuIngest
+
+        with pytest.raises(L.EngineError, match="no CPU fallback"):
+            GpuIngest(0)
 
 
 def test_oracle_has_not_drifted(oracle_model, pcm_batch):
