@@ -127,14 +127,14 @@ k_decode_mix(const unsigned char* __restrict__ frames, float* __restrict__ mono,
 }
 
 __device__ __forceinline__ void block_absmax(float v, unsigned* peak_bits) {
-  __shared__ float red[IG_THREADS / 32];
+  __shared__ float red[32];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
   if (threadIdx.x == 0) {
     float m = red[0];
-    for (int i = 1; i < IG_THREADS / 32; i++) m = fmaxf(m, red[i]);
+    for (int i = 1; i < (int)(blockDim.x >> 5); i++) m = fmaxf(m, red[i]);
     atomicMax(peak_bits, __float_as_uint(m));        // |y| >= +0: bit patterns order like unsigned integers
   }
   __syncthreads();
@@ -159,6 +159,73 @@ k_resample(const float* __restrict__ x, float* __restrict__ y, const float* __re
       }
       y[i] = acc;
       amax = fmaxf(amax, fabsf(acc));
+    }
+  }
+  block_absmax(amax, peak_bits);
+}
+
+// Phase-per-thread resampler.  The filter phase of output i only depends on i mod up, so a block whose output stride S is
+// a multiple of up gives every thread ONE phase for its whole life: its per_phase taps sit in shared memory as a column
+// hs[t][tid] (conflict-free: consecutive threads, consecutive words) and never have to be gathered again, and the input
+// index advances by exactly (S / up) * down per step.  Products and sums are the same float32 operations in the same
+// order as k_resample (oldest sample first, no FMA), so both kernels give identical bits.
+//   block b owns outputs [b * S * J, (b + 1) * S * J); thread tid handles b * S * J + j * S + tid, j < J.
+__global__ void __launch_bounds__(1024)
+k_resample_phase(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ hcol, unsigned* __restrict__ peak_bits,
+                 long n_in, long n_out, int up, int down, int per_phase, int n_pre_remove, int S, int J) {
+  extern __shared__ float hs[];
+  const int tid = threadIdx.x;
+  const bool active = tid < S;
+  // hcol is the tap table already in column order [t][tid] (built on the host for this S): straight coalesced copy
+  // (16-byte cp.async pieces: the host pads the table to a multiple of 4 floats and aligns it)
+  for (int i = tid; i < (per_phase * S + 3) >> 2; i += blockDim.x)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(hs + 4 * i)), "l"(hcol + 4 * i) : "memory");
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  float amax = 0.0f;
+  if (active) {
+    const long xi0 = ((long)(tid + n_pre_remove) * down) / up;
+    const long xstep = (long)(S / up) * down;
+    const long base = (long)blockIdx.x * S * J;
+    long xi = xi0 + (base / up) * down;
+    const float* hc = hs + tid;
+    // four outputs of this thread at a time: they share every tap (same phase), so a tap costs one shared-memory load,
+    // four cached global loads and four independent multiply / add chains.  Groups that touch either end of the signal
+    // (or the end of the output) take the bounds-checked loop; only the first and last blocks ever do.
+    for (int j = 0; j < J; j += 4, xi += 4 * xstep) {
+      const long i = base + (long)j * S + tid;
+      if (i >= n_out) break;
+      if (j + 4 <= J && i + 3L * S < n_out && xi - (per_phase - 1) >= 0 && xi + 3 * xstep < n_in) {
+        const float* q0 = x + xi - (per_phase - 1);        // oldest sample of the first output
+        const float* q1 = q0 + xstep;
+        const float* q2 = q1 + xstep;
+        const float* q3 = q2 + xstep;
+        const float* hq = hc + (per_phase - 1) * S;
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+#pragma unroll 4
+        for (int tt = 0; tt < per_phase; tt++) {           // oldest sample first (scipy upfirdn's loop order)
+          const float h = hq[-tt * S];
+          a0 = __fadd_rn(a0, __fmul_rn(__ldg(q0 + tt), h));
+          a1 = __fadd_rn(a1, __fmul_rn(__ldg(q1 + tt), h));
+          a2 = __fadd_rn(a2, __fmul_rn(__ldg(q2 + tt), h));
+          a3 = __fadd_rn(a3, __fmul_rn(__ldg(q3 + tt), h));
+        }
+        y[i] = a0; y[i + S] = a1; y[i + 2L * S] = a2; y[i + 3L * S] = a3;
+        amax = fmaxf(fmaxf(amax, fmaxf(fabsf(a0), fabsf(a1))), fmaxf(fabsf(a2), fabsf(a3)));
+      } else {
+        for (int jj = 0; jj < 4 && j + jj < J; jj++) {
+          const long ii = i + (long)jj * S;
+          if (ii >= n_out) break;
+          const long xj = xi + jj * xstep;
+          float acc = 0.0f;
+          for (int t = per_phase - 1; t >= 0; t--) {
+            const long idx = xj - t;
+            if (idx >= 0 && idx < n_in) acc = __fadd_rn(acc, __fmul_rn(__ldg(x + idx), hc[t * S]));
+          }
+          y[ii] = acc;
+          amax = fmaxf(amax, fabsf(acc));
+        }
+      }
     }
   }
   block_absmax(amax, peak_bits);
@@ -215,6 +282,7 @@ struct bn_ingest {
   float* d_out = nullptr; size_t out_cap = 0;
   unsigned* d_peak = nullptr;
   std::map<std::pair<int, int>, std::pair<PolyFilter, float*>> filters;   // (up, down) -> host taps, device phase-major taps
+                                                                          // followed by the column table of k_resample_phase
   int64_t launches = 0;
 };
 
@@ -324,6 +392,12 @@ extern "C" int bn_ingest_filter(int up, int down, float* h_out, int cap, int* n_
   return BN_OK;
 }
 
+// output stride of a k_resample_phase block: a whole number of phase periods, about 256 threads; 0 = does not fit a block
+static int phase_stride(int up) {
+  const int S = up <= 256 ? up * ((256 + up - 1) / up) : up;
+  return S <= 1024 ? S : 0;
+}
+
 static int grid_for(const bn_ingest* g, long n) {
   long b = (n + IG_THREADS - 1) / IG_THREADS;
   const long cap = (long)g->sms * 8;
@@ -395,8 +469,15 @@ static int ingest_core(bn_ingest* g, const void* frames, int fmt, int64_t n_fram
       }
     }
     if (it == g->filters.end()) {
-      std::vector<float> hp((size_t)up * probe.per_phase, 0.0f);
+      const size_t n_hp = ((size_t)up * probe.per_phase + 3) & ~(size_t)3;   // keeps the column table 16-byte aligned
+      const int S = phase_stride(up);
+      std::vector<float> hp(n_hp + (S ? (size_t)S * probe.per_phase + 4 : 0), 0.0f);
       for (int k = 0; k < probe.n_taps; k++) hp[(size_t)(k % up) * probe.per_phase + k / up] = probe.h[k];
+      for (int tid = 0; tid < S; tid++) {                 // column of thread tid = taps of its phase, [t][tid]
+        const long p0 = (long)(tid + probe.n_pre_remove) * down;
+        const int k0 = (int)(p0 % up);
+        for (int t = 0; t < probe.per_phase; t++) hp[n_hp + (size_t)t * S + tid] = hp[(size_t)k0 * probe.per_phase + t];
+      }
       float* d_hp = nullptr;
       IG_CU(cudaMalloc((void**)&d_hp, hp.size() * sizeof(float)));
       IG_CU(cudaMemcpyAsync(d_hp, hp.data(), hp.size() * sizeof(float), cudaMemcpyHostToDevice, st));
@@ -404,8 +485,26 @@ static int ingest_core(bn_ingest* g, const void* frames, int fmt, int64_t n_fram
       it = g->filters.emplace(key, std::make_pair(probe, d_hp)).first;
     }
     const PolyFilter& F = it->second.first;
-    k_resample<<<grid_for(g, n_out), IG_THREADS, 0, st>>>(d_mono, d_y, it->second.second, g->d_peak, n_frames, n_out, up, down,
-                                                         F.per_phase, F.n_pre_remove);
+    // phase-per-thread kernel when a whole number of phase periods fits a block and the tap columns fit shared memory
+    const int S = phase_stride(up);
+    const size_t hs_bytes = ((size_t)F.per_phase * S + 4) * sizeof(float);
+    static const bool force_generic = getenv("BN_INGEST_GENERIC") != nullptr;
+    if (S > 0 && hs_bytes <= 200 * 1024 && !force_generic) {
+      static bool attr = false;
+      if (!attr) { cudaFuncSetAttribute(k_resample_phase, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+      const long steps = (n_out + S - 1) / S;                       // block steps in total
+      const int per_sm = (int)(200 * 1024 / (hs_bytes + 1024)) < (2048 / ((S + 31) & ~31)) ? (int)(200 * 1024 / (hs_bytes + 1024)) : (2048 / ((S + 31) & ~31));
+      long blocks = (long)g->sms * (per_sm < 1 ? 1 : per_sm);
+      if (blocks > steps) blocks = steps;
+      int J = (int)((steps + blocks - 1) / blocks);
+      J = (J + 3) & ~3;                                  // whole groups of four outputs per thread
+      blocks = (steps + J - 1) / J;
+      k_resample_phase<<<(int)blocks, (S + 31) & ~31, hs_bytes, st>>>(d_mono, d_y, it->second.second + (((size_t)up * F.per_phase + 3) & ~(size_t)3), g->d_peak, n_frames, n_out, up, down,
+                                                                   F.per_phase, F.n_pre_remove, S, J);
+    } else {
+      k_resample<<<grid_for(g, n_out), IG_THREADS, 0, st>>>(d_mono, d_y, it->second.second, g->d_peak, n_frames, n_out, up, down,
+                                                           F.per_phase, F.n_pre_remove);
+    }
     g->launches++;
   }
   *d_res = d_y;

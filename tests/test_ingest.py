@@ -170,7 +170,8 @@ def test_gpu_ingest_matches_reference_golden(ingest):
 def test_gpu_ingest_long_windows_vs_oracle(ingest):
     rng = np.random.default_rng(11)
     for sr_in, sr_out, ch, secs in ((48000, 22050, 2, 61.0), (44100, 24000, 1, 20.0), (96000, 22050, 1, 5.0), (8000, 24000, 2, 7.3),
-                                    (22050, 24000, 1, 3.1)):
+                                    (22050, 24000, 1, 3.1), (22051, 22050, 1, 0.4), (44100, 22050, 2, 12.0)):
+        # (22051 -> 22050 is coprime: up = 22050 phases do not fit a block, so the generic gather kernel runs)
         n = int(min(secs, 60) * sr_in)
         x = (rng.standard_normal((n, ch)) * 0.2).clip(-1, 1)
         x[:, 0] += 0.5 * np.sin(2 * np.pi * 1234.5 * np.arange(n) / sr_in)
