@@ -234,6 +234,10 @@ def run_b200(args):
     n_chunks = int(offs_np[-1])
 
     runner = GpuRunner(blob, cfg, device=local, wave=args.wave)
+    if args.host_wave:
+        from birdnet_stm32 import _lib as _L
+
+        runner.set_option(_L.BN_OPT_HOST_WAVE, args.host_wave)
     pcm = synth_device_pcm(torch, n_chunks, T, cfg["sample_rate"], seed=2024 + rank, device=dev)
     peak = file_peaks_device(torch, pcm, offs_np)
     offs = torch.as_tensor(offs_np, device=dev)
@@ -381,6 +385,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--files", type=int, default=2048, help="files per GPU per step")
     ap.add_argument("--wave", type=int, default=0, help="chunks per engine wave (0 = engine default)")
+    ap.add_argument("--host-wave", type=int, default=0, help="chunks per wave for host-memory inputs, e2e leg (0 = engine default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -31,6 +31,7 @@ BN_SAMPLE_FORMAT = {"s16": 0, "s24": 1, "s32": 2, "f32": 3, "u8": 4}
 BN_POOL = {"avg": 0, "mean": 0, "average": 0, "max": 1, "lme": 2, "log_mean_exp": 2, "log_mean_exponential": 2}
 BN_OPT_ROUNDING, BN_OPT_MEAN_VARIANT, BN_OPT_FORCE_GENERIC, BN_OPT_WAVE, BN_OPT_PROFILE, BN_OPT_TENSOR_CORE = 1, 2, 3, 4, 5, 6
 BN_OPT_FUSION = 7
+BN_OPT_HOST_WAVE = 8
 
 
 class BnInfo(C.Structure):

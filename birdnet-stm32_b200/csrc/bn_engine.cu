@@ -47,7 +47,10 @@ struct bn_engine {
   const bn_blob_op* ops = nullptr;
   // workspace
   int wave = 0;                       // chunks the workspace is sized for
-  int wave_opt = 2048;                 // requested wave size
+  int wave_opt = 2368;                 // requested wave size (8 x 296 resident CTAs: whole tile rounds in every kernel)
+  int host_wave = 592;                 // wave size when the input lives in host memory: the upload of wave i+1 hides under the
+                                       // compute of wave i, so the exposed part of a call is one wave's upload plus one wave's
+                                       // compute -- small waves keep a PCIe-bound call close to the link rate (BN_OPT_HOST_WAVE)
   std::vector<void*> buf;             // per tensor slot: device buffer for one wave (const -> into d_blob)
   std::vector<void*> last_ptr;        // pointers used by the last wave (taps)
   size_t workspace_bytes = 0;
@@ -417,7 +420,8 @@ static int infer_impl(bn_engine* e, const void* pcm_v, int sbytes, const float* 
   }
   if (B == 0 && !offs) return BN_OK;
 
-  const int wave = B > 0 ? pick_wave(e, B) : 1;
+  int wave = B > 0 ? pick_wave(e, B) : 1;
+  if (!dev_in && wave > e->host_wave) wave = e->host_wave;
   rc = ensure_workspace(e, wave);
   if (rc) return rc;
   const bool pooled = offs != nullptr;
@@ -675,6 +679,9 @@ extern "C" int bn_set_option(bn_engine* e, int key, int value) {
       if (value < 1 || value > 65535) return set_err(BN_ERR_ARG, "wave must be in [1, 65535]");
       if (value != e->wave_opt) { cudaDeviceSynchronize(); free_workspace(e); }
       e->wave_opt = value; break;
+    case BN_OPT_HOST_WAVE:
+      if (value < 1) return set_err(BN_ERR_ARG, "host wave must be >= 1");
+      e->host_wave = value; break;
     case BN_OPT_TENSOR_CORE:
       e->fast.use_tc = value ? 1 : 0; break;
     case BN_OPT_FUSION:

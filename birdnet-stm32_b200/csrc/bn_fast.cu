@@ -61,7 +61,17 @@ Profiler::~Profiler() { for (auto e : pool) cudaEventDestroy(e); for (auto& p : 
 // =================================================================================================
 // Plan data
 // =================================================================================================
-constexpr int FE_SUBWAVE = 256;  // chunks per frontend sub-wave (K1 -> K2 through an L2-resident scratch buffer)
+// Chunks per frontend launch pair (K1 writes the float32 magnitudes, K2 reads them back).  Measured on B200 (round 1,
+// scripts/g18.sh / g19.sh): keeping this scratch inside the 126 MB L2 (256 chunks = 69 MB) is NOT what matters -- HBM has
+// bandwidth to spare at this arithmetic intensity -- while every extra launch pair costs a ramp-up (110 registers of
+// window / twiddle tables per thread) and a ragged tail: 256 -> 4.92 + 2.67 ms per 21.7 k chunks, 444 -> 4.51 + 2.48,
+// 888 -> 4.27 + 2.18, whole wave (2368) -> 4.09 + 1.97.  So the default is the whole wave, in multiples of 2 x 148 CTAs.
+static int fe_subwave() {
+  static int v = 0;
+  if (!v) { const char* e = getenv("BN_FE_SUBWAVE"); v = e ? atoi(e) : 2368; if (v < 1) v = 2368; }
+  return v;
+}
+#define FE_SUBWAVE (fe_subwave())
 constexpr int HEAD_N = 64;        // mel channels handled by the head kernel
 constexpr int HEAD_M = 128;       // frames per CTA
 constexpr int GEMM_LDA = 132;     // words per k-row of the transposed A tile (128 + 4 pad, keeps 16-byte alignment)
@@ -1481,9 +1491,8 @@ static int run_body(FastPlan& fp, int Bw, float* d_scores, int rounding, int mea
   return cudaGetLastError() == cudaSuccess ? 0 : BN_ERR_CUDA;
 }
 
-// The frontend runs in sub-waves: K1 writes the float32 magnitudes of FE_SUBWAVE chunks (69 MB) into the same scratch
-// buffer each time and K2 consumes them straight away, so the 270 KB/chunk intermediate stays in the 126 MB L2
-// instead of making a round trip through HBM.
+// K1 writes the float32 magnitudes of up to FE_SUBWAVE chunks into a scratch buffer and K2 consumes them straight away
+// (see fe_subwave() for why the sub-wave is the whole wave by default).
 
 int fast_run_pcm(FastPlan& fp, const void* d_pcm, int f32, const float* d_peak, int Bw, float* d_scores, int rounding,
                  int mean_variant, cudaStream_t st, int64_t* launches, Profiler* prof) {

@@ -61,6 +61,8 @@ enum {
   BN_OPT_WAVE = 4,          /* chunks processed per internal wave (workspace is sized for it)           */
   BN_OPT_PROFILE = 5,       /* 1 = time every kernel with CUDA events, 0 = off, 2 = on + reset counters  */
   BN_OPT_TENSOR_CORE = 6,   /* 1 (default) = pointwise convs on tcgen05.mma kind::i8, 0 = dp4a CUDA-core GEMM */
+  BN_OPT_HOST_WAVE = 8,     /* wave size for calls whose input is in HOST memory (default 592): uploads are double-buffered under
+                               compute, so a smaller wave shortens the un-overlapped first upload / last compute of a call */
   BN_OPT_FUSION = 7         /* bit 0: depthwise + pointwise (+ADD) fused per DS block, bit 1: tensor-core head (quantise +
                                mel mixer + PWL LUT), bit 2: depthwise conv of stride-1 blocks on the tensor core too
                                (shifted no-swizzle descriptors; bit-exact, measured slower, off); default 3 */
