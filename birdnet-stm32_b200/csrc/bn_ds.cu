@@ -36,8 +36,10 @@ __device__ __forceinline__ int rq64(int acc, int c_lo, int c_hi, int mult, int r
   return (v + rz + (v >> 31)) >> n;
 }
 __device__ __forceinline__ int clamp2(int v, int lo, int hi) { return max(lo, min(v, hi)); }
-template <int S, int TR, int ADD, int DWT>
-__global__ void __launch_bounds__(DS_THREADS, 2)
+// MB = resident CTAs per SM the register allocation is sized for: 2 (128 registers) or 3 (80 registers; only the
+// transposed depthwise fits that without meaningful spilling).
+template <int S, int TR, int ADD, int DWT, int MB>
+__global__ void __launch_bounds__(DS_THREADS, MB)
 k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles, DsParams P) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -407,11 +409,11 @@ size_t ds_smem_bytes(const DsParams& P, int S, int TR) {
   return b + 1024;                                   // alignment slack
 }
 
-template <int S, int TR, int ADD, int DWT>
+template <int S, int TR, int ADD, int DWT, int MB>
 static int launch_one(const int8_t* in, int8_t* out, int Bw, int ntiles, int grid, size_t smem, const DsParams& P, cudaStream_t st) {
   static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(k_ds<S, TR, ADD, DWT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; }
-  k_ds<S, TR, ADD, DWT><<<grid, DS_THREADS, smem, st>>>(in, out, Bw, ntiles, P);
+  if (!attr) { cudaFuncSetAttribute(k_ds<S, TR, ADD, DWT, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; }
+  k_ds<S, TR, ADD, DWT, MB><<<grid, DS_THREADS, smem, st>>>(in, out, Bw, ntiles, P);
   return 0;
 }
 
@@ -422,8 +424,9 @@ int launch_ds(const int8_t* in, int8_t* out, int Bw, const DsParams& P, const Ds
   if (grid < 1) return 0;
 #define DS_CASE(s, tr, add)                                                                                         \
   if (L.S == s && L.TR == tr && L.add_mode == add)                                                                  \
-    return L.dwt ? launch_one<s, tr, add, 1>(in, out, Bw, ntiles, grid, L.smem, P, st)                              \
-                 : launch_one<s, tr, add, 0>(in, out, Bw, ntiles, grid, L.smem, P, st)
+    return !L.dwt ? launch_one<s, tr, add, 0, 2>(in, out, Bw, ntiles, grid, L.smem, P, st)                          \
+         : L.ctas_per_sm >= 3 ? launch_one<s, tr, add, 1, 3>(in, out, Bw, ntiles, grid, L.smem, P, st)              \
+                              : launch_one<s, tr, add, 1, 2>(in, out, Bw, ntiles, grid, L.smem, P, st)
   DS_CASE(1, 4, 0); DS_CASE(1, 4, 1); DS_CASE(1, 4, 2);
   DS_CASE(1, 8, 0); DS_CASE(1, 8, 1); DS_CASE(1, 8, 2);
   DS_CASE(2, 4, 0); DS_CASE(2, 8, 0);

@@ -463,7 +463,12 @@ static bool prep_ds(FastPlan& fp, FastImpl* im, Block& bl) {
   // pick the pipeline depth: score = resident CTAs per SM x (pipelined ? 1.5 : 1); deeper prefetch wins ties
   {
     const int limit = 225 * 1024;
-    const int ds_cta_cap = getenv("BN_DS_CTAS") ? atoi(getenv("BN_DS_CTAS")) : 2;
+    // registers: 128 per thread -> 2 CTAs of 256 threads; the transposed-depthwise build also exists at 80 registers -> 3
+    // (measured: 3 CTAs / SM gives 1.119 M vs 1.101 M chunks/s with 2; the early layers gain 4 - 10 %, the late ones are bound
+    // to 2 by shared memory / TMEM columns anyway)
+    int ds_cta_cap = getenv("BN_DS_CTAS") ? atoi(getenv("BN_DS_CTAS")) : 3;
+    if (ds_cta_cap > 2 && !L.dwt) ds_cta_cap = 2;
+    if (ds_cta_cap > 3) ds_cta_cap = 3;
     double best = -1.0;
     for (int nst = 1; nst <= 3; nst++) {
       DsParams Q = D;
@@ -478,7 +483,10 @@ static bool prep_ds(FastPlan& fp, FastImpl* im, Block& bl) {
       if (per < 1) continue;
       // measured: with 2-3 co-resident CTAs per SM the software pipeline adds nothing (the other CTAs already fill the
       // stalls), so the unpipelined loop is preferred unless it would leave the SM with a single CTA
-      const double score = per >= 2 ? per - 0.01 * nst : (nst > 1 ? 1.5 : 1.0) + 0.01 * nst;
+      // exception (measured, round 1): the first block (stride 2, 16 channels, 9 input rows of 2 KB per tile) is the one layer
+      // whose tile loads are long enough to show -- prefetch distance 2 takes it from 2.16 to 1.95 ms per 21.7 k chunks
+      double score = per >= 2 ? per - 0.01 * nst : (nst > 1 ? 1.5 : 1.0) + 0.01 * nst;
+      if (per >= 2 && S == 2 && C <= 16 && nst == 3) score = per + 0.5;
       if (score > best) { best = score; D.nst = nst; D.tmem_cols = c2; L.smem = sm; L.ctas_per_sm = per; }
     }
     if (best < 0) { if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: reject at check 16 (line %d)\n", __LINE__); return false; }
