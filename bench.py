@@ -337,8 +337,8 @@ def run_b200(args):
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "r1", "ncu_traffic.json")))
         ent = tr.get(dom[0])
-        if ent and abs(ent["chunks_per_launch"] - chunks_per_launch) < 1:
-            traffic = ent["dram_bytes_per_launch"]
+        if ent:   # per-chunk DRAM bytes of the captured launch x the chunks an average launch of this run processed
+            traffic = ent["dram_bytes_per_launch"] / ent["chunks_per_launch"] * chunks_per_launch
     except Exception:
         pass
     roofline = {

@@ -24,6 +24,8 @@ EXPORTS = (
     # include/bn_ingest.h
     "bn_ingest_create", "bn_ingest_destroy", "bn_ingest_out_len", "bn_ingest_num_chunks", "bn_ingest_filter",
     "bn_ingest_window", "bn_ingest_chunks", "bn_ingest_launch_count",
+    # include/bn_metrics.h
+    "bn_metrics_compute",
 )
 
 BN_SAMPLE_FORMAT = {"s16": 0, "s24": 1, "s32": 2, "f32": 3, "u8": 4}
@@ -50,6 +52,16 @@ class BnFeatParams(C.Structure):
         ("sample_rate", C.c_int32), ("chunk_len", C.c_int32), ("n_fft", C.c_int32), ("spec_width", C.c_int32),
         ("n_mels", C.c_int32), ("mode", C.c_int32), ("mag_scale", C.c_int32), ("n_mfcc", C.c_int32),
         ("pcen_b", C.c_float), ("reserved", C.c_int32 * 7),
+    ]
+
+
+class BnMetricsResult(C.Structure):
+    """`bn_metrics_result` of include/bn_metrics.h"""
+
+    _fields_ = [
+        ("roc_auc_micro", C.c_double), ("map_micro", C.c_double), ("cmap", C.c_double), ("precision", C.c_double),
+        ("recall", C.c_double), ("f1", C.c_double), ("n_positive", C.c_int64), ("n_cells", C.c_int64),
+        ("classes_without_positives", C.c_int32), ("n_launches", C.c_int32), ("reserved", C.c_int32 * 4),
     ]
 
 
@@ -120,6 +132,7 @@ def load():
     L.bn_ingest_chunks.argtypes = [vp, vp, i32, i64, i32, i32, i32, i32, i32, vp, i32, C.POINTER(i32), vp, vp]
     L.bn_ingest_launch_count.argtypes = [vp]
     L.bn_ingest_launch_count.restype = i64
+    L.bn_metrics_compute.argtypes = [vp, vp, i32, i32, i32, C.POINTER(BnMetricsResult), vp]
     _lib = L
     return L
 

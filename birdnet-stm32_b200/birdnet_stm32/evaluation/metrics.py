@@ -120,8 +120,13 @@ def _metrics_from_scores(y_true_arr: np.ndarray, y_scores_arr: np.ndarray) -> di
 def evaluate(model_runner, files: list[str], classes: list[str], cfg: dict, pooling: str = "average",
              batch_size: int = 64, overlap: float = 0.0, mep_beta: float = 10.0, measure_latency: bool = False,
              profile_memory: bool = False, device_batch_chunks: int = 4096,
-             frontend_runner=None) -> tuple[dict, list[dict], np.ndarray, np.ndarray]:
-    """Run inference per chunk, pool to file level and compute metrics (see module docstring)."""
+             frontend_runner=None, metrics_backend: str = "sklearn") -> tuple[dict, list[dict], np.ndarray, np.ndarray]:
+    """Run inference per chunk, pool to file level and compute metrics (see module docstring).
+
+    metrics_backend: "sklearn" (the reference's own calls, host) or "device" (`evaluation/device_metrics.py`: the same
+    definitions evaluated by `bn_metrics_compute` on the GPU -- for evaluations with millions of (file, class) cells)."""
+    if metrics_backend not in ("sklearn", "device"):
+        raise ValueError(f"Unsupported metrics backend: {metrics_backend}")
     frontend = normalize_frontend_name(cfg["audio_frontend"])
     mag_scale = cfg.get("mag_scale", "none")
     n_fft = int(cfg["fft_length"])
@@ -265,7 +270,12 @@ def evaluate(model_runner, files: list[str], classes: list[str], cfg: dict, pool
 
     y_true_arr = np.asarray(y_true, dtype=np.float32)
     y_scores_arr = np.asarray(y_scores, dtype=np.float32)
-    metrics = _metrics_from_scores(y_true_arr, y_scores_arr)
+    if metrics_backend == "device":
+        from birdnet_stm32.evaluation.device_metrics import metrics_from_scores_device
+
+        metrics = metrics_from_scores_device(y_true_arr, y_scores_arr, int(getattr(model_runner, "device", 0)))
+    else:
+        metrics = _metrics_from_scores(y_true_arr, y_scores_arr)
 
     if measure_latency and latencies_ms:
         lat = np.array(latencies_ms)

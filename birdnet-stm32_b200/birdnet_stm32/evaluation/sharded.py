@@ -82,4 +82,9 @@ def evaluate_sharded(model_runner, files: list[str], classes: list[str], cfg: di
         raise RuntimeError("No valid test samples found for the provided class set.")
     y_true_g = np.zeros((labels_g.shape[0], len(classes)), dtype=np.float32)
     y_true_g[np.arange(labels_g.shape[0]), labels_g] = 1.0
+    if kw.get("metrics_backend", "sklearn") == "device":
+        # the gathered [F, C] matrix goes back to this rank's GPU once: sort / count / accumulate there (bn_metrics_compute)
+        from birdnet_stm32.evaluation.device_metrics import metrics_from_scores_device
+
+        return metrics_from_scores_device(y_true_g, scores_g, int(getattr(model_runner, "device", 0))), per_file, y_true_g, scores_g
     return _metrics_from_scores(y_true_g, scores_g), per_file, y_true_g, scores_g

@@ -121,7 +121,7 @@ def test_c_abi_library_loads_and_exports_every_declared_symbol():
     from birdnet_stm32 import _lib as L
 
     lib = L.load()
-    header = "".join(open(os.path.join(ROOT, "include", h)).read() for h in ("bn_engine.h", "bn_features.h", "bn_ingest.h"))
+    header = "".join(open(os.path.join(ROOT, "include", h)).read() for h in ("bn_engine.h", "bn_features.h", "bn_ingest.h", "bn_metrics.h"))
     declared = set(re.findall(r"BN_API\s+[\w\s\*]+?\b(bn_\w+)\s*\(", header))
     assert declared == set(L.EXPORTS), declared ^ set(L.EXPORTS)
     for name in declared:
