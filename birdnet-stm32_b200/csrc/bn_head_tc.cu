@@ -41,6 +41,29 @@ __device__ __forceinline__ int quant_code(float f, float mn, float den, float qm
   return q;
 }
 
+// Two elements at a time with packed FP32 pairs (FADD2 / FMUL2, same IEEE results as the scalar form): 5 packed
+// instructions + 2 x (compare, integer subtract) instead of 2 x 7.
+__device__ __forceinline__ void quant_code2(float f0, float f1, float mn, float den, float qmul, float scale, int zp_bits, int zp, int& q0, int& q1) {
+  unsigned long long f, m, k, c, d, t, tm, r, df;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(f) : "f"(f0), "f"(f1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(m) : "f"(mn));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(k) : "f"(qmul));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(c) : "f"(12582912.0f));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f), "l"(m));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(d), "l"(k));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(tm) : "l"(t), "l"(c));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(tm), "l"(c));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(df) : "l"(t), "l"(r));
+  float d0, d1, tm0, tm1, df0, df1;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(tm0), "=f"(tm1) : "l"(tm));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(df0), "=f"(df1) : "l"(df));
+  q0 = __float_as_int(tm0) - zp_bits;                   // RNE(t) + zp
+  q1 = __float_as_int(tm1) - zp_bits;
+  if (fabsf(df0) > 0.49975f) q0 = (int)roundf(__fdiv_rn(__fdiv_rn(d0, den), scale)) + zp;
+  if (fabsf(df1) > 0.49975f) q1 = (int)roundf(__fdiv_rn(__fdiv_rn(d1, den), scale)) + zp;
+}
+
 __global__ void __launch_bounds__(HT_THREADS, 2)
 k_head_tc(const float* __restrict__ mags, const unsigned* __restrict__ mnmx, int8_t* __restrict__ out, int ntiles, HeadTcParams P) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -97,10 +120,9 @@ k_head_tc(const float* __restrict__ mags, const unsigned* __restrict__ mnmx, int
       for (int u = 0; u < 8; u++) {
         const int i = base + u * HT_THREADS + tid;
         const int row = i >> 6, k4 = i & 63;
-        const int q0 = quant_code(vv[u].x, mn, den, qmul, P.q_scale, zp_bits, P.q_zp);
-        const int q1 = quant_code(vv[u].y, mn, den, qmul, P.q_scale, zp_bits, P.q_zp);
-        const int q2 = quant_code(vv[u].z, mn, den, qmul, P.q_scale, zp_bits, P.q_zp);
-        const int q3 = quant_code(vv[u].w, mn, den, qmul, P.q_scale, zp_bits, P.q_zp);
+        int q0, q1, q2, q3;
+        quant_code2(vv[u].x, vv[u].y, mn, den, qmul, P.q_scale, zp_bits, P.q_zp, q0, q1);
+        quant_code2(vv[u].z, vv[u].w, mn, den, qmul, P.q_scale, zp_bits, P.q_zp, q2, q3);
         // k = 4 k4: k-block k4 >> 5, 16-byte chunk (k4 >> 2) & 7 (XOR row & 7), word k4 & 3
         const int off = (k4 >> 5) * (HT_M * 128) + row * 128 + (((((k4 >> 2) & 7) ^ (row & 7)) << 4)) + ((k4 & 3) << 2);
         *reinterpret_cast<unsigned*>(sA + off) = pack4_sat(q0, q1, q2, q3);
