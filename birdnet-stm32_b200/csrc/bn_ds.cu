@@ -430,6 +430,7 @@ int launch_ds(const int8_t* in, int8_t* out, int Bw, const DsParams& P, const Ds
   DS_CASE(1, 4, 0); DS_CASE(1, 4, 1); DS_CASE(1, 4, 2);
   DS_CASE(1, 8, 0); DS_CASE(1, 8, 1); DS_CASE(1, 8, 2);
   DS_CASE(2, 4, 0); DS_CASE(2, 8, 0);
+  DS_CASE(1, 16, 0); DS_CASE(1, 16, 1); DS_CASE(1, 16, 2); DS_CASE(2, 16, 0);
 #undef DS_CASE
   return BN_ERR_UNSUPPORTED;
 }

@@ -394,10 +394,29 @@ static bool prep_ds(FastPlan& fp, FastImpl* im, Block& bl) {
   if (S == 2 && (D.oh * 2 != D.ih || D.ow * 2 != D.iw)) { if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: reject at check 4 (line %d)\n", __LINE__); return false; }
   const int npix = D.oh * D.ow;
   int TR, NB;
-  if (npix >= 256) { TR = 256 / D.ow; NB = 1; }
-  else if (npix >= 128) { TR = 128 / D.ow; NB = 1; }
+  // Tile = TR output rows of one chunk (or NB whole chunks when a chunk has fewer than 128 pixels).  Bigger tiles amortise
+  // the per-tile latency chain (tile load -> depthwise -> MMA round trip -> epilogue, a barrier between phases) and the
+  // depthwise halo rows: measured 256 -> 512 pixels: ds_00 1.86 -> 1.54 ms, ds_01 3.06 -> 2.68 ms per 21.7 k chunks.
+  const int tile_px = getenv("BN_DS_TILE_PX") ? atoi(getenv("BN_DS_TILE_PX")) : 1024;
+  if (npix >= 128) {
+    TR = 0; NB = 1;
+    for (int tr : {16, 8, 4}) {
+      const int px = tr * D.ow;
+      if (tr > D.oh || D.oh % tr || px % 128 || px > tile_px || (px / 128) * N > 512) continue;
+      if (S == 2 && tr > 4) {
+        // stride-2 blocks stage (2 TR + 1) x 2 ow input pixels per tile: measured, they lose more from dropping to two
+        // resident CTAs than they gain from a bigger tile (ds_02: 0.78 ms at 256 px / 3 CTAs, 0.82 at 512 px / 2 CTAs)
+        DsParams Q = D;
+        Q.NB = 1; Q.MT = px / 128; Q.KP = bl.tc.KP; Q.nst = 1;
+        if (3 * (ds_smem_bytes(Q, S, tr) + 1024) > 225 * 1024) continue;
+      }
+      TR = tr;
+      break;
+    }
+    if (!TR) { if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: reject at check 5a (line %d)\n", __LINE__); return false; }
+  }
   else { if (128 % npix) { if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: reject at check 5 (line %d)\n", __LINE__); return false; } NB = 128 / npix; TR = D.oh; }
-  if (!(TR == 4 || TR == 8) || TR > D.oh || D.oh % TR) { if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: reject at check 6 (line %d)\n", __LINE__); return false; }
+  if (!(TR == 4 || TR == 8 || TR == 16) || TR > D.oh || D.oh % TR) { if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: reject at check 6 (line %d)\n", __LINE__); return false; }
   D.NB = NB; D.MT = TR * D.ow * NB / 128;
   if (D.MT < 1 || TR * D.ow * NB != D.MT * 128) { if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: reject at check 7 (line %d)\n", __LINE__); return false; }
   D.ow_log = ilog2_exact(D.ow); D.trow_log = ilog2_exact(TR * D.ow); D.cg_log = ilog2_exact(C / 4);
