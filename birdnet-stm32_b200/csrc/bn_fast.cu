@@ -1404,6 +1404,71 @@ k_tail(const int8_t* __restrict__ x, float* __restrict__ scores, TailParams Q, i
   }
 }
 
+// K6g: the same tail for groups of TG chunks per step of a persistent CTA.  The FC weights are transposed once into
+// shared memory ([K/4][N] words: threads with consecutive n read consecutive words) and reused for every group; a thread
+// owns one (chunk, class) dot product, so there are no warp reductions and each weight word is read once per group
+// instead of once per chunk.  Integer results are identical to k_tail (same sums, same requantisation).
+constexpr int TG = 8;
+__global__ void __launch_bounds__(256)
+k_tail_g(const int8_t* __restrict__ x, float* __restrict__ scores, TailParams Q, int variant, int R, int Bw) {
+  extern __shared__ __align__(16) unsigned char tsm[];
+  const int KW = Q.K >> 2;
+  int* wT = reinterpret_cast<int*>(tsm);                       // [KW][N]
+  int* mq = wT + KW * Q.N;                                     // [TG][KW] quantised means, 4 channels per word
+  const int tid = threadIdx.x;
+  for (int i = tid; i < KW * Q.N; i += 256) {
+    const int n = i / KW, kw = i - n * KW;                     // coalesced global read, transposed shared write
+    wT[kw * Q.N + n] = __ldg(reinterpret_cast<const int*>(Q.w) + i);
+  }
+  const int N = Q.npix;
+  for (int g0 = blockIdx.x * TG; g0 < Bw; g0 += gridDim.x * TG) {
+    const int ng = Bw - g0 < TG ? Bw - g0 : TG;
+    __syncthreads();                                           // previous group's FC is done with mq (and wT is filled)
+    // MEAN over the npix positions: a thread sums 4 channels (one word) of one chunk
+    for (int i = tid; i < ng * KW; i += 256) {
+      const int j = i / KW, kw = i - j * KW;
+      const int* xp = reinterpret_cast<const int*>(x + (long)(g0 + j) * N * Q.K) + kw;
+      int s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll 8
+      for (int p = 0; p < N; p++) {
+        const int v = __ldg(xp + (long)p * KW);
+        s0 = __dp4a(v, 0x00000001, s0); s1 = __dp4a(v, 0x00000100, s1); s2 = __dp4a(v, 0x00010000, s2); s3 = __dp4a(v, 0x01000000, s3);
+      }
+      int o[4];
+      const int sums[4] = {s0, s1, s2, s3};
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const int sum = sums[c];
+        if (variant == 1) {
+          float scale = __fdiv_rn(Q.mean_in_scale, Q.mean_out_scale);
+          float bias = __fmul_rn(-(float)Q.mean_in_zp, scale);
+          float fm = __fdiv_rn((float)sum, (float)N);
+          o[c] = (int)roundf(__fadd_rn(__fmul_rn(fm, scale), bias)) + Q.mean_out_zp;
+        } else if (variant == 2) {
+          o[c] = requant(sum - Q.mean_in_zp * N, Q.mean_mult_n, Q.mean_shift_n, R) + Q.mean_out_zp;
+        } else {
+          int acc = requant(sum - Q.mean_in_zp * N, Q.mean_mult, Q.mean_shift, R);
+          acc = acc > 0 ? (acc + N / 2) / N : (acc - N / 2) / N;
+          o[c] = acc + Q.mean_out_zp;
+        }
+      }
+      mq[j * KW + kw] = (int)pack4_sat(o[0], o[1], o[2], o[3]);
+    }
+    __syncthreads();
+    // FC + LOGISTIC + DEQUANTIZE: one (chunk, class) per thread
+    for (int i = tid; i < ng * Q.N; i += 256) {
+      const int j = i / Q.N, n = i - j * Q.N;
+      const int* m = mq + j * KW;
+      int acc = 0;
+#pragma unroll 8
+      for (int kw = 0; kw < KW; kw++) acc = __dp4a(m[kw], wT[kw * Q.N + n], acc);
+      const int q = clampi(requant(acc + __ldg(Q.bias + n), __ldg(Q.mult + n), __ldg(Q.shift + n), R) + Q.fc_out_zp, Q.fc_act_min, Q.fc_act_max);
+      const int l = (int)__ldg(Q.lut + (uint8_t)(q + 128));
+      scores[(long)(g0 + j) * Q.N + n] = __fmul_rn(Q.dq_scale, (float)(l - Q.dq_zp));
+    }
+  }
+}
+
 // =================================================================================================
 // run
 // =================================================================================================
@@ -1517,7 +1582,17 @@ static int run_body(FastPlan& fp, int Bw, float* d_scores, int rounding, int mea
     const int variant = mean_variant ? mean_variant : (im->tail.keep_dims ? 3 : 2);
     const int8_t* last = (const int8_t*)im->slot_buf[im->blocks.back().out_slot];
     if (prof) prof->begin("K6_tail", st);
-    k_tail<<<Bw, 256, 0, st>>>(last, d_scores, im->tail, variant, R);
+    const size_t tsm = ((size_t)(im->tail.K / 4) * im->tail.N + (size_t)TG * (im->tail.K / 4)) * 4;
+    static const bool tail_single = getenv("BN_TAIL_SINGLE") != nullptr;
+    if (!tail_single && (im->tail.K & 3) == 0 && tsm <= 96 * 1024) {
+      static bool attr = false;
+      if (!attr) { cudaFuncSetAttribute(k_tail_g, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; }
+      int grid = (Bw + TG - 1) / TG;
+      if (grid > fp.num_sms * 4) grid = fp.num_sms * 4;
+      k_tail_g<<<grid, 256, tsm, st>>>(last, d_scores, im->tail, variant, R, Bw);
+    } else {
+      k_tail<<<Bw, 256, 0, st>>>(last, d_scores, im->tail, variant, R);
+    }
     if (prof) prof->end(st);
     (*launches)++;
   }
