@@ -38,8 +38,10 @@ __device__ __forceinline__ int rq64(int acc, int c_lo, int c_hi, int mult, int r
 __device__ __forceinline__ int clamp2(int v, int lo, int hi) { return max(lo, min(v, hi)); }
 // MB = resident CTAs per SM the register allocation is sized for: 2 (128 registers) or 3 (80 registers; only the
 // transposed depthwise fits that without meaningful spilling).
-template <int S, int TR, int ADD, int DWT, int MB>
-__global__ void __launch_bounds__(DS_THREADS, MB)
+// NT = threads per CTA: 256, or 512 for the late layers whose shared-memory footprint (64 KB weight image, four-chunk tiles)
+// leaves one CTA per SM -- 16 warps instead of 8 to hide the phase latencies.
+template <int S, int TR, int ADD, int DWT, int MB, int NT>
+__global__ void __launch_bounds__(NT, MB)
 k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles, DsParams P) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -66,17 +68,17 @@ k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles
     mbar_init(smem_u32(&mbar[1]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = tid; i < b_bytes / 16; i += DS_THREADS) cp_async16(smem_u32(sB + 16 * i), P.w_img + 16 * (size_t)i);
+  for (int i = tid; i < b_bytes / 16; i += NT) cp_async16(smem_u32(sB + 16 * i), P.w_img + 16 * (size_t)i);
   cp_async_commit();
-  for (int i = tid; i < N; i += DS_THREADS) { s_rq[i] = __ldg(P.pw_rq + i); s_rz[i] = __ldg(P.pw_rz + i); }
-  if (P.C < KP) for (int i = tid; i < NAB * a_bytes / 16; i += DS_THREADS) *reinterpret_cast<uint4*>(sA0 + 16 * i) = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < N; i += NT) { s_rq[i] = __ldg(P.pw_rq + i); s_rz[i] = __ldg(P.pw_rz + i); }
+  if (P.C < KP) for (int i = tid; i < NAB * a_bytes / 16; i += NT) *reinterpret_cast<uint4*>(sA0 + 16 * i) = make_uint4(0, 0, 0, 0);
   const unsigned zpw = 0x01010101u * (unsigned)(uint8_t)P.dw_in_zp;
   {  // halo columns hold the zero point for the whole kernel (cp.async never touches them)
     const int rows = P.NB * TRIN;
     const int wpc = C >> 2;                           // words per pixel
     for (int sb = 0; sb < NST; sb++) {
       unsigned* tw = reinterpret_cast<unsigned*>(sT0 + sb * tile_bytes);
-      for (int i = tid; i < rows * wpc * 2; i += DS_THREADS) {
+      for (int i = tid; i < rows * wpc * 2; i += NT) {
         const int side = i & 1, rest = i >> 1;
         const int row = rest / wpc, w = rest - row * wpc;
         if (side == 0 && P.pl == 0) continue;
@@ -133,7 +135,7 @@ k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles
   auto stage = [&](int tile, unsigned char* sT) {
     int b0, oy0;
     tile_origin(tile, b0, oy0);
-    for (int row = warp; row < P.NB * TRIN; row += DS_THREADS / 32) {
+    for (int row = warp; row < P.NB * TRIN; row += NT / 32) {
       const int bb = row / TRIN, tr = row - bb * TRIN;
       const int iy = oy0 * S - P.pt + tr;
       const bool ok = (b0 + bb) < Bw && iy >= 0 && iy < P.ih;
@@ -146,7 +148,7 @@ k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles
 
   // ---- (2) depthwise 3x3 -> swizzled A operand --------------------------------------------------------------------
   auto depthwise = [&](const unsigned char* sT, unsigned char* sA) {
-    for (int sidx = tid; sidx < nstrips; sidx += DS_THREADS) {
+    for (int sidx = tid; sidx < nstrips; sidx += NT) {
       const int rest = sidx >> P.cg_log;
       const int ox = rest & (P.ow - 1), bb = rest >> P.ow_log;
       const unsigned* tp = reinterpret_cast<const unsigned*>(sT) + ((size_t)(bb * TRIN) * TW + ox * S) * CG + cg;
@@ -202,7 +204,7 @@ k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles
     constexpr int NCOL = S == 1 ? 2 : 1;              // output columns per thread
     const int owp_log = P.ow_log - (S == 1 ? 1 : 0);
     const int nst = nstrips >> (S == 1 ? 1 : 0);
-    for (int sidx = tid; sidx < nst; sidx += DS_THREADS) {
+    for (int sidx = tid; sidx < nst; sidx += NT) {
       const int rest = sidx >> P.cg_log;
       const int oxp = rest & ((1 << owp_log) - 1), bb = rest >> owp_log;
       const int ox = oxp * NCOL;
@@ -283,7 +285,7 @@ k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles
     int b0, oy0;
     tile_origin(tile, b0, oy0);
     const size_t pix0 = ((size_t)b0 * P.oh + oy0) << P.ow_log;
-    for (int t = hsel; t < P.MT * NG; t += 2) {
+    for (int t = hsel; t < P.MT * NG; t += NT / 128) {
       const int j = t / NG, g = t - j * NG;
       const int m = j * 128 + 32 * q + lane;
       const int bb = m >> P.trow_log;
@@ -409,11 +411,11 @@ size_t ds_smem_bytes(const DsParams& P, int S, int TR) {
   return b + 1024;                                   // alignment slack
 }
 
-template <int S, int TR, int ADD, int DWT, int MB>
+template <int S, int TR, int ADD, int DWT, int MB, int NT = DS_THREADS>
 static int launch_one(const int8_t* in, int8_t* out, int Bw, int ntiles, int grid, size_t smem, const DsParams& P, cudaStream_t st) {
   static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(k_ds<S, TR, ADD, DWT, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; }
-  k_ds<S, TR, ADD, DWT, MB><<<grid, DS_THREADS, smem, st>>>(in, out, Bw, ntiles, P);
+  if (!attr) { cudaFuncSetAttribute(k_ds<S, TR, ADD, DWT, MB, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; }
+  k_ds<S, TR, ADD, DWT, MB, NT><<<grid, NT, smem, st>>>(in, out, Bw, ntiles, P);
   return 0;
 }
 
@@ -422,6 +424,12 @@ int launch_ds(const int8_t* in, int8_t* out, int Bw, const DsParams& P, const Ds
   int grid = num_sms * L.ctas_per_sm;
   if (grid > ntiles) grid = ntiles;
   if (grid < 1) return 0;
+  // 512-thread build for single-CTA layers (transposed depthwise only; the two shapes the late layers use)
+  if (L.threads == 512 && L.dwt && L.ctas_per_sm == 1) {
+    if (L.S == 1 && L.TR == 4 && L.add_mode == 2) return launch_one<1, 4, 2, 1, 1, 512>(in, out, Bw, ntiles, grid, L.smem, P, st);
+    if (L.S == 1 && L.TR == 4 && L.add_mode == 1) return launch_one<1, 4, 1, 1, 1, 512>(in, out, Bw, ntiles, grid, L.smem, P, st);
+    if (L.S == 2 && L.TR == 4 && L.add_mode == 0) return launch_one<2, 4, 0, 1, 1, 512>(in, out, Bw, ntiles, grid, L.smem, P, st);
+  }
 #define DS_CASE(s, tr, add)                                                                                         \
   if (L.S == s && L.TR == tr && L.add_mode == add)                                                                  \
     return !L.dwt ? launch_one<s, tr, add, 0, 2>(in, out, Bw, ntiles, grid, L.smem, P, st)                          \

@@ -47,6 +47,7 @@ struct DsLaunch {
   size_t smem;
   int ctas_per_sm;
   int tcdw;               // 1 = run bn_ds_tc.cu (both convolutions on the tensor core)
+  int threads;            // 256, or 512 for single-CTA layers (see k_ds)
   int dwt;                // 1 = depthwise with filter rows along the dp4a axis (PRMT transpose, 3 dp4a per output), 0 = masked words (9)
 };
 

@@ -525,7 +525,9 @@ static bool prep_ds(FastPlan& fp, FastImpl* im, Block& bl) {
         D.nst = f; D.tmem_cols = c2; L.smem = sm; L.ctas_per_sm = per;
       }
     }
-    if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: C=%d N=%d S=%d nst=%d smem=%zu ctas/SM=%d tmem=%d\n", C, N, S, D.nst, L.smem, L.ctas_per_sm, D.tmem_cols);
+    L.threads = 256;
+    if (L.ctas_per_sm == 1 && L.dwt && TR == 4 && (getenv("BN_DS_512") ? atoi(getenv("BN_DS_512")) : 1)) L.threads = 512;
+    if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: C=%d N=%d S=%d nst=%d smem=%zu ctas/SM=%d tmem=%d threads=%d\n", C, N, S, D.nst, L.smem, L.ctas_per_sm, D.tmem_cols, L.threads);
   }
   // Variant with both convolutions on the tensor core (bn_ds_tc.cu) for stride-1 blocks whose diagonal depthwise
   // operand fits.  It is prepared next to the default kernel and selected at run time by BN_OPT_FUSION bit 2: measured
