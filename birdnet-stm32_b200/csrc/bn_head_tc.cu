@@ -16,19 +16,22 @@
 // constant; the (rare) near-tie elements take the exact two-division chain.
 #include "bn_head_tc.cuh"
 
+#include <cstdlib>
+
 #include "bn_common.cuh"
 #include "bn_tc.cuh"
 
 namespace bn {
 
 constexpr int HT_THREADS = 256;
+constexpr int HT_CTAS = 3;           // resident CTAs per SM (80 registers, 74 KB shared memory each)
 constexpr int HT_M = 128;
 constexpr int HT_A_BYTES = HT_M * HT_KP;            // 36864
 constexpr int HT_OFF_A = HT_B_BYTES;                // 18432 (1024-aligned)
 constexpr int HT_OFF_LUT = HT_OFF_A + HT_A_BYTES;   // 55296
-constexpr int HT_OFF_OUT = HT_OFF_LUT + HT_N * 256; // 71680
-constexpr int HT_OFF_RQ = HT_OFF_OUT + HT_N * HT_M; // 79872
-constexpr int HT_OFF_BAR = HT_OFF_RQ + HT_N * 16;   // 80896
+constexpr int HT_OFF_OUT = HT_OFF_A;                // the transposed output tile reuses the A operand (dead once the MMAs have completed)
+constexpr int HT_OFF_RQ = HT_OFF_LUT + HT_N * 256;  // 71680
+constexpr int HT_OFF_BAR = HT_OFF_RQ + HT_N * 16;   // 72704  -> 74 KB per CTA, three CTAs per SM
 constexpr int HT_SMEM = HT_OFF_BAR + 16 + 1024;
 
 __device__ __forceinline__ int quant_code(float f, float mn, float den, float qmul, float scale, int zp_bits, int zp) {
@@ -64,7 +67,7 @@ __device__ __forceinline__ void quant_code2(float f0, float f1, float mn, float 
   if (fabsf(df1) > 0.49975f) q1 = (int)roundf(__fdiv_rn(__fdiv_rn(d1, den), scale)) + zp;
 }
 
-__global__ void __launch_bounds__(HT_THREADS, 2)
+__global__ void __launch_bounds__(HT_THREADS, HT_CTAS)
 k_head_tc(const float* __restrict__ mags, const unsigned* __restrict__ mnmx, int8_t* __restrict__ out, int ntiles, HeadTcParams P) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -188,6 +191,7 @@ k_head_tc(const float* __restrict__ mags, const unsigned* __restrict__ mnmx, int
       const int c = i >> 3, piece = i & 7;
       *reinterpret_cast<uint4*>(ob + (size_t)c * P.W + 16 * piece) = *reinterpret_cast<const uint4*>(sOut + c * HT_M + 16 * piece);
     }
+    __syncthreads();                                      // sOut aliases sA: the next tile's quantisation overwrites it
   }
   tc_fence_before();
   __syncthreads();
@@ -212,7 +216,7 @@ int launch_head_tc(const float* mags, const unsigned* mnmx, int8_t* out, int Bw,
   if (!attr) { cudaFuncSetAttribute(k_head_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_SMEM); attr = true; }
   if (P.W % HT_M || (P.ldk != 260 && P.ldk != 264) || P.K_real != 257) return BN_ERR_UNSUPPORTED;
   const int ntiles = Bw * (P.W / HT_M);
-  int grid = num_sms * 2;
+  int grid = num_sms * (getenv("BN_HEAD_CTAS") ? atoi(getenv("BN_HEAD_CTAS")) : HT_CTAS);
   if (grid > ntiles) grid = ntiles;
   if (grid < 1) return 0;
   k_head_tc<<<grid, HT_THREADS, HT_SMEM, st>>>(mags, mnmx, out, ntiles, P);
