@@ -25,7 +25,8 @@ namespace bn {
 constexpr int KF_THREADS = 256;
 constexpr int KF_LDK = 264;          // floats per frame row of the magnitude scratch
 constexpr int KF_FG = 32;            // frames staged per step
-constexpr int KF_SUBWAVE = 256;      // chunks per K1 -> KF round (scratch stays in L2)
+constexpr int KF_SUBWAVE = 1184;     // chunks per K1 -> KF round (4 x 296 resident K1 CTAs; measured on the classification path: fewer,
+                                     // larger launches beat keeping the 270 KB/chunk scratch inside L2, see bn_fast.cu fe_subwave())
 
 struct FeatDev {
   const float* basis;   // [n_mels][bins]
