@@ -29,6 +29,8 @@ def get_args(argv=None) -> argparse.Namespace:
     p.add_argument("--profile_memory", action="store_true", default=False)
     p.add_argument("--device", type=int, default=None, help="CUDA device (default: LOCAL_RANK or 0)")
     p.add_argument("--device_batch_chunks", type=int, default=4096, help="Chunks sent to the device per call")
+    p.add_argument("--metrics_backend", type=str, default="sklearn", choices=["sklearn", "device"],
+                   help="Metric tail: the reference's scikit-learn calls on the host, or the same definitions on the GPU")
     return p.parse_args(argv)
 
 
@@ -56,7 +58,8 @@ def main(argv=None):
     device = args.device if args.device is not None else local
     runner = load_model_runner(args.model_path, model_config=cfg, device=device)
     kw = dict(pooling=args.pooling, batch_size=args.batch_size, overlap=max(0.0, min(cfg["chunk_duration"] - 0.1, args.overlap)),
-              measure_latency=args.benchmark_latency, profile_memory=args.profile_memory, device_batch_chunks=args.device_batch_chunks)
+              measure_latency=args.benchmark_latency, profile_memory=args.profile_memory, device_batch_chunks=args.device_batch_chunks,
+              metrics_backend=args.metrics_backend)
     if world > 1:
         import torch
         import torch.distributed as dist
