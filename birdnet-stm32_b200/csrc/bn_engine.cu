@@ -5,8 +5,15 @@
 // (birdnet_stm32/evaluation/metrics.py:117-147); here chunks of many files are processed in
 // waves, host buffers are moved with double-buffered async copies, and per-file pooling runs on
 // the device.  There is no CPU execution path in this library.
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE
+#endif
+#include <ctype.h>
+#include <sched.h>
+
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -711,9 +718,68 @@ extern "C" int bn_profile_read(bn_engine* e, int index, char* name, size_t name_
 
 extern "C" int64_t bn_launch_count(const bn_engine* e) { return e ? e->launches : 0; }
 
+// NUMA placement of pinned buffers.  On a two-socket host the pages of a pinned buffer land on the socket of the thread that
+// calls cudaMallocHost; when that is not the socket the GPU hangs off, every upload crosses the inter-socket link.  So the
+// calling thread is bound to the CPUs of the current device's NUMA node for the duration of the allocation.  (On the round-1
+// measurement boxes this is a no-op: they are VMs that expose one NUMA node and numa_node = -1 for every PCI device; their
+// aggregate host-to-device rate saturates at about 115 GB/s with 4 and 186 GB/s with 8 GPUs uploading at once, which is what
+// bounds the multi-GPU end-to-end numbers in profiles/r1/bench_N4 / bench_N8.)
+static int device_numa_node(int dev) {
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof bus, dev) != cudaSuccess) { cudaGetLastError(); return -1; }
+  for (char* c = bus; *c; c++) *c = (char)tolower(*c);
+  char path[128];
+  snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+  FILE* f = fopen(path, "r");
+  if (!f) return -1;
+  int node = -1;
+  if (fscanf(f, "%d", &node) != 1) node = -1;
+  fclose(f);
+  return node;
+}
+
+static bool numa_node_cpus(int node, cpu_set_t* set) {
+  char path[128];
+  snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+  FILE* f = fopen(path, "r");
+  if (!f) return false;
+  char buf[4096] = {0};
+  const bool ok = fgets(buf, sizeof buf, f) != nullptr;
+  fclose(f);
+  if (!ok) return false;
+  CPU_ZERO(set);
+  int n = 0;
+  for (char* tok = strtok(buf, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+    int a = 0, b = 0;
+    const int got = sscanf(tok, "%d-%d", &a, &b);
+    if (got == 1) b = a;
+    if (got < 1) continue;
+    for (int c = a; c <= b && c < CPU_SETSIZE; c++) { CPU_SET(c, set); n++; }
+  }
+  return n > 0;
+}
+
 extern "C" void* bn_host_alloc(size_t nbytes) {
   void* p = nullptr;
-  if (cudaMallocHost(&p, nbytes) != cudaSuccess) { cudaGetLastError(); set_err(BN_ERR_CUDA, "cudaMallocHost(%zu) failed", nbytes); return nullptr; }
+  cpu_set_t old_set, want;
+  bool bound = false;
+  if (!getenv("BN_NO_NUMA_BIND")) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) {
+      const int node = device_numa_node(dev);
+      if (node >= 0 && numa_node_cpus(node, &want) && sched_getaffinity(0, sizeof old_set, &old_set) == 0) {
+        cpu_set_t both;
+        CPU_AND(&both, &want, &old_set);                // stay inside the CPUs this process is allowed to use
+        if (CPU_COUNT(&both) > 0 && sched_setaffinity(0, sizeof both, &both) == 0) bound = true;
+      }
+    } else {
+      cudaGetLastError();
+    }
+  }
+  const cudaError_t ce = cudaMallocHost(&p, nbytes);
+  if (ce == cudaSuccess && bound && nbytes) memset(p, 0, nbytes < (1u << 20) ? nbytes : (1u << 20));   // harmless; pages are already resident
+  if (bound) sched_setaffinity(0, sizeof old_set, &old_set);
+  if (ce != cudaSuccess) { cudaGetLastError(); set_err(BN_ERR_CUDA, "cudaMallocHost(%zu) failed", nbytes); return nullptr; }
   return p;
 }
 extern "C" void bn_host_free(void* p) { if (p) cudaFreeHost(p); }
