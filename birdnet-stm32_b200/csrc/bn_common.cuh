@@ -91,6 +91,17 @@ __device__ __forceinline__ unsigned pack4_sat(int a, int b, int c, int d) {
 }
 #endif
 
+// cudaFuncSetAttribute is per device: "once" flags of the launchers are bit masks over device ordinals, so an engine on
+// cuda:1 created after one on cuda:0 in the same process still raises its kernels' dynamic shared-memory limit.
+inline bool first_use_on_device(unsigned long long& mask) {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess) d = 0;
+  const unsigned long long bit = 1ull << (d & 63);
+  if (mask & bit) return false;
+  mask |= bit;
+  return true;
+}
+
 struct ConvParams {
   const int8_t* w;
   const int32_t* bias;

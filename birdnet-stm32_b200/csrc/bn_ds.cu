@@ -413,8 +413,8 @@ size_t ds_smem_bytes(const DsParams& P, int S, int TR) {
 
 template <int S, int TR, int ADD, int DWT, int MB, int NT = DS_THREADS>
 static int launch_one(const int8_t* in, int8_t* out, int Bw, int ntiles, int grid, size_t smem, const DsParams& P, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(k_ds<S, TR, ADD, DWT, MB, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; }
+  static unsigned long long attr = 0;
+  if (first_use_on_device(attr)) cudaFuncSetAttribute(k_ds<S, TR, ADD, DWT, MB, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   k_ds<S, TR, ADD, DWT, MB, NT><<<grid, NT, smem, st>>>(in, out, Bw, ntiles, P);
   return 0;
 }

@@ -280,8 +280,8 @@ void dst_weight_image(const int8_t* w /*[9][C]*/, int C, std::vector<uint8_t>& i
 
 template <int ADD>
 static int launch_one_t(const int8_t* in, int8_t* out, int Bw, int ntiles, int grid, size_t smem, const DsParams& P, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(k_dst<ADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; }
+  static unsigned long long attr = 0;
+  if (first_use_on_device(attr)) cudaFuncSetAttribute(k_dst<ADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   k_dst<ADD><<<grid, DST_THREADS, smem, st>>>(in, out, Bw, ntiles, P);
   return 0;
 }

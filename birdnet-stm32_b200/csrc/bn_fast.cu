@@ -1484,15 +1484,14 @@ static size_t pw_smem(const PwParams& P) {
 static int run_head(FastPlan& fp, int mode, const float* src, const unsigned* mnmx, int b0, int nb, int rounding, cudaStream_t st,
                     int64_t* launches, Profiler* prof) {
   FastImpl* im = fp.impl;
-  static bool attrs = false;
-  if (!attrs) {
+  static unsigned long long attrs = 0;
+  if (first_use_on_device(attrs)) {
     cudaFuncSetAttribute(k_head<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_head<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_head<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_head<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_pw<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_pw<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attrs = true;
   }
   const int R = rounding;
   int8_t* head_out = (int8_t*)im->slot_buf[im->head_out_slot] + (size_t)b0 * HEAD_N * im->W;
@@ -1587,8 +1586,8 @@ static int run_body(FastPlan& fp, int Bw, float* d_scores, int rounding, int mea
     const size_t tsm = ((size_t)(im->tail.K / 4) * im->tail.N + (size_t)TG * (im->tail.K / 4)) * 4;
     static const bool tail_single = getenv("BN_TAIL_SINGLE") != nullptr;
     if (!tail_single && (im->tail.K & 3) == 0 && tsm <= 96 * 1024) {
-      static bool attr = false;
-      if (!attr) { cudaFuncSetAttribute(k_tail_g, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; }
+      static unsigned long long attr = 0;
+      if (first_use_on_device(attr)) cudaFuncSetAttribute(k_tail_g, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
       int grid = (Bw + TG - 1) / TG;
       if (grid > fp.num_sms * 4) grid = fp.num_sms * 4;
       k_tail_g<<<grid, 256, tsm, st>>>(last, d_scores, im->tail, variant, R, Bw);

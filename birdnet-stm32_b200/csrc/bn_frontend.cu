@@ -314,11 +314,11 @@ __global__ void k_init_minmax(unsigned* mnmx, int B) {
 
 // tw512[m] = exp(-2 pi i m / 512) (float2) followed by the periodic Hann window win[m] = 0.5 - 0.5 cos(2 pi m / 512)
 static const float4* stft_tables() {
-  static float4* d_tab = nullptr;
-  static int dev_of = -1;
+  static float4* d_tabs[64] = {nullptr};                // one copy per device ordinal
   int dev = 0;
   cudaGetDevice(&dev);
-  if (d_tab && dev_of == dev) return d_tab;
+  float4*& d_tab = d_tabs[dev & 63];
+  if (d_tab) return d_tab;
   float h[NFFT * 3];
   const double PI = 3.14159265358979323846;
   for (int m = 0; m < NFFT; m++) {
@@ -326,9 +326,8 @@ static const float4* stft_tables() {
     h[2 * m + 1] = (float)(-sin(2.0 * PI * m / NFFT));
     h[2 * NFFT + m] = (float)(0.5 - 0.5 * cos(2.0 * PI * m / NFFT));
   }
-  if (cudaMalloc(&d_tab, sizeof h) != cudaSuccess) return nullptr;
+  if (cudaMalloc(&d_tab, sizeof h) != cudaSuccess) { d_tab = nullptr; return nullptr; }
   cudaMemcpy(d_tab, h, sizeof h, cudaMemcpyHostToDevice);
-  dev_of = dev;
   return d_tab;
 }
 
@@ -364,11 +363,8 @@ int launch_stft_mag(const void* pcm, int f32, const float* peak, float* out, uns
   if (n_fft != NFFT) return BN_ERR_UNSUPPORTED;
   const size_t smem = stft_smem_bytes(hop, false, f32 != 0);
   if (smem > 227 * 1024) return BN_ERR_UNSUPPORTED;
-  static bool attr_done = false;
-  if (!attr_done) {
-    set_stft_attrs();
-    attr_done = true;
-  }
+  static unsigned long long attr_done = 0;
+  if (first_use_on_device(attr_done)) set_stft_attrs();
   const float4* tab = stft_tables();
   if (!tab) return BN_ERR_CUDA;
   if (W % FRAMES_PER_CTA) return BN_ERR_UNSUPPORTED;
@@ -385,11 +381,8 @@ int launch_stft_mag_fm(const void* pcm, int f32, const float* peak, float* out, 
   if (n_fft != NFFT || ldk < BINS) return BN_ERR_UNSUPPORTED;
   const size_t smem = stft_smem_bytes(hop, true, f32 != 0);
   if (smem > 227 * 1024) return BN_ERR_UNSUPPORTED;
-  static bool attr_done = false;
-  if (!attr_done) {
-    set_stft_attrs();
-    attr_done = true;
-  }
+  static unsigned long long attr_done = 0;
+  if (first_use_on_device(attr_done)) set_stft_attrs();
   const float4* tab = stft_tables();
   if (!tab) return BN_ERR_CUDA;
   if (W % FRAMES_PER_CTA) return BN_ERR_UNSUPPORTED;

@@ -212,8 +212,8 @@ void head_tc_weight_image(const int8_t* w, int K, std::vector<uint8_t>& img) {
 }
 
 int launch_head_tc(const float* mags, const unsigned* mnmx, int8_t* out, int Bw, const HeadTcParams& P, int num_sms, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(k_head_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_SMEM); attr = true; }
+  static unsigned long long attr = 0;
+  if (first_use_on_device(attr)) cudaFuncSetAttribute(k_head_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_SMEM);
   if (P.W % HT_M || (P.ldk != 260 && P.ldk != 264) || P.K_real != 257) return BN_ERR_UNSUPPORTED;
   const int ntiles = Bw * (P.W / HT_M);
   int grid = num_sms * (getenv("BN_HEAD_CTAS") ? atoi(getenv("BN_HEAD_CTAS")) : HT_CTAS);

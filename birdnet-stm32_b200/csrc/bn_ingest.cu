@@ -490,8 +490,8 @@ static int ingest_core(bn_ingest* g, const void* frames, int fmt, int64_t n_fram
     const size_t hs_bytes = ((size_t)F.per_phase * S + 4) * sizeof(float);
     static const bool force_generic = getenv("BN_INGEST_GENERIC") != nullptr;
     if (S > 0 && hs_bytes <= 200 * 1024 && !force_generic) {
-      static bool attr = false;
-      if (!attr) { cudaFuncSetAttribute(k_resample_phase, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+      static unsigned long long attr = 0;
+      if (first_use_on_device(attr)) cudaFuncSetAttribute(k_resample_phase, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       const long steps = (n_out + S - 1) / S;                       // block steps in total
       const int per_sm = (int)(200 * 1024 / (hs_bytes + 1024)) < (2048 / ((S + 31) & ~31)) ? (int)(200 * 1024 / (hs_bytes + 1024)) : (2048 / ((S + 31) & ~31));
       long blocks = (long)g->sms * (per_sm < 1 ? 1 : per_sm);

@@ -205,8 +205,8 @@ void pw_tc_weight_image(const int8_t* w, int K, int N, std::vector<uint8_t>& img
 size_t pw_tc_smem_bytes(const PwTcParams& P) { return (size_t)P.N * P.KP + 2 * 128 * (size_t)P.KP + 3 * P.N * 4 + 64 + 1024; }
 
 int launch_pw_tc(const int8_t* x, const int8_t* res, int8_t* y, long M, const PwTcParams& P, int num_sms, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(k_pw_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+  static unsigned long long attr = 0;
+  if (first_use_on_device(attr)) cudaFuncSetAttribute(k_pw_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (M <= 0 || M > 0x7fffffffL) return BN_ERR_ARG;
   const int ntiles = (int)((M + 127) / 128);
   const size_t smem = pw_tc_smem_bytes(P);
