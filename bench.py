@@ -329,7 +329,7 @@ def run_b200(args):
     tot_ms = sum(v[0] for v in prof.values()) or 1.0
     dom = max(prof.items(), key=lambda kv: kv[1][0]) if prof else ("none", (1.0, 1))
     dom_ms_per_launch = dom[1][0] / max(dom[1][1], 1)
-    # chunks one launch of that kernel processes (the frontend kernels run in sub-waves, the body in whole waves)
+    # chunks one launch of that kernel processes (every kernel runs once per wave; the last wave of a step is partial)
     chunks_per_launch = n_chunks * args.steps / max(dom[1][1], 1)
     achieved = BYTES_PER_CHUNK_ALG * chunks_per_launch / (dom_ms_per_launch / 1e3) / 1e9
     # DRAM bytes per launch of the same kernel from the committed `ncu --set full` capture (profiles/r1/ncu_traffic.json)

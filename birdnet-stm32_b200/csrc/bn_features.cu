@@ -10,7 +10,7 @@
 //                                                   reductions, (MFCC: dB + DCT), normalize(), store [rows][W]
 //
 // Everything a chunk needs after the STFT lives in shared memory (<= 74 KB mel tile), so the features make one trip:
-// magnitudes in (L2-resident scratch written by K1 just before), normalised features out.
+// magnitudes in (scratch written by K1 just before), normalised features out.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
