@@ -61,6 +61,8 @@ def split_audio_into_chunks(audio: np.ndarray, sample_rate: int = 24000, chunk_d
         return np.empty((0, max(size, 0)), dtype=dtype)
     y = y.astype(dtype, copy=False)
     starts = chunk_starts(y.size, sample_rate, chunk_duration, chunk_overlap)
+    if y.size == starts.size * size and (starts.size == 1 or int(starts[1]) == size):
+        return y.reshape(starts.size, size)            # back-to-back chunks of an exact multiple: a view, no copy
     out = np.zeros((starts.size, size), dtype=dtype)
     if y.size <= size:
         out[0, : y.size] = y
@@ -137,7 +139,9 @@ def load_pcm16_window(path: str, sample_rate: int, max_duration: float | None = 
     pcm, sr0 = read_wav_pcm16(path, limit)
     if sr0 != sample_rate:
         raise UnsupportedAudio(f"{path}: sample rate {sr0} != model rate {sample_rate} (host resampling is a next-step row)")
-    peak = np.float32(np.abs(pcm.astype(np.float32) / np.float32(32768.0)).max()) if pcm.size else np.float32(0)
+    # max|s / 32768| in float32 == max|s| / 32768 (division by a power of two is exact and monotone): two int16 passes
+    # instead of a float32 copy, abs and max (2.0 -> 0.2 ms per 60 s file)
+    peak = np.float32(max(int(pcm.max()), -int(pcm.min()))) / np.float32(32768.0) if pcm.size else np.float32(0)
     return pcm, peak
 
 
@@ -189,3 +193,31 @@ def save_wav(audio: np.ndarray, path: str, sample_rate: int = 24000) -> None:
         wf.setsampwidth(2)
         wf.setframerate(int(sample_rate))
         wf.writeframes(a.astype("<i2").tobytes())
+
+
+def prefetch_ordered(fn, items, workers: int = 8, depth: int | None = None):
+    """Yield `fn(item)` for every item, in order, computed by a pool of reader threads that runs ahead of the
+    consumer by at most `depth` items.  File reads and the numpy copies behind `fn` release the GIL, so the GPU
+    path is fed while the next files are still being read (the reference reads, decodes and resamples each file
+    serially before its `predict` calls, `evaluation/metrics.py:117-147`).  `workers <= 1` is a plain loop."""
+    items = list(items)
+    if workers <= 1 or len(items) <= 1:
+        for it in items:
+            yield fn(it)
+        return
+    from collections import deque
+    from concurrent.futures import ThreadPoolExecutor
+
+    depth = depth or 4 * workers
+    with ThreadPoolExecutor(max_workers=workers, thread_name_prefix="bn-io") as pool:
+        pending: deque = deque()
+        nxt = 0
+        while nxt < len(items) and len(pending) < depth:
+            pending.append(pool.submit(fn, items[nxt]))
+            nxt += 1
+        while pending:
+            fut = pending.popleft()
+            if nxt < len(items):
+                pending.append(pool.submit(fn, items[nxt]))
+                nxt += 1
+            yield fut.result()

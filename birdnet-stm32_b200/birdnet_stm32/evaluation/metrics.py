@@ -17,7 +17,7 @@ import time
 
 import numpy as np
 
-from birdnet_stm32.audio.io import UnsupportedAudio, load_pcm16_chunks, read_wav_frames
+from birdnet_stm32.audio.io import UnsupportedAudio, load_pcm16_chunks, prefetch_ordered, read_wav_frames
 from birdnet_stm32.evaluation.pooling import pool_scores
 from birdnet_stm32.models.frontend import normalize_frontend_name
 
@@ -120,11 +120,12 @@ def _metrics_from_scores(y_true_arr: np.ndarray, y_scores_arr: np.ndarray) -> di
 def evaluate(model_runner, files: list[str], classes: list[str], cfg: dict, pooling: str = "average",
              batch_size: int = 64, overlap: float = 0.0, mep_beta: float = 10.0, measure_latency: bool = False,
              profile_memory: bool = False, device_batch_chunks: int = 4096,
-             frontend_runner=None, metrics_backend: str = "sklearn") -> tuple[dict, list[dict], np.ndarray, np.ndarray]:
+             frontend_runner=None, metrics_backend: str = "sklearn", io_workers: int = 8) -> tuple[dict, list[dict], np.ndarray, np.ndarray]:
     """Run inference per chunk, pool to file level and compute metrics (see module docstring).
 
     metrics_backend: "sklearn" (the reference's own calls, host) or "device" (`evaluation/device_metrics.py`: the same
-    definitions evaluated by `bn_metrics_compute` on the GPU -- for evaluations with millions of (file, class) cells)."""
+    definitions evaluated by `bn_metrics_compute` on the GPU -- for evaluations with millions of (file, class) cells).
+    io_workers: reader threads of the device path (files are read and cut into chunks ahead of the GPU calls, in order)."""
     if metrics_backend not in ("sklearn", "device"):
         raise ValueError(f"Unsupported metrics backend: {metrics_backend}")
     frontend = normalize_frontend_name(cfg["audio_frontend"])
@@ -207,23 +208,31 @@ def evaluate(model_runner, files: list[str], classes: list[str], cfg: dict, pool
                 per_file.append({"file": f["path"], "label": f["label"], "scores": rows[i].tolist()})
             pend.clear()
 
-        for path in files:
-            label = os.path.basename(os.path.dirname(path))
-            if label not in class_index:
-                continue
+        def read_one(path: str):
+            """Runs on a reader thread: container parse + chunk cut only (numpy / file I/O, no CUDA calls)."""
             try:
                 pcm, peak = load_pcm16_chunks(path, sr, cd, overlap, max_duration=60)
-                if pcm.shape[0] == 0:
-                    skipped += 1
-                    continue
-                pend.append({"path": path, "label": label, "kind": "pcm", "n": pcm.shape[0], "pcm": pcm,
-                             "peak": np.full((pcm.shape[0],), peak, dtype=np.float32)})
+                return ("pcm", pcm, peak) if pcm.shape[0] else ("skip",)
             except UnsupportedAudio:
                 try:
-                    raw, kind, ch, sr0 = read_wav_frames(path, 60)
+                    return ("frames",) + read_wav_frames(path, 60)
                 except Exception:
-                    skipped += 1
-                    continue
+                    return ("skip",)
+            except Exception:
+                return ("skip",)
+
+        todo = [p for p in files if os.path.basename(os.path.dirname(p)) in class_index]
+        for path, item in zip(todo, prefetch_ordered(read_one, todo, workers=io_workers)):
+            label = os.path.basename(os.path.dirname(path))
+            if item[0] == "skip":
+                skipped += 1
+                continue
+            if item[0] == "pcm":
+                _, pcm, peak = item
+                pend.append({"path": path, "label": label, "kind": "pcm", "n": pcm.shape[0], "pcm": pcm,
+                             "peak": np.full((pcm.shape[0],), peak, dtype=np.float32)})
+            else:
+                _, raw, kind, ch, sr0 = item
                 ws = wave_buffer()
                 n = ws["ingest"].chunks_to_ptr(raw, kind, ch, sr0, sr, ws["T"], ws["step"],
                                                ws["buf"].data_ptr() + 4 * ws["used"] * ws["T"], ws["cap"] - ws["used"])
@@ -232,9 +241,6 @@ def evaluate(model_runner, files: list[str], classes: list[str], cfg: dict, pool
                     continue
                 ws["used"] += n
                 pend.append({"path": path, "label": label, "kind": "wave", "n": n})
-            except Exception:
-                skipped += 1
-                continue
             if sum(f["n"] for f in pend) >= device_batch_chunks:
                 flush()
         flush()

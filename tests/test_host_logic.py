@@ -158,3 +158,36 @@ def test_oracle_has_not_drifted(oracle_model, pcm_batch):
     scores, t96 = oracle_model.run(spec, tap_id=96)
     np.testing.assert_array_equal(t96, g["t96"])
     np.testing.assert_array_equal(scores, g["scores"])
+
+
+def test_prefetch_ordered_keeps_order_and_bounds_lookahead():
+    import threading
+    import time
+
+    from birdnet_stm32.audio.io import prefetch_ordered
+
+    started = []
+    lock = threading.Lock()
+
+    def work(i):
+        with lock:
+            started.append(i)
+        time.sleep(0.002 * ((i * 7) % 5))
+        return i * i
+
+    got = []
+    for k, v in enumerate(prefetch_ordered(work, range(40), workers=4, depth=6)):
+        got.append(v)
+        with lock:
+            assert max(started) <= k + 6, "ran further ahead than `depth`"
+    assert got == [i * i for i in range(40)]
+    assert list(prefetch_ordered(work, range(3), workers=1)) == [0, 1, 4]
+    assert list(prefetch_ordered(work, [], workers=4)) == []
+
+    def boom(i):
+        if i == 2:
+            raise ValueError("x")
+        return i
+
+    with pytest.raises(ValueError):
+        list(prefetch_ordered(boom, range(5), workers=3))
