@@ -23,7 +23,13 @@
  *   LUT-based int8 LOGISTIC, and librosa.stft(center=True, pad_mode="constant").
  * What IS pinned: pooling (reference tests/test_pooling.py known answers and the
  * importable reference evaluation/pooling.py, see tests/golden/), chunk geometry
- * (audio/io.py:133-174) and the per-op float-shadow check in tests/test_oracle_graph.py.
+ * (audio/io.py:133-174), the per-op float-shadow check in tests/test_oracle_graph.py, and --
+ * at network level -- the reference's own conversion gate against its shipped FLOAT checkpoint:
+ * the scores of checkpoints/birdnet_stm32n6_100.keras (read without TensorFlow, oracle/h5min.py +
+ * oracle/keras_float_model.py, golden in tests/golden/keras_float_reference.npz) and the int8
+ * scores of this oracle have cosine similarity 0.994 (gate: >= 0.95, conversion/validate.py:51-105,
+ * cli/convert.py:187-195), tests/test_keras_float_pin.py.  What stays unpinned is the bit level:
+ * rounding tie-breaks of the TFLite kernels (see BN_OPT_ROUNDING / BN_OPT_MEAN_VARIANT).
  *
  * Build: gcc -O2 -fopenmp -shared -fPIC (see oracle/Makefile).  -ffast-math must
  * NOT be used (rounding behaviour is the point).

@@ -1,0 +1,93 @@
+"""Pin of the int8 path against the reference's shipped FLOAT checkpoint, with the reference's own conversion gate.
+
+`tests/golden/keras_float_reference.npz` holds the sigmoid scores of `checkpoints/birdnet_stm32n6_100.keras` (the Keras
+model the shipped `.tflite` was converted from) on the seeded 16-chunk batch, computed from the archive's float weights and
+BatchNorm statistics (`tests/golden/make_golden_keras.py`).  The reference accepts a conversion when the int8 outputs and
+the Keras outputs have mean cosine similarity >= 0.95 (`conversion/validate.py:51-105`, `cli/convert.py:187-195`); the same
+gate is applied here to the CPU oracle and to the CUDA engine.  It is an independent route to the network output (no
+quantisation parameters, no folded weights), so it checks the reading of the `.tflite` -- layouts, padding, per-channel
+axes, residual wiring, the PWL frontend -- that the bit-exact tests take for granted.
+
+The last four chunks of the batch are the synthetic edge cases (silence, full-scale square, impulse, pure sine): far outside
+the training distribution, all scores near zero, where cosine similarity is ill-conditioned (the reference's own rule gives
+0.0 when exactly one side is all-zero).  They are reported but the gate is evaluated on the 12 chirp + noise chunks.
+"""
+
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import CONFIG, GOLDEN
+
+N_GATED = 12
+
+
+def cosine(a, b, eps=1e-8):
+    an, bn = np.linalg.norm(a), np.linalg.norm(b)
+    if an < eps and bn < eps:
+        return 1.0
+    if an < eps or bn < eps:
+        return 0.0
+    return float(np.dot(a, b) / (an * bn))
+
+
+def batch(synth):
+    cfg = json.load(open(CONFIG))
+    T = int(cfg["sample_rate"] * cfg["chunk_duration"])
+    pcm = synth.synth_pcm16(16, T, cfg["sample_rate"], seed=1234, edge_cases=True)
+    return cfg, T, pcm, synth.file_peaks(pcm)
+
+
+def gate(scores, ref):
+    cos = [cosine(ref[i].astype(np.float64), scores[i].astype(np.float64)) for i in range(len(ref))]
+    return cos, float(np.mean(cos[:N_GATED])), float(np.mean(np.abs(scores[:N_GATED] - ref[:N_GATED])))
+
+
+def test_int8_oracle_passes_the_reference_conversion_gate(synth, oracle_model):
+    from oracle import bn_oracle
+
+    ref = np.load(os.path.join(GOLDEN, "keras_float_reference.npz"))
+    cfg, T, pcm, peak = batch(synth)
+    spec = bn_oracle.frontend_hybrid(pcm, peak, cfg["fft_length"], T // cfg["spec_width"], cfg["spec_width"])
+    np.testing.assert_allclose(spec.astype(np.float64).sum(axis=(1, 2, 3)), ref["spec_sum"], rtol=1e-6)   # same inputs as the golden run
+    scores = oracle_model.predict(spec)
+    cos, cos_mean, mae = gate(scores, ref["scores"])
+    print(f"int8 oracle vs Keras float: cosine mean {cos_mean:.4f} (min {min(cos[:N_GATED]):.4f}), MAE {mae:.5f}; edge cases {np.round(cos[N_GATED:], 3)}")
+    assert cos_mean >= 0.95                       # the reference's default --min_cosine_sim
+    assert min(cos[:N_GATED]) >= 0.95
+    assert mae <= 0.01
+    agree = int((scores[:N_GATED].argmax(1) == ref["scores"][:N_GATED].argmax(1)).sum())
+    assert agree >= N_GATED - 2, agree            # top-1 may flip between near-tied classes after quantisation
+
+
+def test_keras_archive_reader_when_reference_is_mounted():
+    """Re-derives the golden scores from the archive itself (build container only; skipped on the GPU box)."""
+    path = "/root/reference/checkpoints/birdnet_stm32n6_100.keras"
+    if not os.path.exists(path):
+        pytest.skip("reference checkout not mounted")
+    from oracle.h5min import read_keras_weights
+
+    cfg, w = read_keras_weights(path)
+    layer_w = {k: v for k, v in w.items() if k.startswith("/layers/")}
+    ref = np.load(os.path.join(GOLDEN, "keras_float_reference.npz"))
+    assert sum(v.size for v in layer_w.values()) == int(ref["n_layer_params"])
+    assert w["/layers/dense/vars/0"].shape == (256, 100) and w["/layers/conv2d/vars/0"].shape == (3, 3, 1, 16)
+    assert len([l for l in cfg["config"]["layers"] if l["class_name"] == "BatchNormalization"]) == 23
+
+
+@pytest.mark.gpu
+def test_gpu_engine_passes_the_reference_conversion_gate(synth, blob):
+    from birdnet_stm32.evaluation.gpu_runner import GpuRunner
+
+    ref = np.load(os.path.join(GOLDEN, "keras_float_reference.npz"))
+    cfg, T, pcm, peak = batch(synth)
+    runner = GpuRunner(blob, cfg)
+    try:
+        scores = runner.predict_pcm16(pcm, peak)          # full CUDA path: STFT frontend + int8 graph
+    finally:
+        runner.close()
+    cos, cos_mean, mae = gate(scores, ref["scores"])
+    print(f"CUDA engine vs Keras float: cosine mean {cos_mean:.4f} (min {min(cos[:N_GATED]):.4f}), MAE {mae:.5f}")
+    assert cos_mean >= 0.95 and min(cos[:N_GATED]) >= 0.95 and mae <= 0.01
