@@ -72,10 +72,16 @@ class KerasFloatModel:
             out = out + kk[None, :, None] * (y * sw[None, :, None] + sb[None, :, None]).clamp_min(0.0)
         return out[:, None, :, :]                                                              # [B, 1, mel, T]
 
-    def predict(self, spec: np.ndarray) -> np.ndarray:
-        """float32 [B, 257, 256, 1] -> sigmoid scores float32 [B, 100]."""
+    def predict(self, spec: np.ndarray, taps: dict | None = None) -> np.ndarray:
+        """float32 [B, 257, 256, 1] -> sigmoid scores float32 [B, 100].  If `taps` is a dict it receives the activations
+        after the frontend ("frontend"), after every ReLU layer (by layer name), after the pooling ("gap") and the
+        pre-sigmoid logits ("logits") as NHWC numpy arrays."""
         import torch
         import torch.nn.functional as F
+
+        def keep(key, t):
+            if taps is not None:
+                taps[key] = (t.permute(0, 2, 3, 1) if t.dim() == 4 else t).numpy().copy()
 
         with torch.no_grad():
             x = None
@@ -87,6 +93,7 @@ class KerasFloatModel:
                     continue
                 if cls == "AudioFrontendLayer":
                     x = self.frontend(spec)
+                    keep("frontend", x)
                 elif cls == "Conv2D":
                     w = torch.from_numpy(self.var(name, 0)).permute(3, 2, 0, 1).contiguous()  # HWIO -> OIHW
                     x = F.conv2d(_same_pad(x, c["kernel_size"], c["strides"]), w, stride=tuple(c["strides"]))
@@ -100,12 +107,15 @@ class KerasFloatModel:
                     x = x * scale[None, :, None, None] + (b - m * scale)[None, :, None, None]
                 elif cls == "ReLU":
                     x = x.clamp(0.0, float(c["max_value"])) if c.get("max_value") is not None else x.clamp_min(0.0)
+                    keep(name, x)
                 elif cls == "Add":
                     x = x + block_in
                 elif cls == "GlobalAveragePooling2D":
                     x = x.mean(dim=(2, 3))
+                    keep("gap", x)
                 elif cls == "Dense":
                     x = x @ torch.from_numpy(self.var(name, 0)) + torch.from_numpy(self.var(name, 1))
+                    keep("logits", x)
                     if c.get("activation") == "sigmoid":
                         x = torch.sigmoid(x)
                 else:

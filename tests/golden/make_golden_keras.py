@@ -30,10 +30,24 @@ def main():
     peak = synth.file_peaks(pcm)
     spec = bn_oracle.frontend_hybrid(pcm, peak, cfg["fft_length"], T // cfg["spec_width"], cfg["spec_width"])
     km = KerasFloatModel("/root/reference/checkpoints/birdnet_stm32n6_100.keras")
-    scores = km.predict(spec)
+    taps: dict = {}
+    scores = km.predict(spec, taps)
     n_params = int(sum(v.size for k, v in km.w.items() if k.startswith("/layers/")))
-    np.savez_compressed(os.path.join(HERE, "keras_float_reference.npz"), scores=scores, n_layer_params=np.int64(n_params),
-                        spec_sum=spec.astype(np.float64).sum(axis=(1, 2, 3)))
+    out = dict(scores=scores, n_layer_params=np.int64(n_params), spec_sum=spec.astype(np.float64).sum(axis=(1, 2, 3)))
+    # layer-by-layer pin: per-chunk activation profiles of the float model along each axis (mean over the other two) for
+    # the first 12 chunks -- small, but a channel permutation, a transposed map or a shifted padding changes them
+    names = list(taps)
+    out["tap_names"] = np.array(names)
+    for i, k in enumerate(names):
+        a = taps[k][:12].astype(np.float64)
+        if a.ndim == 4:
+            out[f"tap{i}_c"] = a.mean(axis=(1, 2)).astype(np.float32)
+            out[f"tap{i}_h"] = a.mean(axis=(2, 3)).astype(np.float32)
+            out[f"tap{i}_w"] = a.mean(axis=(1, 3)).astype(np.float32)
+        else:
+            out[f"tap{i}_c"] = a.astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, "keras_float_reference.npz"), **out)
+    print("taps", len(names), names[:4], "...")
     print("scores", scores.shape, "layer parameters", n_params, "top-1", scores.argmax(1).tolist())
 
 

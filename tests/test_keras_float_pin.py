@@ -91,3 +91,45 @@ def test_gpu_engine_passes_the_reference_conversion_gate(synth, blob):
     cos, cos_mean, mae = gate(scores, ref["scores"])
     print(f"CUDA engine vs Keras float: cosine mean {cos_mean:.4f} (min {min(cos[:N_GATED]):.4f}), MAE {mae:.5f}")
     assert cos_mean >= 0.95 and min(cos[:N_GATED]) >= 0.95 and mae <= 0.01
+
+
+def test_int8_layers_track_the_float_checkpoint_layer_by_layer(synth, oracle_model, graph):
+    """Every post-activation tensor of the int8 graph, dequantised, against the float model's activation at the same
+    layer: per-chunk profiles along channels, rows and columns (mean over the other two axes).  Correlation >= 0.97 and
+    relative L2 error <= 0.25 per layer (quantisation noise accumulates with depth; a permuted channel axis, a
+    transposed map or a wrong padding side gives correlations near zero)."""
+    from oracle import bn_oracle
+
+    ref = np.load(os.path.join(GOLDEN, "keras_float_reference.npz"))
+    names = [str(n) for n in ref["tap_names"]]
+    cfg, T, pcm, peak = batch(synth)
+    spec = bn_oracle.frontend_hybrid(pcm[:N_GATED], peak[:N_GATED], cfg["fft_length"], T // cfg["spec_width"], cfg["spec_width"])
+    # tflite tensors in the order of the float taps: frontend output = input of the stem conv; then every op with a fused
+    # activation from the stem on (CONV_2D / DEPTHWISE_CONV_2D with RELU6, residual ADD with RELU6); MEAN; FULLY_CONNECTED
+    stem = next(op for op in graph.ops if op.kind == "CONV_2D" and op.options.get("stride_w") == 2)
+    tids = [stem.inputs[0]]
+    tids += [op.outputs[0] for op in graph.ops if op.index >= stem.index and op.kind in ("CONV_2D", "DEPTHWISE_CONV_2D", "ADD")
+             and op.options.get("act", "NONE") != "NONE"]
+    tids += [next(op.outputs[0] for op in graph.ops if op.kind == "MEAN"), next(op.outputs[0] for op in graph.ops if op.kind == "FULLY_CONNECTED")]
+    assert len(tids) == len(names) == 26
+    worst_corr, worst_rel = 1.0, 0.0
+    for i, (name, tid) in enumerate(zip(names, tids)):
+        t = graph.tensors[tid]
+        _, tap = oracle_model.run(spec, tap_id=tid)
+        q = tap.reshape((spec.shape[0],) + tuple(t.shape[1:])).astype(np.float64)
+        x = (q - float(t.zero_point[0])) * float(t.scale[0])
+        if x.ndim == 4 and name == "frontend":
+            pass                                       # [B, 64 mel, 256, 1] in both graphs
+        profiles = [("c", x.mean(axis=(1, 2)) if x.ndim == 4 else x)]
+        if x.ndim == 4:
+            profiles += [("h", x.mean(axis=(2, 3))), ("w", x.mean(axis=(1, 3)))]
+        for ax, got in profiles:
+            want = ref[f"tap{i}_{ax}"].astype(np.float64)
+            assert got.shape == want.shape, (name, ax, got.shape, want.shape)
+            if want.shape[1] < 3 or np.std(want) < 1e-9:
+                continue
+            corr = float(np.corrcoef(got.reshape(-1), want.reshape(-1))[0, 1])
+            rel = float(np.linalg.norm(got - want) / (np.linalg.norm(want) + 1e-12))
+            worst_corr, worst_rel = min(worst_corr, corr), max(worst_rel, rel)
+            assert corr >= 0.97 and rel <= 0.25, (name, ax, corr, rel)
+    print(f"26 layers vs float checkpoint: worst profile correlation {worst_corr:.4f}, worst relative L2 error {worst_rel:.3f}")
