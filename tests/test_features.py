@@ -167,3 +167,30 @@ def test_gpu_features_device_pointers_and_batches(synth):
     fx.close()
     assert np.array_equal(do.cpu().numpy(), host)
     assert np.array_equal(host[:10], host[290:300])
+
+
+def test_oracle_agrees_with_torchaudio_independent_implementation():
+    """librosa is not installable here, but torch / torchaudio ship their own implementations of the same published
+    conventions: Slaney mel filterbank with area normalisation (`melscale_fbanks(norm="slaney", mel_scale="slaney")`,
+    which torchaudio tests against librosa.filters.mel) and a centred STFT with a periodic Hann window and constant
+    padding (`torch.stft`).  The oracle's restatement of `librosa.filters.mel` / `librosa.stft`
+    (`audio/spectrogram.py:106-130`) must agree with them: an independent cross-check of the librosa boundary."""
+    torch = pytest.importorskip("torch")
+    AF = pytest.importorskip("torchaudio.functional")
+    from oracle import bn_features_oracle as FO
+
+    from birdnet_stm32.audio.mel import mel_filterbank
+
+    for sr in (22050, 24000, 16000):
+        ta = AF.melscale_fbanks(257, 150.0, float(sr // 2), 64, sr, norm="slaney", mel_scale="slaney").numpy().T
+        assert np.abs(FO.mel_basis(sr, 512, 64, 150.0, sr // 2) - ta).max() <= 2e-7
+        assert np.abs(mel_filterbank(sr, 512, 64, 150.0, sr // 2) - ta).max() <= 2e-7       # the table the CUDA kernel receives
+    rng = np.random.default_rng(0)
+    for T in (66150, 72000):
+        y = (rng.standard_normal(T) * 0.1).astype(np.float32)
+        hop = T // 256
+        m = FO.stft_mag(y, 512, hop)
+        Y = torch.stft(torch.from_numpy(y), n_fft=512, hop_length=hop, win_length=512, window=torch.hann_window(512, periodic=True),
+                       center=True, pad_mode="constant", return_complex=True).abs().numpy()
+        assert m.shape[0] == 257 and m.shape[1] <= Y.shape[1]
+        assert np.abs(m - Y[:, : m.shape[1]]).max() <= 1e-5 * np.abs(Y).max()
