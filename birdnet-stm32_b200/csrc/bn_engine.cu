@@ -54,7 +54,10 @@ struct bn_engine {
   const bn_blob_op* ops = nullptr;
   // workspace
   int wave = 0;                       // chunks the workspace is sized for
-  int wave_opt = 2368;                 // requested wave size (8 x 296 resident CTAs: whole tile rounds in every kernel)
+  int wave_opt = 23680;                // requested wave size = 80 x 296 resident CTAs (whole tile rounds in every kernel).  Measured on
+                                       // 21.7 k chunks: wave 2368 -> 4736 -> 9472 -> whole job: 1.222 -> 1.260 -> 1.274 -> 1.291 M chunks/s
+                                       // (fewer launches and ragged tails); the workspace is allocated for min(B, wave) chunks, about
+                                       // 0.9 MB per chunk, i.e. up to 21 GB of the 180 GB when a call brings that many chunks
   int host_wave = 592;                 // wave size when the input lives in host memory: the upload of wave i+1 hides under the
                                        // compute of wave i, so the exposed part of a call is one wave's upload plus one wave's
                                        // compute -- small waves keep a PCIe-bound call close to the link rate (BN_OPT_HOST_WAVE)

@@ -65,10 +65,10 @@ Profiler::~Profiler() { for (auto e : pool) cudaEventDestroy(e); for (auto& p : 
 // scripts/g18.sh / g19.sh): keeping this scratch inside the 126 MB L2 (256 chunks = 69 MB) is NOT what matters -- HBM has
 // bandwidth to spare at this arithmetic intensity -- while every extra launch pair costs a ramp-up (110 registers of
 // window / twiddle tables per thread) and a ragged tail: 256 -> 4.92 + 2.67 ms per 21.7 k chunks, 444 -> 4.51 + 2.48,
-// 888 -> 4.27 + 2.18, whole wave (2368) -> 4.09 + 1.97.  So the default is the whole wave, in multiples of 2 x 148 CTAs.
+// 888 -> 4.27 + 2.18, whole wave (2368) -> 4.09 + 1.97.  So the default is the whole wave (BN_OPT_WAVE, a multiple of 2 x 148 CTAs).
 static int fe_subwave() {
   static int v = 0;
-  if (!v) { const char* e = getenv("BN_FE_SUBWAVE"); v = e ? atoi(e) : 2368; if (v < 1) v = 2368; }
+  if (!v) { const char* e = getenv("BN_FE_SUBWAVE"); v = e ? atoi(e) : (1 << 30); if (v < 1) v = 1 << 30; }   // default: the whole wave
   return v;
 }
 #define FE_SUBWAVE (fe_subwave())

@@ -1,5 +1,5 @@
 cd /root/repo
-for cfg in "1184 2368" "2368 2368" "1184 3552" "1776 3552"; do
+for cfg in "4736 4736" "3552 3552" "2368 2368"; do
   set -- $cfg
   echo "== subwave $1 wave $2"
   env BN_FE_SUBWAVE=$1 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu --wave $2 > gpurun_out/bq.json 2> gpurun_out/bq.err; tail -2 gpurun_out/bq.err
