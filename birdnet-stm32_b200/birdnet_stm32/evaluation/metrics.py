@@ -297,3 +297,110 @@ def evaluate(model_runner, files: list[str], classes: list[str], cfg: dict, pool
     if skipped:
         metrics["skipped_files"] = skipped
     return metrics, per_file, y_true_arr, y_scores_arr
+
+
+# ---------------------------------------------------------------------------------------------------------
+# consumers of evaluate()'s (y_true, y_scores): threshold tuning, bootstrap intervals, DET curve
+# (reference `evaluation/metrics.py:210-372`; same results, sort-once formulations instead of per-threshold /
+# per-resample rescans so that they stay usable on the 100k-file evaluations the GPU path makes routine)
+# ---------------------------------------------------------------------------------------------------------
+def optimize_thresholds(y_true: np.ndarray, y_scores: np.ndarray, classes: list[str]) -> dict[str, float]:
+    """Per-class threshold maximising F1 on the precision-recall curve (reference `metrics.py:210-237`)."""
+    from sklearn.metrics import precision_recall_curve
+
+    optimal: dict[str, float] = {}
+    for ci, name in enumerate(classes):
+        col_true, col_scores = y_true[:, ci], y_scores[:, ci]
+        if col_true.sum() == 0:
+            optimal[name] = 0.5
+            continue
+        prec, rec, thresholds = precision_recall_curve(col_true, col_scores)
+        f1 = 2 * prec[:-1] * rec[:-1] / (prec[:-1] + rec[:-1] + 1e-12)
+        optimal[name] = float(thresholds[int(np.argmax(f1))])
+    return optimal
+
+
+def _weighted_ap_sorted(labels_sorted: np.ndarray, group_end: np.ndarray, weights: np.ndarray) -> np.ndarray:
+    """Average precision of resamples given as per-sample multiplicities.
+
+    labels_sorted: [n] 0/1 in descending-score order; group_end: indices of the last element of every run of equal
+    scores; weights: [R, n] multiplicities in the same order.  Equals sklearn's average_precision_score on the
+    materialised resample: thresholds are the distinct scores, AP = sum (R_k - R_{k-1}) P_k."""
+    w = weights.astype(np.float64)
+    tp = np.cumsum(w * labels_sorted[None, :], axis=1)[:, group_end]
+    cnt = np.cumsum(w, axis=1)[:, group_end]
+    P = tp[:, -1:]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        prec = np.where(cnt > 0, tp / cnt, 0.0)
+        rec = tp / P
+    drec = np.diff(np.concatenate([np.zeros((w.shape[0], 1)), rec], axis=1), axis=1)
+    return np.sum(drec * prec, axis=1)
+
+
+def bootstrap_ap_ci(y_true: np.ndarray, y_scores: np.ndarray, classes: list[str], n_bootstrap: int = 1000,
+                    confidence: float = 0.95, seed: int = 42) -> list[dict]:
+    """Per-class AP with bootstrap confidence intervals (reference `metrics.py:240-322`).
+
+    Same random stream as the reference (`default_rng(seed)`, one `integers(0, n, size=n)` draw per resample, classes in
+    order, degenerate classes skipped before drawing), same skipping of single-class resamples and the same percentiles.
+    Each class is sorted once; a resample is a vector of multiplicities, so its AP costs two cumulative sums instead of a
+    sort inside scikit-learn."""
+    from sklearn.metrics import average_precision_score
+
+    rng = np.random.default_rng(seed)
+    n = y_true.shape[0]
+    alpha = (1 - confidence) / 2
+    results: list[dict] = []
+    for ci, name in enumerate(classes):
+        col_true, col_scores = y_true[:, ci], y_scores[:, ci]
+        n_pos = int(col_true.sum())
+        try:
+            ap = float(average_precision_score(col_true, col_scores))
+        except Exception:
+            ap = float("nan")
+        if n_pos == 0 or n_pos == n:
+            results.append({"class": name, "ap": ap, "ci_lower": ap, "ci_upper": ap, "n_positive": n_pos, "n_total": n})
+            continue
+        order = np.argsort(-col_scores, kind="stable")
+        s_sorted = col_scores[order]
+        lab_sorted = (col_true[order] != 0).astype(np.float64)
+        group_end = np.flatnonzero(np.r_[s_sorted[1:] != s_sorted[:-1], True])
+        inv = np.empty(n, dtype=np.int64)
+        inv[order] = np.arange(n)                       # original index -> position in sorted order
+        boot: list[float] = []
+        block = max(1, min(n_bootstrap, (1 << 22) // max(n, 1)))
+        for b0 in range(0, n_bootstrap, block):
+            nb = min(block, n_bootstrap - b0)
+            weights = np.zeros((nb, n), dtype=np.int32)
+            for r in range(nb):
+                idx = rng.integers(0, n, size=n)
+                weights[r] = np.bincount(inv[idx], minlength=n)
+            pos = weights @ lab_sorted
+            keep = (pos > 0) & (pos < n)
+            if keep.any():
+                boot.extend(_weighted_ap_sorted(lab_sorted, group_end, weights[keep]).tolist())
+        if boot:
+            lo, hi = float(np.percentile(boot, 100 * alpha)), float(np.percentile(boot, 100 * (1 - alpha)))
+        else:
+            lo = hi = ap
+        results.append({"class": name, "ap": ap, "ci_lower": lo, "ci_upper": hi, "n_positive": n_pos, "n_total": n})
+    return results
+
+
+def compute_det_curve(y_true: np.ndarray, y_scores: np.ndarray) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """DET curve points (far, frr, thresholds), one per distinct score in descending order (reference `metrics.py:325-372`)."""
+    y_t = np.asarray(y_true).ravel()
+    y_s = np.asarray(y_scores).ravel()
+    total_pos = float(y_t.sum())
+    total_neg = float(len(y_t) - total_pos)
+    if total_pos == 0 or total_neg == 0:
+        return np.array([0.0]), np.array([0.0]), np.array([0.5])
+    order = np.argsort(-y_s, kind="stable")
+    s_sorted = y_s[order]
+    end = np.flatnonzero(np.r_[s_sorted[1:] != s_sorted[:-1], True])    # last index of each run: "score >= threshold"
+    tp = np.cumsum(y_t[order].astype(np.float64))[end]
+    fp = (end + 1).astype(np.float64) - tp
+    out_dt = y_t.dtype if np.issubdtype(y_t.dtype, np.floating) else np.float64
+    far = (fp / total_neg).astype(out_dt)
+    frr = ((total_pos - tp) / total_pos).astype(out_dt)
+    return far, frr, s_sorted[end].astype(np.float64)

@@ -232,3 +232,62 @@ def test_gpu_evaluate_mixed_rates_and_formats(tmp_path, blob, cfg, oracle_model)
         np.testing.assert_allclose(ys2, y_scores, rtol=0, atol=3e-6)
     finally:
         runner.close()
+
+
+def _ref_bootstrap(y_true, y_scores, classes, n_bootstrap, confidence, seed):
+    """The reference's formulation (`metrics.py:240-322`): materialise every resample and call scikit-learn on it."""
+    from sklearn.metrics import average_precision_score
+
+    rng = np.random.default_rng(seed)
+    n = y_true.shape[0]
+    alpha = (1 - confidence) / 2
+    out = []
+    for ci, name in enumerate(classes):
+        ct, cs = y_true[:, ci], y_scores[:, ci]
+        n_pos = int(ct.sum())
+        ap = float(average_precision_score(ct, cs))
+        if n_pos == 0 or n_pos == n:
+            out.append((ap, ap, ap))
+            continue
+        boot = []
+        for _ in range(n_bootstrap):
+            idx = rng.integers(0, n, size=n)
+            bt, bs = ct[idx], cs[idx]
+            if bt.sum() == 0 or bt.sum() == len(bt):
+                continue
+            boot.append(float(average_precision_score(bt, bs)))
+        out.append((ap, float(np.percentile(boot, 100 * alpha)), float(np.percentile(boot, 100 * (1 - alpha)))) if boot else (ap, ap, ap))
+    return out
+
+
+def test_metric_consumers_match_the_reference_formulations():
+    import warnings
+
+    from birdnet_stm32.evaluation.metrics import bootstrap_ap_ci, compute_det_curve, optimize_thresholds
+
+    rng = np.random.default_rng(4)
+    n, C = 90, 5
+    y_true = np.zeros((n, C), dtype=np.float32)
+    y_true[np.arange(n), rng.integers(0, 3, size=n)] = 1.0            # classes 3 and 4 have no positives
+    y_true[:5, 1] = 1.0
+    y_scores = (np.round(rng.random((n, C)) * 32) / 32).astype(np.float32)   # ties
+    classes = [f"c{i}" for i in range(C)]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got = bootstrap_ap_ci(y_true, y_scores, classes, n_bootstrap=60, confidence=0.9, seed=7)
+        want = _ref_bootstrap(y_true, y_scores, classes, 60, 0.9, 7)
+    for g, w in zip(got, want):
+        assert abs(g["ap"] - w[0]) <= 1e-12 and abs(g["ci_lower"] - w[1]) <= 1e-12 and abs(g["ci_upper"] - w[2]) <= 1e-12, (g, w)
+    assert got[3]["n_positive"] == 0 and got[3]["ci_lower"] == got[3]["ap"]
+    # DET curve: the reference's per-threshold rescan
+    far, frr, thr = compute_det_curve(y_true, y_scores)
+    y_t, y_s = y_true.ravel(), y_scores.ravel()
+    uniq = np.unique(y_s)[::-1]
+    P, N = y_t.sum(), len(y_t) - y_t.sum()
+    np.testing.assert_array_equal(thr, uniq.astype(np.float64))
+    for k in (0, len(uniq) // 2, len(uniq) - 1):
+        pred = y_s >= uniq[k]
+        assert far[k] == np.sum(1 - y_t[pred]) / N and frr[k] == (P - np.sum(y_t[pred])) / P
+    assert compute_det_curve(np.zeros(4), np.ones(4))[2].tolist() == [0.5]
+    th = optimize_thresholds(y_true, y_scores, classes)
+    assert th["c3"] == 0.5 and 0.0 <= th["c0"] <= 1.0 and set(th) == set(classes)
