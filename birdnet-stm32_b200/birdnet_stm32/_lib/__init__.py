@@ -26,6 +26,8 @@ EXPORTS = (
     "bn_ingest_window", "bn_ingest_chunks", "bn_ingest_launch_count",
     # include/bn_metrics.h
     "bn_metrics_compute",
+    # include/bn_reader.h
+    "bn_wav_probe", "bn_read_pcm16_batch",
 )
 
 BN_SAMPLE_FORMAT = {"s16": 0, "s24": 1, "s32": 2, "f32": 3, "u8": 4}
@@ -62,6 +64,15 @@ class BnMetricsResult(C.Structure):
         ("roc_auc_micro", C.c_double), ("map_micro", C.c_double), ("cmap", C.c_double), ("precision", C.c_double),
         ("recall", C.c_double), ("f1", C.c_double), ("n_positive", C.c_int64), ("n_cells", C.c_int64),
         ("classes_without_positives", C.c_int32), ("n_launches", C.c_int32), ("reserved", C.c_int32 * 4),
+    ]
+
+
+class BnReaderFile(C.Structure):
+    """`bn_reader_file` of include/bn_reader.h"""
+
+    _fields_ = [
+        ("status", C.c_int32), ("n_chunks", C.c_int32), ("sample_rate", C.c_int32), ("channels", C.c_int32), ("fmt", C.c_int32),
+        ("peak", C.c_float), ("n_frames", C.c_int64), ("data_offset", C.c_int64),
     ]
 
 
@@ -133,6 +144,9 @@ def load():
     L.bn_ingest_launch_count.argtypes = [vp]
     L.bn_ingest_launch_count.restype = i64
     L.bn_metrics_compute.argtypes = [vp, vp, i32, i32, i32, C.POINTER(BnMetricsResult), vp]
+    L.bn_wav_probe.argtypes = [C.c_char_p, C.c_double, C.POINTER(BnReaderFile)]
+    L.bn_read_pcm16_batch.argtypes = [C.POINTER(C.c_char_p), i32, i32, i32, i32, C.c_double, vp, i32, i32, C.POINTER(BnReaderFile),
+                                      C.POINTER(i32)]
     _lib = L
     return L
 

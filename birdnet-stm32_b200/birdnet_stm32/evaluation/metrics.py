@@ -120,12 +120,15 @@ def _metrics_from_scores(y_true_arr: np.ndarray, y_scores_arr: np.ndarray) -> di
 def evaluate(model_runner, files: list[str], classes: list[str], cfg: dict, pooling: str = "average",
              batch_size: int = 64, overlap: float = 0.0, mep_beta: float = 10.0, measure_latency: bool = False,
              profile_memory: bool = False, device_batch_chunks: int = 4096,
-             frontend_runner=None, metrics_backend: str = "sklearn", io_workers: int = 8) -> tuple[dict, list[dict], np.ndarray, np.ndarray]:
+             frontend_runner=None, metrics_backend: str = "sklearn", io_workers: int = 8,
+             native_reader: bool = True) -> tuple[dict, list[dict], np.ndarray, np.ndarray]:
     """Run inference per chunk, pool to file level and compute metrics (see module docstring).
 
     metrics_backend: "sklearn" (the reference's own calls, host) or "device" (`evaluation/device_metrics.py`: the same
     definitions evaluated by `bn_metrics_compute` on the GPU -- for evaluations with millions of (file, class) cells).
-    io_workers: reader threads of the device path (files are read and cut into chunks ahead of the GPU calls, in order)."""
+    io_workers: reader threads of the device path (files are read and cut into chunks ahead of the GPU calls, in order).
+    native_reader: device path only -- read the files with the C++ thread pool of `bn_read_pcm16_batch` straight into
+    pinned batch buffers (double-buffered against the GPU calls) instead of the Python reader threads."""
     if metrics_backend not in ("sklearn", "device"):
         raise ValueError(f"Unsupported metrics backend: {metrics_backend}")
     frontend = normalize_frontend_name(cfg["audio_frontend"])
@@ -222,6 +225,89 @@ def evaluate(model_runner, files: list[str], classes: list[str], cfg: dict, pool
                 return ("skip",)
 
         todo = [p for p in files if os.path.basename(os.path.dirname(p)) in class_index]
+        if native_reader and todo:
+            # ---- native reader: batches of files -> pinned int16 chunk buffers, read of batch k + 1 under the GPU call of k ----
+            from concurrent.futures import ThreadPoolExecutor
+
+            from birdnet_stm32 import _lib as _L
+            from birdnet_stm32.audio import reader as _rd
+            from birdnet_stm32.audio.ingest import chunk_step as _chunk_step
+
+            T, step = _chunk_step(sr, cd, overlap)
+            cap = int(device_batch_chunks) + int(60 * sr / step) + 4
+            stage = []
+            for _ in range(2):
+                try:
+                    from birdnet_stm32.evaluation.gpu_runner import PinnedArray
+
+                    pa = PinnedArray((cap, T), np.int16)
+                    stage.append((pa, pa.array))
+                except Exception:                      # no CUDA runtime (stub runners in the CPU tests): ordinary memory
+                    stage.append((None, np.empty((cap, T), dtype=np.int16)))
+            window = 2048                              # paths offered to one reader call
+
+            def read_batch(start: int, slot: int):
+                paths = todo[start:start + window]
+                n_files, used, info = _rd.read_pcm16_batch(paths, sr, T, step, stage[slot][1], max_seconds=60, threads=max(1, io_workers))
+                return start, n_files, used, info
+
+            with ThreadPoolExecutor(max_workers=1, thread_name_prefix="bn-read") as pool:
+                fut = pool.submit(read_batch, 0, 0)
+                slot = 0
+                while fut is not None:
+                    start, n_files, used, info = fut.result()
+                    if n_files == 0:
+                        raise RuntimeError(f"{todo[start]}: more chunks than the batch buffer holds ({cap})")
+                    nxt = start + n_files
+                    fut = pool.submit(read_batch, nxt, slot ^ 1) if nxt < len(todo) else None
+                    buf = stage[slot][1]
+                    rows: dict[int, np.ndarray] = {}
+                    t0 = time.perf_counter()
+                    ok = [i for i in range(n_files) if info[i].status == _rd.RD_OK]
+                    if ok:
+                        counts = np.array([info[i].n_chunks for i in ok], dtype=np.int64)
+                        offs = np.zeros(len(ok) + 1, dtype=np.int32)
+                        offs[1:] = np.cumsum(counts)
+                        peak = np.repeat(np.array([info[i].peak for i in ok], dtype=np.float32), counts)
+                        pooled = model_runner.predict_pooled(buf[:used], peak, offs, pooling=pooling, beta=mep_beta)
+                        rows.update(zip(ok, pooled))
+                    n_batch = used
+                    for i in range(n_files):
+                        if info[i].status != _rd.RD_NEEDS_INGEST:
+                            continue
+                        try:
+                            raw, kind, ch, sr0 = read_wav_frames(todo[start + i], 60)
+                        except Exception:
+                            continue
+                        ws = wave_buffer()
+                        n = ws["ingest"].chunks_to_ptr(raw, kind, ch, sr0, sr, ws["T"], ws["step"], ws["buf"].data_ptr(), ws["cap"])
+                        if n == 0:
+                            continue
+                        torch = ws["torch"]
+                        d_offs = torch.tensor([0, n], dtype=torch.int32, device=ws["dev"])
+                        d_out = torch.empty((1, num_classes), dtype=torch.float32, device=ws["dev"])
+                        torch.cuda.synchronize(ws["dev"])
+                        model_runner.infer_pool_wave_ptr(ws["buf"].data_ptr(), None, d_offs.data_ptr(), 1, pooling, mep_beta, d_out.data_ptr(), None)
+                        rows[i] = d_out.cpu().numpy()[0]
+                        n_batch += n
+                    if measure_latency and n_batch:
+                        per = (time.perf_counter() - t0) * 1000 / n_batch
+                        latencies_ms.extend([per] * n_batch)
+                    total_chunks += n_batch
+                    for i in range(n_files):
+                        path = todo[start + i]
+                        if i not in rows:
+                            skipped += 1
+                            continue
+                        label = os.path.basename(os.path.dirname(path))
+                        y_true.append(target_for(label))
+                        y_scores.append(rows[i])
+                        per_file.append({"file": path, "label": label, "scores": rows[i].tolist()})
+                    slot ^= 1
+            for pa, _ in stage:
+                if pa is not None:
+                    pa.free()
+            todo = []
         for path, item in zip(todo, prefetch_ordered(read_one, todo, workers=io_workers)):
             label = os.path.basename(os.path.dirname(path))
             if item[0] == "skip":

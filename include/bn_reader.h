@@ -1,0 +1,53 @@
+/* bn_reader.h -- C ABI of the native file reader (libbn_b200.so, host code only), SURVEY section 8 row f1.
+ *
+ *   reference interface                                              replaced by
+ *   ------------------------------------------------------------   ---------------------------------------------
+ *   sf.info + sf.SoundFile.read per file, serial                      bn_read_pcm16_batch: RIFF/WAVE headers and sample
+ *     birdnet_stm32/audio/io.py:90-116                                 data of many files read by a pool of native threads
+ *   peak = max|y| (file window)              audio/io.py:122           max|s| / 32768 per file (exact: float32 division by 2^15)
+ *   split_audio_into_chunks                  audio/io.py:133-174       chunks written straight into the caller's (pinned)
+ *   per-file list building in evaluate()     metrics.py:117-147        batch buffer in file order
+ *
+ * Scope: mono 16-bit PCM files at the model rate are turned into int16 chunks ready for bn_infer_pool; every other WAV
+ * (other rate, several channels, 8 / 24 / 32-bit, float) is reported with status BN_RD_NEEDS_INGEST so that the caller
+ * sends it through bn_ingest_chunks; anything else is BN_RD_UNREADABLE (the reference skips such files, metrics.py:125-126).
+ */
+#ifndef BN_READER_H
+#define BN_READER_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "bn_engine.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { BN_RD_OK = 0, BN_RD_NEEDS_INGEST = 1, BN_RD_UNREADABLE = 2 };
+
+typedef struct bn_reader_file {
+  int32_t status;       /* BN_RD_* */
+  int32_t n_chunks;     /* chunks written for this file (0 unless BN_RD_OK) */
+  int32_t sample_rate;  /* from the header (0 if unreadable) */
+  int32_t channels;
+  int32_t fmt;          /* BN_SF_* of bn_ingest.h, -1 if not a supported sample format */
+  float peak;           /* max|s| / 32768 over the window read (BN_RD_OK) */
+  int64_t n_frames;     /* frames in the window: min(frames in file, int(max_seconds * sample_rate)) */
+  int64_t data_offset;  /* byte offset of the sample data in the file */
+} bn_reader_file;
+
+/* Header of one file. */
+BN_API int bn_wav_probe(const char* path, double max_seconds, bn_reader_file* out);
+
+/* Reads paths[0 ..] in order into `chunks` (int16 [cap_chunks, chunk_len], host memory, ideally from bn_host_alloc) until
+ * the next BN_RD_OK file would not fit; chunk geometry as split_audio_into_chunks with step = int(sr * (duration - overlap)).
+ * files_out[i] is filled for every consumed file; *chunks_used = chunks written.  Returns the number of files consumed
+ * (0 .. n_paths; 0 with n_paths > 0 means the first file alone exceeds cap_chunks) or a negative bn_status. */
+BN_API int bn_read_pcm16_batch(const char* const* paths, int n_paths, int sample_rate, int chunk_len, int step, double max_seconds,
+                               int16_t* chunks, int cap_chunks, int threads, bn_reader_file* files_out, int* chunks_used);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BN_READER_H */

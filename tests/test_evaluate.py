@@ -291,3 +291,36 @@ def test_metric_consumers_match_the_reference_formulations():
     assert compute_det_curve(np.zeros(4), np.ones(4))[2].tolist() == [0.5]
     th = optimize_thresholds(y_true, y_scores, classes)
     assert th["c3"] == 0.5 and 0.0 <= th["c0"] <= 1.0 and set(th) == set(classes)
+
+
+def test_native_reader_path_equals_python_reader_path(tmp_path):
+    """evaluate()'s device path with the C++ batch reader vs the Python reader threads, through a stub runner whose
+    pooled scores are a checksum of the chunks it is handed: same files, same chunks, same order, same results."""
+    import warnings
+
+    from birdnet_stm32.evaluation.metrics import evaluate
+
+    classes = ["bird_a", "bird_b", "bird_c"]
+    files = make_dataset(str(tmp_path), classes, n_per_class=4, sr=22050, seconds=(3.0, 7.4, 1.2, 6.0))
+    (tmp_path / "bird_a" / "broken.wav").write_bytes(b"RIFFxxxxWAVEnope")
+    files.insert(3, str(tmp_path / "bird_a" / "broken.wav"))
+
+    class Stub:
+        device = 0
+
+        def predict_pooled(self, pcm, peak, offs, pooling="avg", beta=10.0):
+            out = np.zeros((len(offs) - 1, len(classes)), dtype=np.float32)
+            for f in range(len(offs) - 1):
+                seg = pcm[offs[f]:offs[f + 1]].astype(np.float64)
+                out[f] = [abs(seg.sum()) % 97 / 97.0, (np.abs(seg).sum() % 89) / 89.0, float(peak[offs[f]])]
+            return out
+
+    cfg = dict(RAW_CFG, audio_frontend="hybrid")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = evaluate(Stub(), files, classes, cfg, pooling="avg", device_batch_chunks=5, native_reader=True, io_workers=3)
+        b = evaluate(Stub(), files, classes, cfg, pooling="avg", device_batch_chunks=5, native_reader=False, io_workers=3)
+    assert [f["file"] for f in a[1]] == [f["file"] for f in b[1]] and len(a[1]) == 12
+    np.testing.assert_array_equal(a[3], b[3])
+    np.testing.assert_array_equal(a[2], b[2])
+    assert a[0]["skipped_files"] == b[0]["skipped_files"] == 1

@@ -121,7 +121,7 @@ def test_c_abi_library_loads_and_exports_every_declared_symbol():
     from birdnet_stm32 import _lib as L
 
     lib = L.load()
-    header = "".join(open(os.path.join(ROOT, "include", h)).read() for h in ("bn_engine.h", "bn_features.h", "bn_ingest.h", "bn_metrics.h"))
+    header = "".join(open(os.path.join(ROOT, "include", h)).read() for h in ("bn_engine.h", "bn_features.h", "bn_ingest.h", "bn_metrics.h", "bn_reader.h"))
     declared = set(re.findall(r"BN_API\s+[\w\s\*]+?\b(bn_\w+)\s*\(", header))
     assert declared == set(L.EXPORTS), declared ^ set(L.EXPORTS)
     for name in declared:
@@ -191,3 +191,55 @@ def test_prefetch_ordered_keeps_order_and_bounds_lookahead():
 
     with pytest.raises(ValueError):
         list(prefetch_ordered(boom, range(5), workers=3))
+
+
+def test_native_batch_reader_matches_python_loader(tmp_path):
+    """bn_read_pcm16_batch (C++ threads) against the Python loader that is itself pinned on the reference's chunk geometry:
+    identical chunks, peaks and statuses for exact multiples, tails, short files, overlap, foreign formats, junk."""
+    from test_ingest import write_wav
+
+    from birdnet_stm32.audio import io, reader
+    from birdnet_stm32.audio.ingest import chunk_step
+
+    sr = 8000
+    rng = np.random.default_rng(5)
+    paths, kinds = [], []
+    for i, secs in enumerate((3.0, 6.0, 7.37, 0.4, 9.0, 2.999875, 12.5, 61.0)):
+        p = str(tmp_path / f"a{i}.wav")
+        io.save_wav((rng.standard_normal(int(sr * secs)) * 9000).clip(-32768, 32767).astype(np.int16), p, sr)
+        paths.append(p); kinds.append("ok")
+    p = str(tmp_path / "stereo.wav"); write_wav(p, rng.integers(-3000, 3000, 2 * 4000).astype("<i2"), "s16", 2, sr); paths.insert(2, p); kinds.insert(2, "ingest")
+    p = str(tmp_path / "rate.wav"); write_wav(p, rng.integers(-3000, 3000, 9000).astype("<i2"), "s16", 1, 16000, extensible=True); paths.insert(5, p); kinds.insert(5, "ingest")
+    p = str(tmp_path / "float.wav"); write_wav(p, rng.standard_normal(5000).astype("<f4"), "f32", 1, sr); paths.append(p); kinds.append("ingest")
+    p = str(tmp_path / "junk.wav"); open(p, "wb").write(b"RIFFxxxxWAVEjunk"); paths.append(p); kinds.append("bad")
+    p = str(tmp_path / "empty.wav"); io.save_wav(np.zeros((0,), np.int16), p, sr); paths.append(p); kinds.append("bad")
+    paths.append(str(tmp_path / "missing.wav")); kinds.append("bad")
+    pr = reader.probe(paths[0], 60)
+    assert (pr.status, pr.sample_rate, pr.channels, reader.FMT_NAMES[pr.fmt], pr.n_frames) == (reader.RD_NEEDS_INGEST, sr, 1, "s16", 3 * sr)
+    for cd, ov in ((3.0, 0.0), (3.0, 1.0), (1.5, 0.4)):
+        T, step = chunk_step(sr, cd, ov)
+        for threads in (1, 4):
+            out = np.full((400, T), 77, dtype=np.int16)
+            n_files, used, info = reader.read_pcm16_batch(paths, sr, T, step, out, max_seconds=60, threads=threads)
+            assert n_files == len(paths)
+            row = 0
+            for path, kind, fi in zip(paths, kinds, info):
+                if kind == "ok":
+                    want, peak = io.load_pcm16_chunks(path, sr, cd, ov, max_duration=60)
+                    assert fi.status == reader.RD_OK and fi.n_chunks == want.shape[0], path
+                    assert np.array_equal(out[row:row + fi.n_chunks], want), (path, cd, ov)
+                    assert np.float32(fi.peak) == peak
+                    row += fi.n_chunks
+                elif kind == "ingest":
+                    assert fi.status == reader.RD_NEEDS_INGEST and fi.n_chunks == 0
+                else:
+                    assert fi.status == reader.RD_UNREADABLE and fi.n_chunks == 0
+            assert row == used and np.all(out[used:] == 77)
+    # a full buffer stops at a file boundary
+    T, step = chunk_step(sr, 3.0, 0.0)
+    out = np.zeros((5, T), dtype=np.int16)
+    n_files, used, info = reader.read_pcm16_batch(paths, sr, T, step, out, threads=3)
+    assert n_files == 3 and used == 3                    # 1 + 2 chunks, the stereo file takes none, the 7.37 s file (3) does not fit
+    assert reader.read_pcm16_batch(paths[3:4], sr, T, step, np.zeros((2, T), np.int16))[0] == 0   # first file alone does not fit
+    with pytest.raises(ValueError):
+        reader.read_pcm16_batch(paths, sr, T, step, np.zeros((4, T + 1), np.int16))
