@@ -27,7 +27,7 @@ EXPORTS = (
     # include/bn_metrics.h
     "bn_metrics_compute",
     # include/bn_reader.h
-    "bn_wav_probe", "bn_read_pcm16_batch",
+    "bn_wav_probe", "bn_read_pcm16_batch", "bn_read_raw_batch",
 )
 
 BN_SAMPLE_FORMAT = {"s16": 0, "s24": 1, "s32": 2, "f32": 3, "u8": 4}
@@ -145,6 +145,7 @@ def load():
     L.bn_ingest_launch_count.restype = i64
     L.bn_metrics_compute.argtypes = [vp, vp, i32, i32, i32, C.POINTER(BnMetricsResult), vp]
     L.bn_wav_probe.argtypes = [C.c_char_p, C.c_double, C.POINTER(BnReaderFile)]
+    L.bn_read_raw_batch.argtypes = [C.POINTER(C.c_char_p), i32, C.c_double, vp, C.c_int64, i32, C.POINTER(BnReaderFile), C.POINTER(C.c_int64)]
     L.bn_read_pcm16_batch.argtypes = [C.POINTER(C.c_char_p), i32, i32, i32, i32, C.c_double, vp, i32, i32, C.POINTER(BnReaderFile),
                                       C.POINTER(i32)]
     _lib = L

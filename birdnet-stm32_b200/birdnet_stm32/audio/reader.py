@@ -42,3 +42,33 @@ def read_pcm16_batch(paths: list[str], sample_rate: int, chunk_len: int, step: i
     if rc < 0:
         L.check(rc)
     return rc, used.value, info
+
+
+_RAW_DTYPE = {"s16": "<i2", "s24": np.uint8, "s32": "<i4", "f32": "<f4", "u8": np.uint8}
+
+
+def read_raw_batch(paths: list[str], out: np.ndarray, max_seconds: float = 60.0, threads: int = 8):
+    """Raw interleaved samples of `paths` (in order) into the byte buffer `out` (uint8, C-contiguous).
+
+    Returns (files_consumed, items) where items[i] is None for an unreadable file or
+    `(raw, kind, channels, sample_rate)` -- the tuple `audio.io.read_wav_frames` returns, with `raw` a view into `out`."""
+    if out.dtype != np.uint8 or out.ndim != 1 or not out.flags.c_contiguous:
+        raise ValueError("out must be a C-contiguous uint8 vector")
+    n = len(paths)
+    arr = (C.c_char_p * max(n, 1))(*[os.fsencode(p) for p in paths])
+    info = (L.BnReaderFile * max(n, 1))()
+    offs = (C.c_int64 * (n + 1))()
+    rc = L.load().bn_read_raw_batch(arr, n, float(max_seconds or 0.0), out.ctypes.data_as(C.c_void_p), int(out.size), int(threads), info, offs)
+    if rc < 0:
+        L.check(rc)
+    items = []
+    for i in range(rc):
+        fi = info[i]
+        if fi.status == RD_UNREADABLE:
+            items.append(None)
+            continue
+        kind = FMT_NAMES[fi.fmt]
+        nbytes = fi.n_frames * fi.channels * {"s16": 2, "s24": 3, "s32": 4, "f32": 4, "u8": 1}[kind]
+        raw = out[offs[i]:offs[i] + nbytes].view(_RAW_DTYPE[kind])
+        items.append((raw, kind, int(fi.channels), int(fi.sample_rate)))
+    return rc, items

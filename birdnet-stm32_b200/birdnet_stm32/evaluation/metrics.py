@@ -83,6 +83,29 @@ def make_chunks_for_file(path: str, cfg: dict, frontend: str, mag_scale: str, n_
     raise ValueError(f"Invalid audio_frontend for the B200 path: {frontend}")
 
 
+def _read_foreign(paths: list[str], raw_stage: np.ndarray | None, threads: int) -> list:
+    """`read_wav_frames(path, 60)` for every path (None where it fails), read by the native thread pool into `raw_stage`
+    group by group; a file that does not fit the stage, or any reader error, falls back to the Python parser.  The
+    returned arrays of one call are views into `raw_stage`: consume them before the next call."""
+    out: list = [None] * len(paths)
+    done = 0
+    if raw_stage is not None and paths:
+        try:
+            from birdnet_stm32.audio import reader as _rd
+
+            n, items = _rd.read_raw_batch(paths, raw_stage, max_seconds=60, threads=max(1, threads))
+            out[:n] = items
+            done = n
+        except Exception:
+            done = 0
+    for i in range(done, len(paths)):
+        try:
+            out[i] = read_wav_frames(paths[i], 60)
+        except Exception:
+            out[i] = None
+    return out
+
+
 def _metrics_from_scores(y_true_arr: np.ndarray, y_scores_arr: np.ndarray) -> dict:
     """ROC-AUC (micro), F1/precision/recall @0.5, per-class AP, cmAP, mAP -- reference `metrics.py:152-190`."""
     from sklearn.metrics import average_precision_score, roc_auc_score
@@ -245,6 +268,7 @@ def evaluate(model_runner, files: list[str], classes: list[str], cfg: dict, pool
                 except Exception:                      # no CUDA runtime (stub runners in the CPU tests): ordinary memory
                     stage.append((None, np.empty((cap, T), dtype=np.int16)))
             window = 2048                              # paths offered to one reader call
+            raw_stage = None                           # raw frames of the files that need the ingest (allocated on first use)
 
             def read_batch(start: int, slot: int):
                 paths = todo[start:start + window]
@@ -272,24 +296,28 @@ def evaluate(model_runner, files: list[str], classes: list[str], cfg: dict, pool
                         pooled = model_runner.predict_pooled(buf[:used], peak, offs, pooling=pooling, beta=mep_beta)
                         rows.update(zip(ok, pooled))
                     n_batch = used
-                    for i in range(n_files):
-                        if info[i].status != _rd.RD_NEEDS_INGEST:
-                            continue
-                        try:
-                            raw, kind, ch, sr0 = read_wav_frames(todo[start + i], 60)
-                        except Exception:
-                            continue
-                        ws = wave_buffer()
-                        n = ws["ingest"].chunks_to_ptr(raw, kind, ch, sr0, sr, ws["T"], ws["step"], ws["buf"].data_ptr(), ws["cap"])
-                        if n == 0:
-                            continue
-                        torch = ws["torch"]
-                        d_offs = torch.tensor([0, n], dtype=torch.int32, device=ws["dev"])
-                        d_out = torch.empty((1, num_classes), dtype=torch.float32, device=ws["dev"])
-                        torch.cuda.synchronize(ws["dev"])
-                        model_runner.infer_pool_wave_ptr(ws["buf"].data_ptr(), None, d_offs.data_ptr(), 1, pooling, mep_beta, d_out.data_ptr(), None)
-                        rows[i] = d_out.cpu().numpy()[0]
-                        n_batch += n
+                    foreign = [i for i in range(n_files) if info[i].status == _rd.RD_NEEDS_INGEST]
+                    if foreign and raw_stage is None:
+                        raw_stage = np.empty(256 << 20, dtype=np.uint8)
+                    # the arrays are views into raw_stage, valid until the next group is read
+                    for g0 in range(0, len(foreign), 16):
+                        group = foreign[g0:g0 + 16]
+                        f_items = _read_foreign([todo[start + j] for j in group], raw_stage, io_workers)
+                        for i, item in zip(group, f_items):
+                            if item is None:
+                                continue
+                            raw, kind, ch, sr0 = item
+                            ws = wave_buffer()
+                            n = ws["ingest"].chunks_to_ptr(raw, kind, ch, sr0, sr, ws["T"], ws["step"], ws["buf"].data_ptr(), ws["cap"])
+                            if n == 0:
+                                continue
+                            torch = ws["torch"]
+                            d_offs = torch.tensor([0, n], dtype=torch.int32, device=ws["dev"])
+                            d_out = torch.empty((1, num_classes), dtype=torch.float32, device=ws["dev"])
+                            torch.cuda.synchronize(ws["dev"])
+                            model_runner.infer_pool_wave_ptr(ws["buf"].data_ptr(), None, d_offs.data_ptr(), 1, pooling, mep_beta, d_out.data_ptr(), None)
+                            rows[i] = d_out.cpu().numpy()[0]
+                            n_batch += n
                     if measure_latency and n_batch:
                         per = (time.perf_counter() - t0) * 1000 / n_batch
                         latencies_ms.extend([per] * n_batch)

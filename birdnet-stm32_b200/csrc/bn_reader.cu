@@ -187,3 +187,40 @@ extern "C" int bn_read_pcm16_batch(const char* const* paths, int n_paths, int sa
   *chunks_used = used;
   return consumed;
 }
+
+extern "C" int bn_read_raw_batch(const char* const* paths, int n_paths, double max_seconds, void* dst, int64_t cap_bytes, int threads,
+                                 bn_reader_file* files_out, int64_t* byte_offsets) {
+  if (!paths || n_paths < 0 || !files_out || !byte_offsets || cap_bytes < 0 || (cap_bytes > 0 && !dst))
+    return bn::set_error(BN_ERR_ARG, "bn_read_raw_batch: bad arguments");
+  static const int bytes_per_sample[5] = {2, 3, 4, 4, 1};              // BN_SF_S16, S24, S32, F32, U8
+  parallel_for(n_paths, threads, [&](int i) {
+    bn_reader_file* o = files_out + i;
+    const int fd = paths[i] ? open(paths[i], O_RDONLY | O_CLOEXEC) : -1;
+    if (fd < 0) { memset(o, 0, sizeof *o); o->status = BN_RD_UNREADABLE; o->fmt = -1; return; }
+    probe_fd(fd, max_seconds, o);
+    if (o->status != BN_RD_UNREADABLE && o->n_frames <= 0) o->status = BN_RD_UNREADABLE;
+    close(fd);
+  });
+  int consumed = 0;
+  int64_t used = 0;
+  for (; consumed < n_paths; consumed++) {
+    const bn_reader_file& o = files_out[consumed];
+    int64_t nb = 0;
+    if (o.status != BN_RD_UNREADABLE) nb = o.n_frames * o.channels * bytes_per_sample[o.fmt];
+    const int64_t slot = (nb + 15) & ~(int64_t)15;
+    if (used + slot > cap_bytes) break;
+    byte_offsets[consumed] = used;
+    used += slot;
+  }
+  byte_offsets[consumed] = used;
+  parallel_for(consumed, threads, [&](int i) {
+    bn_reader_file* o = files_out + i;
+    if (o->status == BN_RD_UNREADABLE) return;
+    const int64_t nb = o->n_frames * o->channels * bytes_per_sample[o->fmt];
+    const int fd = open(paths[i], O_RDONLY | O_CLOEXEC);
+    const bool ok = fd >= 0 && pread_all(fd, (unsigned char*)dst + byte_offsets[i], (size_t)nb, (off_t)o->data_offset);
+    if (fd >= 0) close(fd);
+    if (!ok) o->status = BN_RD_UNREADABLE;
+  });
+  return consumed;
+}

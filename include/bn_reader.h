@@ -47,6 +47,14 @@ BN_API int bn_wav_probe(const char* path, double max_seconds, bn_reader_file* ou
 BN_API int bn_read_pcm16_batch(const char* const* paths, int n_paths, int sample_rate, int chunk_len, int step, double max_seconds,
                                int16_t* chunks, int cap_chunks, int threads, bn_reader_file* files_out, int* chunks_used);
 
+/* Raw interleaved sample data of paths[0 ..] (any supported format / rate / channel count), file after file, into `dst`
+ * (16-byte aligned slots) until the next file would not fit in cap_bytes: the input of bn_ingest_chunks for the files
+ * bn_read_pcm16_batch flagged BN_RD_NEEDS_INGEST.  files_out[i] (header fields, n_frames of the window) and
+ * byte_offsets[i] (slot start; byte_offsets[consumed] = bytes used) are filled for the consumed files; unreadable files
+ * take no space.  Returns the number of files consumed or a negative bn_status. */
+BN_API int bn_read_raw_batch(const char* const* paths, int n_paths, double max_seconds, void* dst, int64_t cap_bytes, int threads,
+                             bn_reader_file* files_out, int64_t* byte_offsets);
+
 #ifdef __cplusplus
 }
 #endif

@@ -324,3 +324,28 @@ def test_native_reader_path_equals_python_reader_path(tmp_path):
     np.testing.assert_array_equal(a[3], b[3])
     np.testing.assert_array_equal(a[2], b[2])
     assert a[0]["skipped_files"] == b[0]["skipped_files"] == 1
+
+
+def test_read_foreign_native_and_fallback(tmp_path):
+    from test_ingest import write_wav
+
+    from birdnet_stm32.audio import io
+    from birdnet_stm32.evaluation.metrics import _read_foreign
+
+    rng = np.random.default_rng(2)
+    paths = []
+    for i, (kind, ch, sr, n) in enumerate((("s16", 2, 48000, 50000), ("f32", 1, 44100, 30000), ("s24", 2, 32000, 20000))):
+        raw = rng.standard_normal(n * ch).astype("<f4") if kind == "f32" else (
+            rng.integers(0, 256, size=n * ch * 3, dtype=np.uint8) if kind == "s24" else rng.integers(-9000, 9000, size=n * ch).astype("<i2"))
+        p = str(tmp_path / f"x{i}.wav")
+        write_wav(p, raw, kind, ch, sr)
+        paths.append(p)
+    paths.insert(1, str(tmp_path / "gone.wav"))
+    for stage in (np.zeros(1 << 20, np.uint8), np.zeros(250000, np.uint8), None):      # all fit / only the first fits / Python parser only
+        items = _read_foreign(paths, stage, 3)
+        assert len(items) == 4 and items[1] is None
+        for path, item in zip(paths, items):
+            if item is None:
+                continue
+            want = io.read_wav_frames(path, 60)
+            assert item[1:] == want[1:] and np.array_equal(item[0], want[0])

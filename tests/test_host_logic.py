@@ -243,3 +243,39 @@ def test_native_batch_reader_matches_python_loader(tmp_path):
     assert reader.read_pcm16_batch(paths[3:4], sr, T, step, np.zeros((2, T), np.int16))[0] == 0   # first file alone does not fit
     with pytest.raises(ValueError):
         reader.read_pcm16_batch(paths, sr, T, step, np.zeros((4, T + 1), np.int16))
+
+
+def test_native_raw_batch_reader_matches_python_wav_parser(tmp_path):
+    from test_ingest import write_wav
+
+    from birdnet_stm32.audio import io, reader
+
+    rng = np.random.default_rng(8)
+    paths = []
+    for i, (kind, ch, sr, n) in enumerate((("s16", 2, 48000, 30001), ("f32", 1, 44100, 12345), ("s24", 3, 32000, 7777), ("u8", 1, 16000, 5000),
+                                           ("s32", 2, 96000, 4001), ("s16", 1, 22050, 700000))):
+        if kind == "f32":
+            raw = rng.standard_normal(n * ch).astype("<f4")
+        elif kind in ("s24", "u8"):
+            raw = rng.integers(0, 256, size=n * ch * (3 if kind == "s24" else 1), dtype=np.uint8)
+        else:
+            info = np.iinfo(np.int16 if kind == "s16" else np.int32)
+            raw = rng.integers(info.min, info.max, size=n * ch).astype("<i2" if kind == "s16" else "<i4")
+        p = str(tmp_path / f"r{i}.wav")
+        write_wav(p, raw, kind, ch, sr, extensible=(i % 2 == 1))
+        paths.append(p)
+    paths.insert(2, str(tmp_path / "missing.wav"))
+    buf = np.zeros(8 << 20, dtype=np.uint8)
+    for threads in (1, 4):
+        for max_s in (60.0, 0.05):
+            n_files, items = reader.read_raw_batch(paths, buf, max_seconds=max_s, threads=threads)
+            assert n_files == len(paths) and items[2] is None
+            for path, item in zip(paths, items):
+                if item is None:
+                    continue
+                want = io.read_wav_frames(path, max_s)
+                assert item[1:] == want[1:], path
+                assert item[0].dtype == want[0].dtype and np.array_equal(item[0], want[0]), path
+    # a small buffer stops at a file boundary
+    n_files, items = reader.read_raw_batch(paths, np.zeros(200000, dtype=np.uint8), threads=2)
+    assert n_files == 3 and items[2] is None             # 120,004 + 49,380 bytes fit, the missing file takes none, the 24-bit file does not fit
