@@ -349,3 +349,85 @@ def test_read_foreign_native_and_fallback(tmp_path):
                 continue
             want = io.read_wav_frames(path, 60)
             assert item[1:] == want[1:] and np.array_equal(item[0], want[0])
+
+
+def test_device_path_control_flow_with_foreign_files_simulated_on_cpu(tmp_path, monkeypatch):
+    """The device path of evaluate() -- native PCM16 batches, files routed through the ingest, ordering, skips -- driven on
+    the CPU with stand-ins for the CUDA pieces: torch tensors live in host memory, GpuIngest is replaced by the ingest
+    oracle writing through the same pointer interface, and the runner returns checksums of the chunks it is handed.
+    Both reader paths (C++ batch reader / Python threads) must produce identical results in file order."""
+    import ctypes
+    import warnings
+
+    import torch
+
+    from test_ingest import write_wav
+
+    from birdnet_stm32.audio import ingest as ingest_mod
+    from birdnet_stm32.evaluation.metrics import evaluate
+    from oracle import bn_ingest_oracle as O
+
+    classes = ["bird_a", "bird_b"]
+    sr, cd = 8000, 1.0
+    T = int(sr * cd)
+    files = make_dataset(str(tmp_path), classes, n_per_class=3, sr=sr, seconds=(1.0, 2.6, 0.4))
+    rng = np.random.default_rng(3)
+    for i, (kind, ch, sr0, n) in enumerate((("s16", 2, 16000, 30000), ("f32", 1, 11025, 9000), ("s16", 1, 4000, 7000))):
+        raw = rng.standard_normal(n * ch).astype("<f4") * 0.2 if kind == "f32" else rng.integers(-9000, 9000, size=n * ch).astype("<i2")
+        p = str(tmp_path / classes[i % 2] / f"foreign{i}.wav")
+        write_wav(p, raw, kind, ch, sr0)
+        files.insert(2 * i + 1, p)
+    (tmp_path / "bird_b" / "junk.wav").write_bytes(b"not a wav file at all")
+    files.append(str(tmp_path / "bird_b" / "junk.wav"))
+
+    class FakeIngest:
+        def __init__(self, device=0):
+            self.device = device
+
+        def chunks_to_ptr(self, raw, kind, channels, sr_in, sr_out, chunk_len, step, out_ptr, max_chunks):
+            wave, _ = O.load_window(np.asarray(raw), kind, channels, sr_in, sr_out)
+            ch = O.split_chunks(wave, sr_out, chunk_len / sr_out, 0.0)
+            assert ch.shape[0] <= max_chunks and ch.shape[1] == chunk_len
+            ctypes.memmove(out_ptr, np.ascontiguousarray(ch, dtype=np.float32).ctypes.data, ch.nbytes)
+            return ch.shape[0]
+
+        def close(self):
+            pass
+
+    real_device = torch.device
+    monkeypatch.setattr(ingest_mod, "GpuIngest", FakeIngest)
+    monkeypatch.setattr(torch, "device", lambda *a, **k: real_device("cpu"))
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+
+    class Stub:
+        device = 0
+
+        def predict_pooled(self, pcm, peak, offs, pooling="avg", beta=10.0):
+            out = np.zeros((len(offs) - 1, len(classes)), dtype=np.float32)
+            for f in range(len(offs) - 1):
+                seg = pcm[offs[f]:offs[f + 1]].astype(np.float64)
+                out[f] = [abs(seg.sum()) % 97 / 97.0, float(peak[offs[f]])]
+            return out
+
+        def infer_pool_wave_ptr(self, wave_ptr, peak_ptr, offs_ptr, F, pooling, beta, out_ptr, stream=None):
+            offs = np.ctypeslib.as_array(ctypes.cast(offs_ptr, ctypes.POINTER(ctypes.c_int32)), shape=(F + 1,))
+            wave = np.ctypeslib.as_array(ctypes.cast(wave_ptr, ctypes.POINTER(ctypes.c_float)), shape=(int(offs[F]), T))
+            out = np.ctypeslib.as_array(ctypes.cast(out_ptr, ctypes.POINTER(ctypes.c_float)), shape=(F, len(classes)))
+            for f in range(F):
+                seg = wave[offs[f]:offs[f + 1]].astype(np.float64)
+                out[f] = [abs(seg.sum()) % 1.0, float(np.abs(seg).max())]
+
+    cfg = dict(RAW_CFG, audio_frontend="hybrid", sample_rate=sr, chunk_duration=cd)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = evaluate(Stub(), files, classes, cfg, pooling="avg", device_batch_chunks=4, native_reader=True, io_workers=3)
+        b = evaluate(Stub(), files, classes, cfg, pooling="avg", device_batch_chunks=4, native_reader=False, io_workers=3)
+    want_files = [f for f in files if not f.endswith("junk.wav")]
+    assert [f["file"] for f in a[1]] == want_files == [f["file"] for f in b[1]]
+    np.testing.assert_array_equal(a[3], b[3])
+    np.testing.assert_array_equal(a[2], b[2])
+    assert a[0]["skipped_files"] == b[0]["skipped_files"] == 1
+    # the foreign files really went through the ingest stand-in: their second score is max|normalised wave| = 1
+    for row, f in zip(a[3], want_files):
+        if "foreign" in f:
+            assert abs(row[1] - 1.0) < 1e-6
