@@ -28,8 +28,10 @@
  * the scores of checkpoints/birdnet_stm32n6_100.keras (read without TensorFlow, oracle/h5min.py +
  * oracle/keras_float_model.py, golden in tests/golden/keras_float_reference.npz) and the int8
  * scores of this oracle have cosine similarity 0.994 (gate: >= 0.95, conversion/validate.py:51-105,
- * cli/convert.py:187-195), tests/test_keras_float_pin.py.  What stays unpinned is the bit level:
- * rounding tie-breaks of the TFLite kernels (see BN_OPT_ROUNDING / BN_OPT_MEAN_VARIANT).
+ * cli/convert.py:187-195), tests/test_keras_float_pin.py; the same test file reproduces all 205,185
+ * int8 weights of the .tflite exactly from the float checkpoint (BatchNorm folding + per-channel
+ * max/127 quantisation), which fixes layouts and layer identity at the bit level.  What stays
+ * unpinned is the run-time rounding of the TFLite kernels (BN_OPT_ROUNDING / BN_OPT_MEAN_VARIANT).
  *
  * Build: gcc -O2 -fopenmp -shared -fPIC (see oracle/Makefile).  -ffast-math must
  * NOT be used (rounding behaviour is the point).

@@ -133,3 +133,42 @@ def test_int8_layers_track_the_float_checkpoint_layer_by_layer(synth, oracle_mod
             worst_corr, worst_rel = min(worst_corr, corr), max(worst_rel, rel)
             assert corr >= 0.97 and rel <= 0.25, (name, ax, corr, rel)
     print(f"26 layers vs float checkpoint: worst profile correlation {worst_corr:.4f}, worst relative L2 error {worst_rel:.3f}")
+
+
+def test_shipped_tflite_weights_are_reproduced_from_the_float_checkpoint(graph):
+    """Bit-level pin of the weight / bias path against the REAL TensorFlow Lite converter: quantising the float
+    checkpoint's BatchNorm-folded weights per output channel (scale = max|w| / 127, round to nearest) must give exactly
+    the int8 weights the shipped `.tflite` holds, its scales to float32 accuracy, and its int32 biases
+    (bias / (input scale x weight scale)) to within one unit.  This fixes the reading of both files: OHWI / 1HWC layouts,
+    quantised dimension, BatchNorm folding, which convolution is which."""
+    import hashlib
+
+    ref = np.load(os.path.join(GOLDEN, "keras_weight_reference.npz"))
+    names = [str(n) for n in ref["names"]]
+    ops = [op for op in graph.ops if op.kind in ("CONV_2D", "DEPTHWISE_CONV_2D", "FULLY_CONNECTED")
+           and not (op.kind == "DEPTHWISE_CONV_2D" and graph.tensors[op.inputs[1]].shape[1:3] == (1, 1))]      # skip the 1x1 PWL depthwise ops
+    assert len(ops) == len(names) == 25
+    n_weights = n_bias = bias_off = 0
+    for name, op in zip(names, ops):
+        wt = graph.tensors[op.inputs[1]]
+        live = ref[f"{name}/live"]
+        axis = int(ref[f"{name}/axis"])
+        assert wt.quantized_dimension == axis and wt.shape[axis] == live.size, name
+        shape = [1] * len(wt.shape)
+        shape[axis] = -1
+        q = np.where(np.broadcast_to(live.reshape(shape), wt.data.shape), wt.data, 0).astype(np.int8)
+        dig = np.frombuffer(hashlib.sha256(np.ascontiguousarray(q).tobytes()).digest()[:8], dtype=np.uint64)[0]
+        assert dig == ref[f"{name}/digest"], f"{name}: int8 weights differ from the quantised float checkpoint"
+        n_weights += int(np.broadcast_to(live.reshape(shape), wt.data.shape).sum())
+        s_ref = ref[f"{name}/scale"][live]
+        s = wt.scale.astype(np.float64)[live]
+        assert np.all(np.abs(s - s_ref) <= 1e-6 * s_ref), name
+        assert np.all(wt.scale.astype(np.float64)[~live] <= 2e-8), name      # dead channels (|w| ~ 1e-40): the converter's floor scales
+        if f"{name}/bias" in ref.files and len(op.inputs) > 2 and op.inputs[2] >= 0:
+            bt, it = graph.tensors[op.inputs[2]], graph.tensors[op.inputs[0]]
+            want = np.round(ref[f"{name}/bias"] / (float(it.scale[0]) * wt.scale.astype(np.float64)))
+            ok = np.abs(want - bt.data.astype(np.float64)) <= 1
+            n_bias += int(live.sum())
+            bias_off += int((~ok[live]).sum())
+    print(f"{n_weights} int8 weights of 25 layers identical to the quantised float checkpoint; {n_bias - bias_off}/{n_bias} biases within 1")
+    assert n_weights > 180000 and bias_off <= 2
