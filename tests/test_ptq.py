@@ -188,3 +188,37 @@ def test_gpu_generic_plan_bit_exact_on_synthesised_graphs(name):
         checked += 1
     assert checked >= len(g.ops) - 2
     runner.close()
+
+
+def test_ptq_weight_quantiser_reproduces_the_real_converter_output(graph):
+    """Row f3 against the reference's own artefacts: the weight quantiser of `conversion/ptq.py`, fed with the
+    BatchNorm-folded float weights of the shipped Keras checkpoint, must give the int8 weights and scales that the REAL
+    TensorFlow Lite converter wrote into the shipped `.tflite` (build container only: needs the reference checkout)."""
+    import sys
+
+    path = "/root/reference/checkpoints/birdnet_stm32n6_100.keras"
+    if not os.path.exists(path):
+        pytest.skip("reference checkout not mounted")
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden"))
+    from make_golden_weights import expected_layers
+
+    from birdnet_stm32.conversion import ptq
+    from oracle.keras_float_model import KerasFloatModel
+
+    layers = expected_layers(KerasFloatModel(path))
+    ops = [op for op in graph.ops if op.kind in ("CONV_2D", "DEPTHWISE_CONV_2D", "FULLY_CONNECTED")
+           and not (op.kind == "DEPTHWISE_CONV_2D" and graph.tensors[op.inputs[1]].shape[1:3] == (1, 1))]
+    assert len(layers) == len(ops) == 25
+    same = total = 0
+    for (name, wf, axis, _), op in zip(layers, ops):
+        wt = graph.tensors[op.inputs[1]]
+        q, scale = ptq._weight_q(wf.astype(np.float32), axis, per_channel=True)
+        live = scale > 4e-9                                   # dead channels (|w| ~ 1e-40) carry converter floor scales
+        shp = [1] * q.ndim
+        shp[axis] = -1
+        m = np.broadcast_to(live.reshape(shp), q.shape)
+        assert np.array_equal(q[m], wt.data[m]), name
+        assert np.all(np.abs(scale[live].astype(np.float64) - wt.scale.astype(np.float64)[live]) <= 1e-6 * scale[live]), name
+        same += int(m.sum())
+        total += q.size
+    assert same > 200000 and same / total > 0.9            # the rest are dead channels (6.5 % of the weights)
