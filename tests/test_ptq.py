@@ -222,3 +222,61 @@ def test_ptq_weight_quantiser_reproduces_the_real_converter_output(graph):
         same += int(m.sum())
         total += q.size
     assert same > 200000 and same / total > 0.9            # the rest are dead channels (6.5 % of the weights)
+
+
+def test_own_ptq_of_the_shipped_float_checkpoint_passes_the_reference_gate(synth):
+    """Row f3 end to end on the reference's real network: the body of the shipped Keras checkpoint (stem ... dense head,
+    BatchNorm folded) is described as a FloatGraph, quantised by `conversion/ptq.py` on 24 calibration chunks, written as a
+    `.tflite`, exported and run by the int8 oracle; its scores must pass the reference's conversion gate against the float
+    model (mean cosine >= 0.95, `conversion/validate.py`) on 12 held-out chunks -- like the shipped converter output does
+    (build container only: needs the reference checkout)."""
+    path = "/root/reference/checkpoints/birdnet_stm32n6_100.keras"
+    if not os.path.exists(path):
+        pytest.skip("reference checkout not mounted")
+    from conftest import CONFIG
+
+    from oracle import bn_oracle
+    from oracle.keras_float_model import KerasFloatModel, cosine_similarity
+
+    km = KerasFloatModel(path)
+    cfg = json.load(open(CONFIG))
+    T = int(cfg["sample_rate"] * cfg["chunk_duration"])
+
+    def frontend_out(seed, n):
+        pcm = synth.synth_pcm16(n, T, cfg["sample_rate"], seed=seed, edge_cases=False)
+        spec = bn_oracle.frontend_hybrid(pcm, synth.file_peaks(pcm), cfg["fft_length"], T // cfg["spec_width"], cfg["spec_width"])
+        taps: dict = {}
+        scores = km.predict(spec, taps)
+        return taps["frontend"].astype(np.float32), scores          # [n, 64, 256, 1] NHWC
+
+    fg = ptq.FloatGraph((64, 256, 1))
+    x, block_in = 0, None
+    layers = km.layers
+    for i, l in enumerate(layers):
+        cls, c = l["class_name"], l["config"]
+        if cls in ("Conv2D", "DepthwiseConv2D"):
+            bn = layers[i + 1]
+            g, b, m, v = (km.var(bn["config"]["name"], k).astype(np.float64) for k in range(4))
+            sc = g / np.sqrt(v + bn["config"]["epsilon"])
+            nxt = next(t for t in layers[i + 2:] if t["class_name"] not in ("SpatialDropout2D",))
+            act = "RELU6" if nxt["class_name"] == "ReLU" else "NONE"          # a residual Add comes before the ReLU
+            w = km.var(c["name"], 0).astype(np.float64)
+            if cls == "Conv2D":
+                x = fg.conv2d(x, np.transpose(w * sc[None, None, None, :], (3, 0, 1, 2)), b - m * sc, stride=tuple(c["strides"]), act=act)
+            else:
+                block_in = x
+                x = fg.dwconv(x, (w[:, :, :, 0] * sc[None, None, :])[None], b - m * sc, stride=tuple(c["strides"]), act=act)
+        elif cls == "Add":
+            x = fg.add(block_in, x, act="RELU6")
+        elif cls == "GlobalAveragePooling2D":
+            x = fg.mean_hw(x, keep_dims=False)
+        elif cls == "Dense":
+            x = fg.logistic(fg.dense(x, km.var(c["name"], 0).T, km.var(c["name"], 1)))
+    calib, _ = frontend_out(101, 24)
+    test_x, want = frontend_out(202, 12)
+    np.testing.assert_allclose(fg.run(test_x)[x], want, atol=2e-5)       # the FloatGraph IS the float model's body
+    blob = export_blob(read_tflite(ptq.convert(fg, calib, per_channel=True, description="shipped checkpoint, own PTQ")), {})
+    got = bn_oracle.OracleModel(blob).predict(test_x)
+    cos = [cosine_similarity(want[i].astype(np.float64), got[i].astype(np.float64)) for i in range(len(want))]
+    print(f"own PTQ of the shipped float checkpoint: cosine mean {np.mean(cos):.4f}, min {min(cos):.4f}, MAE {np.abs(got - want).mean():.5f}")
+    assert np.mean(cos) >= 0.95 and np.abs(got - want).mean() <= 0.01
