@@ -167,6 +167,16 @@ def load_audio_window(path: str, sample_rate: int = 24000, max_duration: float |
     return y.astype(np.float32, copy=False)
 
 
+def fast_resample(y: np.ndarray, sr_in: int, sr_out: int) -> np.ndarray:
+    """`scipy.signal.resample_poly` twin of the reference (`audio/io.py:14-30`) on the device: float32 mono in, float32 out,
+    bit-identical to scipy (see `audio/ingest.py`).  Equal rates return the input as float32."""
+    if sr_in == sr_out:
+        return np.asarray(y).astype(np.float32, copy=False)
+    from birdnet_stm32.audio.ingest import shared_ingest
+
+    return shared_ingest().window(np.ascontiguousarray(y, dtype=np.float32), "f32", 1, int(sr_in), int(sr_out), normalize=False)
+
+
 def load_audio_file(path: str, sample_rate: int = 24000, max_duration: int = 30, chunk_duration: float = 3.0,
                     chunk_overlap: float = 0.0, random_offset: bool = False):
     """Float32 chunks `[n, chunk_size]` like the reference (`io.py:177-213`); `[]` on error."""

@@ -117,3 +117,34 @@ def get_spectrograms_from_pcm16(pcm: np.ndarray, peak=None, sample_rate: int = 2
         return fx(pcm, peak)
     finally:
         fx.close()
+
+
+def audio_to_pcm16_peak(audio: np.ndarray) -> tuple[np.ndarray, np.float32]:
+    """Float waveform -> (int16 samples, peak) such that the device's `(pcm / 32768) / peak` reproduces it.
+
+    The feature kernels take PCM16 plus a per-chunk divisor.  A float chunk `a` with A = max|a| is stored as
+    `pcm = round(a / A * 32767)` and `peak = 32767 / (32768 * A)`, so the device sees `pcm * A / 32767`: `a` rounded to 16 bits
+    of ITS OWN range (absolute error <= A / 65534).  After the min-max normalisation every frontend ends with, that is an
+    error of about 1e-5 on the mel / PWL / log-mel / MFCC features, inside the 1e-4 frontend tolerance; the dB scaling amplifies
+    the rounding of quiet bins to at most 5e-4, PCEN to 1e-4 (measured against the oracle in `tests/test_features.py`).  Silence gives zeros and peak 0 (= no division)."""
+    a = np.asarray(audio, dtype=np.float32).reshape(-1)
+    amax = float(np.max(np.abs(a))) if a.size else 0.0
+    if not amax > 0.0:
+        return np.zeros(a.shape, dtype=np.int16), np.float32(0.0)
+    pcm = np.round(a.astype(np.float64) / amax * 32767.0).astype(np.int16)
+    return pcm, np.float32(32767.0 / (32768.0 * amax))
+
+
+def get_spectrogram_from_audio(audio: np.ndarray, sample_rate: int = 24000, n_fft: int = 512, mel_bins: int = 64, spec_width: int = 256,
+                               mag_scale: str = "none", mode: str = "mel", n_mfcc: int = 20, device: int = 0) -> np.ndarray:
+    """The reference's per-chunk entry point (`audio/spectrogram.py:24-149`), same arguments and return shape
+    `(mel_bins | n_mfcc, spec_width)` in [0, 1], computed by the CUDA feature kernels for one float chunk.
+
+    Batches should use :class:`FeatureExtractor` (one launch for many chunks).  The linear mode (`mel_bins <= 0`, the hybrid
+    model input) needs the model's engine and is served by `GpuRunner.frontend` / `frontend_wave`."""
+    if mel_bins <= 0 or mode == "linear":
+        raise ValueError("linear STFT magnitudes are the hybrid model input: use GpuRunner.frontend_wave(chunks)")
+    pcm, peak = audio_to_pcm16_peak(audio)
+    out = get_spectrograms_from_pcm16(pcm[None, :], np.array([peak], dtype=np.float32), sample_rate, n_fft, mel_bins, spec_width, mag_scale,
+                                      mode, n_mfcc, device)
+    return out[0]

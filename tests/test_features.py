@@ -194,3 +194,30 @@ def test_oracle_agrees_with_torchaudio_independent_implementation():
                        center=True, pad_mode="constant", return_complex=True).abs().numpy()
         assert m.shape[0] == 257 and m.shape[1] <= Y.shape[1]
         assert np.abs(m - Y[:, : m.shape[1]]).max() <= 1e-5 * np.abs(Y).max()
+
+
+def test_float_audio_shim_stays_inside_the_frontend_tolerance():
+    """`get_spectrogram_from_audio(float chunk)` hands the feature kernels int16 samples + a divisor
+    (`audio_to_pcm16_peak`).  On the oracle: features of that representation vs features of the float chunk itself."""
+    from oracle import bn_features_oracle as FO
+
+    from birdnet_stm32.audio.spectrogram import audio_to_pcm16_peak
+
+    rng = np.random.default_rng(12)
+    T, sr = 66150, 22050
+    t = np.arange(T) / sr
+    for amp in (1.0, 0.03, 7.5):
+        a = (amp * (0.6 * np.sin(2 * np.pi * (900 + 2500 * t) * t) + 0.1 * rng.standard_normal(T))).astype(np.float32)
+        pcm, peak = audio_to_pcm16_peak(a)
+        assert pcm.dtype == np.int16 and np.abs(pcm).max() == 32767
+        rec = pcm.astype(np.float32) / np.float32(32768.0) / peak
+        assert np.abs(rec - a).max() <= np.abs(a).max() / 65000.0
+        # (dB scaling turns the 16-bit rounding of quiet bins into visible differences: 5e-4 there, 1e-4 elsewhere)
+        for mode, mag, tol in (("mel", "none", 1e-4), ("mel", "pwl", 1e-4), ("mel", "pcen", 2e-4), ("mel", "db", 5e-4), ("log_mel", "none", 1e-4),
+                               ("mfcc", "none", 1e-4)):
+            want = FO.get_spectrogram_from_audio(a, sr, 512, 64, 256, mag, mode)
+            got = FO.features_from_pcm16(pcm[None, :], np.array([peak], np.float32), sample_rate=sr, n_fft=512, mel_bins=64, spec_width=256,
+                                         mag_scale=mag, mode=mode)[0]
+            assert got.shape == want.shape and np.abs(got - want).max() <= tol, (amp, mode, mag, float(np.abs(got - want).max()))
+    z, pk = audio_to_pcm16_peak(np.zeros(100, np.float32))
+    assert not z.any() and pk == 0
