@@ -41,6 +41,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -61,6 +62,15 @@ typedef struct bno_model {
 } bno_model;
 
 static __thread char g_err[256];
+/* per-op-kind seconds (single-threaded runs only; switched on by bno_profile(1)) */
+static int g_profile = 0;
+static double g_prof_s[32];
+static double g_prof_op[256];
+BNO_EXPORT void bno_profile(int on, double* out32) {
+  if (out32) memcpy(out32, g_prof_s, sizeof g_prof_s);
+  if (on >= 0) { g_profile = on; memset(g_prof_s, 0, sizeof g_prof_s); }
+}
+BNO_EXPORT void bno_profile_ops(double* out256) { memcpy(out256, g_prof_op, sizeof g_prof_op); memset(g_prof_op, 0, sizeof g_prof_op); }
 BNO_EXPORT const char* bno_last_error(void) { return g_err; }
 
 /* ------------------------------------------------------------------------- */
@@ -147,6 +157,8 @@ static int run_one(const bno_model* m, const float* input, float* output, void**
   memcpy(buf[h->input_tensor], input, T[h->input_tensor].nbytes);
   for (uint32_t oi = 0; oi < h->n_ops; oi++) {
     const bn_blob_op* op = &m->ops[oi];
+    struct timespec ts0;
+    if (g_profile) clock_gettime(CLOCK_MONOTONIC, &ts0);
     const bn_blob_tensor* to = &T[op->out];
     const bn_blob_tensor* ti = op->n_in > 0 ? &T[op->in[0]] : NULL;
     const int32_t* p = op->p;
@@ -228,22 +240,61 @@ static int run_one(const bno_model* m, const float* input, float* output, void**
         const int32_t in_off = -p[BN_CONV_IN_ZP], out_zp = p[BN_CONV_OUT_ZP];
         const int ih = ti->dims[0], iw = ti->dims[1], ic = ti->dims[2];
         const int oh = to->dims[0], ow = to->dims[1], oc = to->dims[2];
-        for (int oy = 0; oy < oh; oy++) for (int ox = 0; ox < ow; ox++) for (int co = 0; co < oc; co++) {
-          int32_t acc = 0;
-          for (int fy = 0; fy < kh; fy++) {
-            int iy = oy * sh - pt + fy;
-            if (iy < 0 || iy >= ih) continue;
-            for (int fx = 0; fx < kw; fx++) {
-              int ix = ox * sw - pl + fx;
-              if (ix < 0 || ix >= iw) continue;
-              const int8_t* xp = x + ((long)iy * iw + ix) * ic;
-              const int8_t* wp = w + (((long)co * kh + fy) * kw + fx) * ic;
-              for (int ci = 0; ci < ic; ci++) acc += ((int32_t)xp[ci] + in_off) * (int32_t)wp[ci];
+        if (kh == 1 && kw == 1 && sh == 1 && sw == 1 && pt == 0 && pl == 0 && ic <= 4096) {
+          /* pointwise conv: the same sums as the general loop below, with the zero-point offset applied once per input
+           * element and int16 operands so that the compiler can vectorise the channel loop */
+          /* weights transposed to [ci][co] int32 so that the inner loop runs over output channels */
+          int32_t* ws = (int32_t*)malloc(sizeof(int32_t) * (size_t)oc * ic);
+          int32_t* __restrict__ accv = (int32_t*)malloc(sizeof(int32_t) * (size_t)oc);
+          for (int co = 0; co < oc; co++) for (int ci = 0; ci < ic; ci++) ws[(long)ci * oc + co] = (int32_t)w[(long)co * ic + ci];
+          const int32_t amin = p[BN_CONV_ACT_MIN], amax = p[BN_CONV_ACT_MAX];
+          for (long px = 0; px < (long)oh * ow; px++) {
+            const int8_t* xp = x + px * ic;
+            for (int co = 0; co < oc; co++) accv[co] = bias[co];
+            for (int ci = 0; ci < ic; ci++) {
+              const int32_t xv = (int32_t)xp[ci] + in_off;
+              const int32_t* __restrict__ wr = ws + (long)ci * oc;
+              for (int co = 0; co < oc; co++) accv[co] += xv * wr[co];
+            }
+            for (int co = 0; co < oc; co++) {
+              const int32_t acc = mbqm(accv[co], mult[co], shift[co], R) + out_zp;
+              y[px * oc + co] = (int8_t)clampi(acc, amin, amax);
             }
           }
-          acc += bias[co];
-          acc = mbqm(acc, mult[co], shift[co], R) + out_zp;
-          y[((long)oy * ow + ox) * oc + co] = (int8_t)clampi(acc, p[BN_CONV_ACT_MIN], p[BN_CONV_ACT_MAX]);
+          free(accv);
+          free(ws);
+          break;
+        }
+        {
+          /* general case: ConvPerChannel's sums (out-of-image taps skipped), output channels innermost on weights
+           * transposed to [fy][fx][ci][co] */
+          int32_t* wt = (int32_t*)malloc(sizeof(int32_t) * (size_t)oc * kh * kw * ic);
+          int32_t* __restrict__ accv = (int32_t*)malloc(sizeof(int32_t) * (size_t)oc);
+          for (int co = 0; co < oc; co++) for (int t = 0; t < kh * kw; t++) for (int ci = 0; ci < ic; ci++)
+            wt[((long)t * ic + ci) * oc + co] = (int32_t)w[((long)co * kh * kw + t) * ic + ci];
+          for (int oy = 0; oy < oh; oy++) for (int ox = 0; ox < ow; ox++) {
+            for (int co = 0; co < oc; co++) accv[co] = bias[co];
+            for (int fy = 0; fy < kh; fy++) {
+              int iy = oy * sh - pt + fy;
+              if (iy < 0 || iy >= ih) continue;
+              for (int fx = 0; fx < kw; fx++) {
+                int ix = ox * sw - pl + fx;
+                if (ix < 0 || ix >= iw) continue;
+                const int8_t* xp = x + ((long)iy * iw + ix) * ic;
+                for (int ci = 0; ci < ic; ci++) {
+                  const int32_t xv = (int32_t)xp[ci] + in_off;
+                  const int32_t* __restrict__ wr = wt + ((long)(fy * kw + fx) * ic + ci) * oc;
+                  for (int co = 0; co < oc; co++) accv[co] += xv * wr[co];
+                }
+              }
+            }
+            int8_t* yp = y + ((long)oy * ow + ox) * oc;
+            for (int co = 0; co < oc; co++) {
+              const int32_t acc = mbqm(accv[co], mult[co], shift[co], R) + out_zp;
+              yp[co] = (int8_t)clampi(acc, p[BN_CONV_ACT_MIN], p[BN_CONV_ACT_MAX]);
+            }
+          }
+          free(accv); free(wt);
         }
       } break;
       case BN_OP_DWCONV2D: {
@@ -259,21 +310,29 @@ static int run_one(const bno_model* m, const float* input, float* output, void**
         const int32_t in_off = -p[BN_CONV_IN_ZP], out_zp = p[BN_CONV_OUT_ZP];
         const int ih = ti->dims[0], iw = ti->dims[1], C = ti->dims[2];
         const int oh = to->dims[0], ow = to->dims[1];
-        for (int oy = 0; oy < oh; oy++) for (int ox = 0; ox < ow; ox++) for (int c = 0; c < C; c++) {
-          int32_t acc = 0;
+        /* same sums as DepthwiseConvPerChannel's loop nest, with the channel loop innermost (taps outside the image are
+         * skipped exactly as there) so that it vectorises */
+        int32_t* __restrict__ accv = (int32_t*)malloc(sizeof(int32_t) * (size_t)C);
+        for (int oy = 0; oy < oh; oy++) for (int ox = 0; ox < ow; ox++) {
+          for (int c = 0; c < C; c++) accv[c] = bias[c];
           for (int fy = 0; fy < kh; fy++) {
             int iy = oy * sh - pt + fy;
             if (iy < 0 || iy >= ih) continue;
             for (int fx = 0; fx < kw; fx++) {
               int ix = ox * sw - pl + fx;
               if (ix < 0 || ix >= iw) continue;
-              acc += ((int32_t)x[((long)iy * iw + ix) * C + c] + in_off) * (int32_t)w[((long)fy * kw + fx) * C + c];
+              const int8_t* __restrict__ xp = x + ((long)iy * iw + ix) * C;
+              const int8_t* __restrict__ wp = w + ((long)fy * kw + fx) * C;
+              for (int c = 0; c < C; c++) accv[c] += ((int32_t)xp[c] + in_off) * (int32_t)wp[c];
             }
           }
-          acc += bias[c];
-          acc = mbqm(acc, mult[c], shift[c], R) + out_zp;
-          y[((long)oy * ow + ox) * C + c] = (int8_t)clampi(acc, p[BN_CONV_ACT_MIN], p[BN_CONV_ACT_MAX]);
+          int8_t* yp = y + ((long)oy * ow + ox) * C;
+          for (int c = 0; c < C; c++) {
+            const int32_t acc = mbqm(accv[c], mult[c], shift[c], R) + out_zp;
+            yp[c] = (int8_t)clampi(acc, p[BN_CONV_ACT_MIN], p[BN_CONV_ACT_MAX]);
+          }
         }
+        free(accv);
       } break;
       case BN_OP_FC: {
         /* reference_integer_ops::FullyConnectedPerChannel; weights [N,K]; applied to each
@@ -304,11 +363,16 @@ static int run_one(const bno_model* m, const float* input, float* output, void**
         const int C = to->dims[2];
         const long n = (long)to->nbytes;
         const int bc = p[BN_ADD_BCAST];
+        /* scaled_input = MBQM((x - zp) << left_shift, m, s) is a function of the int8 code alone (per-tensor scales):
+         * the same expression evaluated once per code instead of once per element */
+        int32_t t1[256], t2[256];
+        for (int q = -128; q < 128; q++) {
+          t1[q + 128] = mbqm((q - p[BN_ADD_IN1_ZP]) * (1 << p[BN_ADD_LEFT_SHIFT]), p[BN_ADD_M1], p[BN_ADD_S1], R);
+          t2[q + 128] = mbqm((q - p[BN_ADD_IN2_ZP]) * (1 << p[BN_ADD_LEFT_SHIFT]), p[BN_ADD_M2], p[BN_ADD_S2], R);
+        }
         for (long i = 0; i < n; i++) {
-          int32_t v1 = (int32_t)a[i] - p[BN_ADD_IN1_ZP];
-          int32_t v2 = (int32_t)b[bc ? (i % C) : i] - p[BN_ADD_IN2_ZP];
-          int32_t s1 = mbqm(v1 * (1 << p[BN_ADD_LEFT_SHIFT]), p[BN_ADD_M1], p[BN_ADD_S1], R);
-          int32_t s2 = mbqm(v2 * (1 << p[BN_ADD_LEFT_SHIFT]), p[BN_ADD_M2], p[BN_ADD_S2], R);
+          const int32_t s1 = t1[(int)a[i] + 128];
+          const int32_t s2 = t2[(int)b[bc ? (i % C) : i] + 128];
           int32_t o = mbqm(s1 + s2, p[BN_ADD_MO], p[BN_ADD_SO], R) + p[BN_ADD_OUT_ZP];
           y[i] = (int8_t)clampi(o, p[BN_ADD_ACT_MIN], p[BN_ADD_ACT_MAX]);
         }
@@ -425,6 +489,13 @@ static int run_one(const bno_model* m, const float* input, float* output, void**
         return -1;
     }
     if ((int)op->out == tap_slot && tap_out) memcpy(tap_out, buf[op->out], to->nbytes);
+    if (g_profile) {
+      struct timespec ts1;
+      clock_gettime(CLOCK_MONOTONIC, &ts1);
+      const double dt = (double)(ts1.tv_sec - ts0.tv_sec) + 1e-9 * (double)(ts1.tv_nsec - ts0.tv_nsec);
+      g_prof_s[op->kind & 31] += dt;
+      g_prof_op[oi & 255] += dt;
+    }
   }
   memcpy(output, buf[h->output_tensor], T[h->output_tensor].nbytes);
   return 0;

@@ -63,10 +63,12 @@ def blob(graph, cfg):
 
 @pytest.fixture(scope="session")
 def oracle_model(blob):
-    from oracle import bn_oracle
+    """The C oracle, running on requantisation constants the oracle derived itself from the `.tflite` scales
+    (`oracle/tflite_quant.py`), not on the integers the product's exporter wrote into the blob."""
+    from oracle import bn_oracle, tflite_quant
 
     bn_oracle.build()
-    return bn_oracle.OracleModel(blob)
+    return bn_oracle.OracleModel(tflite_quant.patch_blob(blob, tflite_quant.derive(TFLITE)))
 
 
 @pytest.fixture(scope="session")
