@@ -37,6 +37,14 @@ for _p in (ROOT, PKG):
 FIX = os.path.join(ROOT, "tests", "fixtures")
 BYTES_PER_CHUNK_ALG = 144_400          # 2*72000 B PCM in + 400 B scores out
 MACS_PER_CHUNK = 26_735_616
+# both arms print the same workload string (the driver compares `config.workload` of the two lines)
+WORKLOAD = ("config5: file-sharded evaluation of synthetic multi-chunk files (chunks/file ~ U{1..20}), "
+            "shipped birdnet_stm32n6_100 graph, 3 s / 24 kHz PCM16 chunks, LME pooling beta=10")
+# CUDA-core work per chunk that no tensor core or HBM bandwidth removes (SURVEY 8(d) "honest third bound"), counted as
+# warp instructions of the shipped kernels' inner loops: 256 real 512-point FFTs + |z| + min/max (K1), 65,792 quantisations
+# + 16,384 LUT epilogues (K2), 131,072 stem outputs x 9 taps (K3), 249,856 depthwise outputs, 311,296 pointwise
+# requantisations of which 188,416 carry TFLite's three-multiplier residual ADD (K45), MEAN + FC (K6).
+CUDA_CORE_WARP_INSTR_PER_CHUNK = 452_000
 
 
 def load_cfg_24k() -> dict:
@@ -144,12 +152,25 @@ def file_peaks_device(torch, pcm, offs_np):
 
 
 # ---------------------------------------------------------------------------------------------------
+def try_real_reference() -> str:
+    """use the real TFLite / librosa if this machine has them.  Returns what was found."""
+    found = []
+    for mod in ("tensorflow", "tflite_runtime", "ai_edge_litert", "librosa"):
+        try:
+            __import__(mod)
+            found.append(mod + " present")
+        except Exception:
+            found.append(mod + " absent")
+    return ", ".join(found)
+
+
 def cpu_port_throughput(cfg, blob, seconds_target: float, threads: int = 0):
-    """Oracle (CPU port of the reference path) on a bounded sample; returns (chunks/s, sample, cores)."""
+    """Oracle (CPU port of the reference path; built -O3 -march=native on THIS machine) on a bounded sample;
+    returns (chunks/s, sample description, threads used)."""
     from birdnet_stm32.audio import synth
     from oracle import bn_oracle
 
-    bn_oracle.build()
+    bn_oracle.use_native_build()
     cores = len(os.sched_getaffinity(0))
     use = threads or cores
     T = int(cfg["sample_rate"] * cfg["chunk_duration"])
@@ -169,7 +190,31 @@ def cpu_port_throughput(cfg, blob, seconds_target: float, threads: int = 0):
     n = int(max(n0, min(4096, n0 * seconds_target / max(dt, 1e-3))))
     n = (n + use - 1) // use * use
     dt = run(n)
-    return n / dt, f"{n} synthetic 3 s / {cfg['sample_rate']} Hz chunks, frontend + int8 graph + LME pooling, {dt:.1f} s", use
+    return n / dt, f"{n} synthetic 3 s / {cfg['sample_rate']} Hz chunks, frontend + int8 graph + LME pooling, {dt:.1f} s, {use} thread(s)", use
+
+
+def h2d_peak_gbs(torch, dev, nbytes: int, dist=None) -> float:
+    """Raw pinned host -> device copy rate of THIS box with all ranks copying at once: plain cudaMemcpyAsync of `nbytes`
+    per rank, best of 3, max time over ranks.  The ceiling the e2e leg is held against."""
+    n = int(min(nbytes, 1 << 30))
+    h = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    d = torch.empty(n, dtype=torch.uint8, device=dev)
+    best = None
+    for _ in range(4):
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        d.copy_(h, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = float(ms.item())
+        best = ms if best is None else min(best, ms)
+    return n / (best / 1e3) / 1e9
 
 
 def run_reference(args):
@@ -182,20 +227,23 @@ def run_reference(args):
     sample = ""
     cores = 0
     total_steps = args.steps + args.warmup
-    budget = min(20.0, 150.0 / max(total_steps, 1))
+    budget = min(20.0, 120.0 / max(total_steps, 1))
     for i in range(total_steps):
         v, sample, cores = cpu_port_throughput(cfg, blob, seconds_target=budget)
         if i >= args.warmup:
             per_step.append(v)
     value = float(np.mean(per_step))
+    one_thread, one_sample, _ = cpu_port_throughput(cfg, blob, seconds_target=8.0, threads=1)
     line = {
         "impl": "reference", "metric": "3s audio chunks/sec (STFT+int8 DS-CNN)", "value": value, "unit": "chunks/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8 (fp64 FFT frontend)",
         "data": "synthetic",
-        "config": {"workload": "config5: synthetic multi-chunk files, shipped DS-CNN graph, 3 s / 24 kHz chunks, LME pooling",
-                   "note": "CPU port (oracle/) of the reference TFLite + librosa path; TensorFlow/librosa are not installable in this image"},
-        "cpu_baseline": {"value": value, "unit": "chunks/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD,
+                   "note": "CPU port (oracle/, gcc -O3 -march=native, OpenMP over chunks) of the reference TFLite + librosa path; "
+                           "TensorFlow/librosa are not installable in this image (import attempts: " + try_real_reference() + ")"},
+        "cpu_baseline": {"value": value, "unit": "chunks/s", "cores": cores, "kind": "port", "sample": sample,
+                         "one_thread": {"value": one_thread, "sample": one_sample}},
         "e2e": {"value": value, "unit": "chunks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -312,6 +360,8 @@ def run_b200(args):
     same = bool(np.array_equal(host_scores, out.cpu().numpy()))
     h2d = n_chunks * T * 2 + n_chunks * 4 + (F + 1) * 4
     d2h = F * C * 4
+    h2d_peak = h2d_peak_gbs(torch, dev, h2d, dist)           # per rank, all ranks copying concurrently
+    e2e_gbs_per_rank = e2e_value / world * (T * 2 + 4) / 1e9
 
     if rank != 0:
         if dist is not None:
@@ -332,46 +382,62 @@ def run_b200(args):
     # chunks one launch of that kernel processes (every kernel runs once per wave; the last wave of a step is partial)
     chunks_per_launch = n_chunks * args.steps / max(dom[1][1], 1)
     achieved = BYTES_PER_CHUNK_ALG * chunks_per_launch / (dom_ms_per_launch / 1e3) / 1e9
-    # DRAM bytes per launch of the same kernel from the committed `ncu --set full` capture (profiles/r1/ncu_traffic.json)
+    # DRAM bytes per launch of the same kernel: NOT measured in this run (ncu cannot wrap a timed run).  Taken from the
+    # committed `ncu --set full` capture of the same kernel at the bench's wave size (profiles/r2/ncu_traffic.json names
+    # the commit it was captured on); null when no capture of this kernel exists.
     traffic = None
+    traffic_src = None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1", "ncu_traffic.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r2", "ncu_traffic.json")))
         ent = tr.get(dom[0])
-        if ent:   # per-chunk DRAM bytes of the captured launch x the chunks an average launch of this run processed
+        if ent:
             traffic = ent["dram_bytes_per_launch"] / ent["chunks_per_launch"] * chunks_per_launch
+            traffic_src = f"ncu --set full capture, commit {tr.get('commit', '?')}, {ent['chunks_per_launch']} chunks per launch (profiles/r2/ncu_traffic.json); scaled by chunks per launch"
     except Exception:
         pass
+    sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
+    issue_peak = 148 * 4 * sm_clock * 1e6                 # warp instructions / s at 1 per scheduler per clock
+    third = {"what": "CUDA-core instruction issue (FP32 FFT, depthwise / stem taps, fixed-point requantisation): warp instructions "
+                     "per chunk of the shipped kernels' inner loops / (148 SMs x 4 schedulers x SM clock)",
+             "warp_instr_per_chunk": CUDA_CORE_WARP_INSTR_PER_CHUNK, "sm_mhz": sm_clock,
+             "bound_chunks_per_s": issue_peak / CUDA_CORE_WARP_INSTR_PER_CHUNK,
+             "frac": value / world / (issue_peak / CUDA_CORE_WARP_INSTR_PER_CHUNK)}
     roofline = {
-        "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
+        "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic, "traffic_source": traffic_src,
         "peak_source": peak_src, "kernel": dom[0], "kernel_share_of_step": dom[1][0] / tot_ms,
         "kernel_ms_per_launch": dom_ms_per_launch, "chunks_per_launch": chunks_per_launch,
         "path_achieved_gbs": value / world * BYTES_PER_CHUNK_ALG / 1e9,
         "path_frac": value / world * BYTES_PER_CHUNK_ALG / 1e9 / hbm,
         "int8_tmacs_achieved": value / world * MACS_PER_CHUNK / 1e12,
+        "cuda_core_bound": third,
         "kernels_ms": {k: round(v[0] / max(args.steps, 1), 4) for k, v in sorted(prof.items())},
     }
 
-    cpu_v, cpu_sample, cpu_cores = cpu_port_throughput(cfg, blob, seconds_target=15.0) if world == 1 and not args.no_cpu else (None, "skipped", 0)
+    cpu_v, cpu_sample, cpu_cores = cpu_port_throughput(cfg, blob, seconds_target=12.0) if world == 1 and not args.no_cpu else (None, "skipped", 0)
+    cpu_1, cpu_1_sample, _ = cpu_port_throughput(cfg, blob, seconds_target=6.0, threads=1) if cpu_v is not None else (None, "", 0)
 
     line = {
         "metric": "3s audio chunks/sec (STFT+int8 DS-CNN)", "value": value, "unit": "chunks/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int8 (int32 accumulate, fp32 STFT frontend)",
         "data": "synthetic",
-        "config": {"workload": "config5: file-sharded evaluation of synthetic multi-chunk files (chunks/file ~ U{1..20}), "
-                               "shipped birdnet_stm32n6_100 graph, 3 s / 24 kHz PCM16 chunks, LME pooling beta=10",
+        "config": {"workload": WORKLOAD,
                    "files_per_gpu_per_step": F, "chunks_per_gpu_per_step": n_chunks, "wave": runner.query().wave,
                    "fast_path": int(runner.query().fast_path),
                    "l2": f"inputs ({n_chunks * T * 2 / 1e9:.2f} GB PCM per step) are larger than L2, no flush needed",
                    "parallelism": f"file-sharded x{world}, one all-gather of pooled scores per step"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "chunks/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "matches_device_run": same},
+                "steps": e2e_steps, "matches_device_run": same,
+                "h2d_peak_gbs": h2d_peak, "h2d_achieved_gbs": e2e_gbs_per_rank, "frac": e2e_gbs_per_rank / h2d_peak,
+                "h2d_note": "per GPU; peak = plain pinned cudaMemcpyAsync of one step's input bytes on all ranks at once, best of 4"},
         "gpu_launches": int(launches),
         "roofline": roofline,
     }
     if cpu_v is not None:
-        line["cpu_baseline"] = {"value": cpu_v, "unit": "chunks/s", "cores": cpu_cores, "kind": "port", "sample": cpu_sample}
+        line["cpu_baseline"] = {"value": cpu_v, "unit": "chunks/s", "cores": cpu_cores, "kind": "port", "sample": cpu_sample,
+                                "one_thread": {"value": cpu_1, "sample": cpu_1_sample},
+                                "real_reference": try_real_reference()}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

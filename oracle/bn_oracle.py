@@ -29,6 +29,20 @@ def build(force: bool = False) -> str:
     return _LIB_PATH
 
 
+def use_native_build() -> str:
+    """Switch to `libbn_oracle_native.so` (-O3 -march=native), compiled on THIS machine -- the build bench.py times for
+    `cpu_baseline` / `--impl reference`.  Must be called before the first `lib()` use; falls back to the portable build."""
+    global _LIB_PATH, _lib
+    native = os.path.join(_HERE, "libbn_oracle_native.so")
+    try:
+        subprocess.run(["make", "-C", _HERE, "-B", "native"], check=True, capture_output=True)
+        if _lib is None or _LIB_PATH != native:
+            _LIB_PATH, _lib = native, None
+    except Exception:
+        pass
+    return _LIB_PATH
+
+
 def lib():
     global _lib
     if _lib is None:
