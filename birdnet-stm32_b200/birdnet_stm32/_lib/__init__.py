@@ -72,7 +72,7 @@ class BnReaderFile(C.Structure):
 
     _fields_ = [
         ("status", C.c_int32), ("n_chunks", C.c_int32), ("sample_rate", C.c_int32), ("channels", C.c_int32), ("fmt", C.c_int32),
-        ("peak", C.c_float), ("n_frames", C.c_int64), ("data_offset", C.c_int64),
+        ("peak", C.c_float), ("n_frames", C.c_int64), ("data_offset", C.c_int64), ("container", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

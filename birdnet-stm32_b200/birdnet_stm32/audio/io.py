@@ -10,14 +10,14 @@ Semantics follow the reference `birdnet_stm32/audio/io.py`:
     step = int(sr * (cd - overlap)) with overlap clamped to [0, cd - 0.1], plus an end-anchored
     tail chunk when samples remain.
 
-Container parsing is done here (RIFF/WAVE: PCM 8/16/24/32-bit and IEEE float32, any channel count;
-soundfile/libsndfile are not part of this image).  Mono 16-bit files at the model rate take the PCM16 path
+Container parsing is done here (RIFF/WAVE: PCM 8/16/24/32-bit and IEEE float32, any channel count) and, for FLAC, by
+the native decoder of the reader (`csrc/bn_flac.h`, RFC 9639; soundfile/libsndfile are not part of this image).  Mono 16-bit files at the model rate take the PCM16 path
 above.  Everything else -- other sample rates, several channels, other sample formats -- is what the
 reference handles with `y.mean(axis=1)` + `scipy.signal.resample_poly` on the host (`io.py:118-120`); here
 the raw interleaved samples go to the device once and `bn_ingest_*` (`audio/ingest.py`, `csrc/bn_ingest.cu`)
-decodes, mixes, resamples, peak-normalises and chunks them on the GPU.  Non-WAV containers raise
+decodes, mixes, resamples, peak-normalises and chunks them on the GPU.  Lossy containers (MP3 / OGG / M4A) raise
 `UnsupportedAudio`; `evaluate()` skips them the way the reference skips unreadable files
-(`metrics.py:125-126`) and counts them.
+(`metrics.py:125-126`), counts them by reason and, with `strict_files=True`, raises instead.
 """
 
 from __future__ import annotations
@@ -72,8 +72,43 @@ def split_audio_into_chunks(audio: np.ndarray, sample_rate: int = 24000, chunk_d
     return out
 
 
+def is_flac(path: str) -> bool:
+    try:
+        with open(path, "rb") as fh:
+            head = fh.read(4)
+    except OSError:
+        return False
+    return head == b"fLaC" or head[:3] == b"ID3"
+
+
+def read_flac_frames(path: str, max_seconds: float | None = None) -> tuple[np.ndarray, str, int, int]:
+    """FLAC -> (interleaved samples left-justified in int16 / int32, "s16" | "s32", channels, sample_rate), decoded by the
+    native reader (`bn_read_raw_batch`).  (s << (16 - bits)) / 32768 is the float libsndfile hands the reference."""
+    from birdnet_stm32.audio import reader as _rd
+
+    info = _rd.probe(path, float(max_seconds or 0.0))
+    if info.status == _rd.RD_UNREADABLE or info.container != 1:
+        raise UnsupportedAudio(f"{path}: not a decodable FLAC stream")
+    nbytes = int(info.n_frames) * int(info.channels) * (2 if _rd.FMT_NAMES[info.fmt] == "s16" else 4)
+    buf = np.empty(nbytes + 16, dtype=np.uint8)
+    n, items = _rd.read_raw_batch([path], buf, max_seconds=float(max_seconds or 0.0), threads=1)
+    if n != 1 or items[0] is None:
+        raise UnsupportedAudio(f"{path}: FLAC decode failed")
+    raw, kind, ch, sr = items[0]
+    return raw.copy(), kind, ch, sr
+
+
 def read_wav_pcm16(path: str, max_frames: int | None = None) -> tuple[np.ndarray, int]:
-    """Mono 16-bit PCM WAV -> (int16 [frames], sample_rate).  Anything else raises UnsupportedAudio."""
+    """Mono PCM of <= 16 bits (WAV, FLAC) -> (int16 [frames], sample_rate).  Anything else raises UnsupportedAudio."""
+    if is_flac(path):
+        from birdnet_stm32.audio import reader as _rd
+
+        info = _rd.probe(path, 0.0)
+        if info.status == _rd.RD_UNREADABLE or info.channels != 1 or _rd.FMT_NAMES.get(info.fmt) != "s16":
+            raise UnsupportedAudio(f"{path}: FLAC stream is not mono with <= 16 bits per sample")
+        secs = None if max_frames is None else (max_frames + 0.5) / float(info.sample_rate)
+        raw, _, _, sr = read_flac_frames(path, secs)
+        return (raw if max_frames is None else raw[:max_frames]).astype(np.int16, copy=False), sr
     try:
         with wave.open(path, "rb") as wf:
             if wf.getsampwidth() != 2 or wf.getcomptype() != "NONE":
@@ -94,10 +129,12 @@ def read_wav_frames(path: str, max_seconds: float | None = None) -> tuple[np.nda
     sample, packed) / int32 / float32 / uint8 with `frames * channels` samples.  `max_seconds` limits the read to
     `int(min(frames, max_seconds * sr))` frames from the start, the window `load_audio_window` reads (`io.py:97-109`).
     """
+    if is_flac(path):
+        return read_flac_frames(path, max_seconds)
     with open(path, "rb") as fh:
         head = fh.read(12)
         if len(head) < 12 or head[:4] != b"RIFF" or head[8:12] != b"WAVE":
-            raise UnsupportedAudio(f"{path}: not a RIFF/WAVE file")
+            raise UnsupportedAudio(f"{path}: not a RIFF/WAVE or FLAC file")
         fmt = None
         while True:
             hdr = fh.read(8)

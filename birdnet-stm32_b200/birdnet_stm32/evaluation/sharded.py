@@ -72,19 +72,79 @@ def evaluate_sharded(model_runner, files: list[str], classes: list[str], cfg: di
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank() if world > 1 else 0
     mine = shard_files(files, world, rank)
+    from birdnet_stm32.evaluation.metrics import NoValidSamples
+
+    local_metrics: dict = {}
     try:
-        _, per_file, y_true, y_scores = evaluate(model_runner, mine, classes, cfg, **kw)
+        local_metrics, per_file, y_true, y_scores = evaluate(model_runner, mine, classes, cfg, **kw)
         labels = y_true.argmax(axis=1).astype(np.int32)
-    except RuntimeError:
+    except NoValidSamples:
+        # only "this rank's shard holds no scorable file" is tolerated; engine / CUDA / reader errors propagate so that every
+        # rank aborts instead of silently computing the metrics of a partial dataset
         per_file, y_scores, labels = [], np.zeros((0, len(classes)), np.float32), np.zeros((0,), np.int32)
     scores_g, labels_g = gather_scores(y_scores, labels)
     if scores_g.shape[0] == 0:
-        raise RuntimeError("No valid test samples found for the provided class set.")
+        raise NoValidSamples("No valid test samples found for the provided class set.")
     y_true_g = np.zeros((labels_g.shape[0], len(classes)), dtype=np.float32)
     y_true_g[np.arange(labels_g.shape[0]), labels_g] = 1.0
     if kw.get("metrics_backend", "sklearn") == "device":
         # the gathered [F, C] matrix goes back to this rank's GPU once: sort / count / accumulate there (bn_metrics_compute)
         from birdnet_stm32.evaluation.device_metrics import metrics_from_scores_device
 
-        return metrics_from_scores_device(y_true_g, scores_g, int(getattr(model_runner, "device", 0))), per_file, y_true_g, scores_g
-    return _metrics_from_scores(y_true_g, scores_g), per_file, y_true_g, scores_g
+        metrics = metrics_from_scores_device(y_true_g, scores_g, int(getattr(model_runner, "device", 0)))
+    else:
+        metrics = _metrics_from_scores(y_true_g, scores_g)
+    metrics.update(reduce_run_stats(local_metrics))
+    return metrics, per_file, y_true_g, scores_g
+
+
+def reduce_run_stats(local: dict) -> dict:
+    """Skipped-file counts, chunk totals and latency statistics of all ranks: sums for the counters, chunk-weighted mean
+    for the mean latency, maximum for the percentiles and the memory figures (an upper bound: the per-chunk samples stay
+    on their rank)."""
+    import torch
+    import torch.distributed as dist
+
+    keys_sum = ["skipped_files", "total_chunks"]
+    keys_max = ["latency_median_ms", "latency_p95_ms", "latency_p99_ms", "peak_rss_mb", "rss_delta_mb"]
+    reasons = sorted((local.get("skipped_by_reason") or {}).items())
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return {k: local[k] for k in keys_sum + keys_max + ["latency_mean_ms", "skipped_by_reason"] if k in local}
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    chunks = float(local.get("total_chunks", 0))
+    vec = [float(local.get(k, 0.0)) for k in keys_sum] + [float(local.get("latency_mean_ms", 0.0)) * chunks]
+    t_sum = torch.tensor(vec, dtype=torch.float64, device=dev)
+    t_max = torch.tensor([float(local.get(k, 0.0)) for k in keys_max], dtype=torch.float64, device=dev)
+    dist.all_reduce(t_sum)
+    dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+    gathered: list = [None] * dist.get_world_size()
+    dist.all_gather_object(gathered, reasons)
+    out: dict = {}
+    for k, v in zip(keys_sum, t_sum.tolist()):
+        if v:
+            out[k] = int(v)
+    if out.get("total_chunks") and "latency_mean_ms" in local or t_sum[2].item() > 0:
+        tot = t_sum[1].item()
+        if tot > 0 and t_sum[2].item() > 0:
+            out["latency_mean_ms"] = t_sum[2].item() / tot
+    for k, v in zip(keys_max, t_max.tolist()):
+        if v:
+            out[k] = v
+    merged: dict = {}
+    for r in gathered:
+        for why, n in (r or []):
+            merged[why] = merged.get(why, 0) + int(n)
+    if merged:
+        out["skipped_by_reason"] = merged
+    return out
+
+
+def gather_per_file(per_file: list[dict]) -> list[dict]:
+    """Rank-local `per_file` rows of every rank, concatenated in rank order (for the predictions CSV)."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return per_file
+    parts: list = [None] * dist.get_world_size()
+    dist.all_gather_object(parts, per_file)
+    return [row for part in parts for row in (part or [])]

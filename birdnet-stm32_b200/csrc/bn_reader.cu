@@ -1,4 +1,4 @@
-// bn_reader.cu -- native, multi-threaded WAV reader feeding the PCM16 batch buffer (host code only; compiled by nvcc with
+// bn_reader.cu -- native, multi-threaded WAV / FLAC reader feeding the PCM16 batch buffer (host code only; compiled by nvcc with
 // the rest of the library, no kernels).
 //
 // Reference: the per-file host work of evaluate() before any inference -- sf.info / SoundFile.read
@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "../../include/bn_ingest.h"
+#include "bn_flac.h"
 #include "bn_kernels.cuh"
 
 namespace {
@@ -37,6 +38,64 @@ bool pread_all(int fd, void* dst, size_t n, off_t off) {
   return true;
 }
 
+bool read_whole(int fd, std::vector<unsigned char>& buf) {
+  struct stat st;
+  if (fstat(fd, &st) != 0 || st.st_size <= 0) return false;
+  buf.resize((size_t)st.st_size);
+  return pread_all(fd, buf.data(), buf.size(), 0);
+}
+
+// FLAC: STREAMINFO gives rate / channels / sample size / frame count; the samples are decoded in phase 2 (bn_flac.h).
+// Samples are delivered left-justified in int16 (<= 16 bits) or int32 containers = BN_SF_S16 / BN_SF_S32.
+bool probe_flac(int fd, off_t file_size, double max_seconds, bn_reader_file* o) {
+  unsigned char h[10];
+  if (!pread_all(fd, h, 10, 0)) return false;
+  off_t pos = 0;
+  if (memcmp(h, "ID3", 3) == 0) {
+    const off_t sz = ((off_t)(h[6] & 0x7f) << 21) | ((off_t)(h[7] & 0x7f) << 14) | ((off_t)(h[8] & 0x7f) << 7) | (off_t)(h[9] & 0x7f);
+    pos = 10 + sz + ((h[5] & 0x10) ? 10 : 0);
+  }
+  unsigned char m[42];
+  if (pos + 42 > file_size || !pread_all(fd, m, 42, pos)) return false;
+  bnflac::Info info;
+  std::string err;
+  unsigned char last_flagged[42];
+  memcpy(last_flagged, m, 42);
+  last_flagged[4] |= 0x80;                              // parse just this block
+  if (!bnflac::parse_header(last_flagged, 42, info, err)) return false;
+  int64_t frames = (int64_t)info.total;
+  if (frames == 0) {                                    // length not recorded: count by decoding
+    std::vector<unsigned char> all;
+    std::vector<int16_t> o16;
+    std::vector<int32_t> o32;
+    if (!read_whole(fd, all)) return false;
+    frames = bnflac::decode(all.data(), all.size(), 0, info, &o16, &o32, err);
+    if (frames < 0) return false;
+  }
+  o->channels = info.channels;
+  o->sample_rate = info.sample_rate;
+  o->fmt = info.bps <= 16 ? BN_SF_S16 : BN_SF_S32;
+  if (max_seconds > 0) {
+    const int64_t lim = (int64_t)(max_seconds * (double)info.sample_rate);
+    if (frames > lim) frames = lim;
+  }
+  o->n_frames = frames;
+  o->data_offset = 0;
+  o->container = BN_CT_FLAC;
+  o->status = BN_RD_NEEDS_INGEST;
+  return true;
+}
+
+// Decode the first o.n_frames frames of a FLAC file; exactly one of out16 / out32 is filled according to o.fmt.
+bool decode_flac_fd(int fd, const bn_reader_file& o, std::vector<int16_t>& out16, std::vector<int32_t>& out32) {
+  std::vector<unsigned char> all;
+  if (!read_whole(fd, all)) return false;
+  bnflac::Info info;
+  std::string err;
+  const int64_t got = bnflac::decode(all.data(), all.size(), o.n_frames, info, &out16, &out32, err);
+  return got == o.n_frames && info.channels == o.channels;
+}
+
 // RIFF/WAVE header walk: fmt chunk (PCM, IEEE float, or WAVE_FORMAT_EXTENSIBLE with one of them as sub-format) and data chunk
 bool probe_fd(int fd, double max_seconds, bn_reader_file* o) {
   memset(o, 0, sizeof *o);
@@ -45,7 +104,9 @@ bool probe_fd(int fd, double max_seconds, bn_reader_file* o) {
   struct stat st;
   if (fstat(fd, &st) != 0) return false;
   unsigned char h[12];
-  if (!pread_all(fd, h, 12, 0) || memcmp(h, "RIFF", 4) != 0 || memcmp(h + 8, "WAVE", 4) != 0) return false;
+  if (!pread_all(fd, h, 12, 0)) return false;
+  if (memcmp(h, "fLaC", 4) == 0 || memcmp(h, "ID3", 3) == 0) return probe_flac(fd, st.st_size, max_seconds, o);
+  if (memcmp(h, "RIFF", 4) != 0 || memcmp(h + 8, "WAVE", 4) != 0) return false;
   off_t pos = 12;
   int tag = 0, bits = 0;
   bool have_fmt = false;
@@ -152,7 +213,12 @@ extern "C" int bn_read_pcm16_batch(const char* const* paths, int n_paths, int sa
     bool ok = fd >= 0;
     std::vector<int16_t> tmp;
     const int16_t* src = nullptr;
-    if (ok) {
+    if (ok && o->container == BN_CT_FLAC) {
+      std::vector<int32_t> unused;
+      ok = decode_flac_fd(fd, *o, tmp, unused);
+      if (ok && (n <= chunk_len || step == chunk_len)) { memcpy(dst, tmp.data(), (size_t)n * 2); src = dst; }
+      else src = tmp.data();
+    } else if (ok) {
       if (n <= chunk_len || step == chunk_len) {
         // back-to-back chunks: the window is read straight into place (the first n samples ARE the full chunks)
         ok = pread_all(fd, dst, (size_t)n * 2, (off_t)o->data_offset);
@@ -218,7 +284,15 @@ extern "C" int bn_read_raw_batch(const char* const* paths, int n_paths, double m
     if (o->status == BN_RD_UNREADABLE) return;
     const int64_t nb = o->n_frames * o->channels * bytes_per_sample[o->fmt];
     const int fd = open(paths[i], O_RDONLY | O_CLOEXEC);
-    const bool ok = fd >= 0 && pread_all(fd, (unsigned char*)dst + byte_offsets[i], (size_t)nb, (off_t)o->data_offset);
+    bool ok = fd >= 0;
+    if (ok && o->container == BN_CT_FLAC) {
+      std::vector<int16_t> o16;
+      std::vector<int32_t> o32;
+      ok = decode_flac_fd(fd, *o, o16, o32);
+      if (ok) memcpy((unsigned char*)dst + byte_offsets[i], o->fmt == BN_SF_S16 ? (const void*)o16.data() : (const void*)o32.data(), (size_t)nb);
+    } else if (ok) {
+      ok = pread_all(fd, (unsigned char*)dst + byte_offsets[i], (size_t)nb, (off_t)o->data_offset);
+    }
     if (fd >= 0) close(fd);
     if (!ok) o->status = BN_RD_UNREADABLE;
   });

@@ -8,9 +8,10 @@
  *   split_audio_into_chunks                  audio/io.py:133-174       chunks written straight into the caller's (pinned)
  *   per-file list building in evaluate()     metrics.py:117-147        batch buffer in file order
  *
- * Scope: mono 16-bit PCM files at the model rate are turned into int16 chunks ready for bn_infer_pool; every other WAV
- * (other rate, several channels, 8 / 24 / 32-bit, float) is reported with status BN_RD_NEEDS_INGEST so that the caller
- * sends it through bn_ingest_chunks; anything else is BN_RD_UNREADABLE (the reference skips such files, metrics.py:125-126).
+ * Scope: RIFF/WAVE and FLAC (RFC 9639, decoded by csrc/bn_flac.h).  Mono files of <= 16 bits at the model rate are turned
+ * into int16 chunks ready for bn_infer_pool; every other file (other rate, several channels, 8 / 24 / 32-bit, float) is
+ * reported with status BN_RD_NEEDS_INGEST so that the caller sends it through bn_ingest_chunks; anything else (MP3, OGG,
+ * M4A: lossy codecs, no decoder here) is BN_RD_UNREADABLE (the reference skips unreadable files, metrics.py:125-126).
  */
 #ifndef BN_READER_H
 #define BN_READER_H
@@ -25,6 +26,7 @@ extern "C" {
 #endif
 
 enum { BN_RD_OK = 0, BN_RD_NEEDS_INGEST = 1, BN_RD_UNREADABLE = 2 };
+enum { BN_CT_WAV = 0, BN_CT_FLAC = 1 };   /* container */
 
 typedef struct bn_reader_file {
   int32_t status;       /* BN_RD_* */
@@ -34,10 +36,13 @@ typedef struct bn_reader_file {
   int32_t fmt;          /* BN_SF_* of bn_ingest.h, -1 if not a supported sample format */
   float peak;           /* max|s| / 32768 over the window read (BN_RD_OK) */
   int64_t n_frames;     /* frames in the window: min(frames in file, int(max_seconds * sample_rate)) */
-  int64_t data_offset;  /* byte offset of the sample data in the file */
+  int64_t data_offset;  /* byte offset of the sample data in the file (WAV) */
+  int32_t container;    /* BN_CT_*: RIFF/WAVE, or FLAC (decoded by the reader; fmt is then the container the decoded samples
+                           are delivered in: S16 for streams of <= 16 bits, S32 above, left-justified) */
+  int32_t reserved;
 } bn_reader_file;
 
-/* Header of one file. */
+/* Header of one file (WAV or FLAC). */
 BN_API int bn_wav_probe(const char* path, double max_seconds, bn_reader_file* out);
 
 /* Reads paths[0 ..] in order into `chunks` (int16 [cap_chunks, chunk_len], host memory, ideally from bn_host_alloc) until
