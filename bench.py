@@ -193,6 +193,51 @@ def cpu_port_throughput(cfg, blob, seconds_target: float, threads: int = 0):
     return n / dt, f"{n} synthetic 3 s / {cfg['sample_rate']} Hz chunks, frontend + int8 graph + LME pooling, {dt:.1f} s, {use} thread(s)", use
 
 
+def e2e_files_leg(runner, cfg, n_files: int, io_workers: int) -> dict:
+    """The reference's real entry point on real files: `evaluate()` (evaluation/metrics.py:75-207 in the reference) over
+    synthetic mono 16-bit WAV files of 1..20 chunks, served from the page cache, read by the native C++ reader straight
+    into pinned batch buffers, classified and pooled on the device, metric tail included."""
+    import shutil
+    import tempfile
+    import wave
+
+    from birdnet_stm32.audio import synth
+    from birdnet_stm32.evaluation.metrics import evaluate
+
+    sr = int(cfg["sample_rate"])
+    T = int(sr * cfg["chunk_duration"])
+    classes = list(cfg.get("class_names") or [f"c{i}" for i in range(100)])[:100]
+    rng = np.random.default_rng(7)
+    root = tempfile.mkdtemp(prefix="bn_e2e_files_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    base = synth.synth_pcm16(24, T, sr, seed=5)                   # a pool of chunks; files are random runs of it
+    files, n_chunks = [], 0
+    try:
+        for i in range(n_files):
+            k = int(rng.integers(1, 21))
+            label = classes[int(rng.integers(0, len(classes)))]
+            os.makedirs(os.path.join(root, label), exist_ok=True)
+            p = os.path.join(root, label, f"f{i:05d}.wav")
+            pcm = base[rng.integers(0, len(base), size=k)].reshape(-1)[: k * T - int(rng.integers(0, T // 2))]
+            with wave.open(p, "wb") as wf:
+                wf.setnchannels(1)
+                wf.setsampwidth(2)
+                wf.setframerate(sr)
+                wf.writeframes(pcm.tobytes())
+            files.append(p)
+            n_chunks += k
+        ecfg = dict(cfg, class_names=classes)
+        evaluate(runner, files[: min(64, n_files)], classes, ecfg, pooling="lme", io_workers=io_workers)      # warm-up
+        t0 = time.perf_counter()
+        metrics, per_file, _, _ = evaluate(runner, files, classes, ecfg, pooling="lme", io_workers=io_workers)
+        dt = time.perf_counter() - t0
+        return {"value": n_chunks / dt, "unit": "chunks/s", "files": len(per_file), "chunks": n_chunks, "files_per_s": len(per_file) / dt,
+                "seconds": dt, "reader": "native (bn_read_pcm16_batch)", "reader_threads": io_workers, "pooling": "lme",
+                "bytes_read": int(sum(os.path.getsize(f) for f in files)), "skipped_files": metrics.get("skipped_files", 0),
+                "what": "evaluate() on synthetic mono PCM16 WAV files in the page cache: read + chunk + H2D + inference + pooling + metrics"}
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
 def h2d_peak_gbs(torch, dev, nbytes: int, dist=None) -> float:
     """Raw pinned host -> device copy rate of THIS box with all ranks copying at once: plain cudaMemcpyAsync of `nbytes`
     per rank, best of 3, max time over ranks.  The ceiling the e2e leg is held against."""
@@ -286,6 +331,8 @@ def run_b200(args):
         from birdnet_stm32 import _lib as _L
 
         runner.set_option(_L.BN_OPT_HOST_WAVE, args.host_wave)
+    if args.fusion >= 0:
+        runner.set_option(L.BN_OPT_FUSION, args.fusion)
     pcm = synth_device_pcm(torch, n_chunks, T, cfg["sample_rate"], seed=2024 + rank, device=dev)
     peak = file_peaks_device(torch, pcm, offs_np)
     offs = torch.as_tensor(offs_np, device=dev)
@@ -413,6 +460,12 @@ def run_b200(args):
         "kernels_ms": {k: round(v[0] / max(args.steps, 1), 4) for k, v in sorted(prof.items())},
     }
 
+    files_leg = None
+    if world == 1 and not args.no_files:
+        try:
+            files_leg = e2e_files_leg(runner, cfg, args.eval_files, io_workers=min(16, len(os.sched_getaffinity(0))))
+        except Exception as exc:                       # the headline numbers do not depend on this leg
+            files_leg = {"error": f"{type(exc).__name__}: {exc}"}
     cpu_v, cpu_sample, cpu_cores = cpu_port_throughput(cfg, blob, seconds_target=12.0) if world == 1 and not args.no_cpu else (None, "skipped", 0)
     cpu_1, cpu_1_sample, _ = cpu_port_throughput(cfg, blob, seconds_target=6.0, threads=1) if cpu_v is not None else (None, "", 0)
 
@@ -434,6 +487,8 @@ def run_b200(args):
         "gpu_launches": int(launches),
         "roofline": roofline,
     }
+    if files_leg is not None:
+        line["e2e_files"] = files_leg
     if cpu_v is not None:
         line["cpu_baseline"] = {"value": cpu_v, "unit": "chunks/s", "cores": cpu_cores, "kind": "port", "sample": cpu_sample,
                                 "one_thread": {"value": cpu_1, "sample": cpu_1_sample},
@@ -452,7 +507,10 @@ def main():
     ap.add_argument("--files", type=int, default=2048, help="files per GPU per step")
     ap.add_argument("--wave", type=int, default=0, help="chunks per engine wave (0 = engine default)")
     ap.add_argument("--host-wave", type=int, default=0, help="chunks per wave for host-memory inputs, e2e leg (0 = engine default)")
+    ap.add_argument("--fusion", type=int, default=-1, help="BN_OPT_FUSION bit mask (A/B runs; -1 = engine default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-files", action="store_true", help="skip the e2e_files leg (evaluate() on WAV files)")
+    ap.add_argument("--eval-files", type=int, default=768, help="files of the e2e_files leg")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

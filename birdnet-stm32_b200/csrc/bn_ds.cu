@@ -36,11 +36,28 @@ __device__ __forceinline__ int rq64(int acc, int c_lo, int c_hi, int mult, int r
   return (v + rz + (v >> 31)) >> n;
 }
 __device__ __forceinline__ int clamp2(int v, int lo, int hi) { return max(lo, min(v, hi)); }
+// hi32(a * b) + c as one IMAD.HI (FMA pipe); b is a run-time value so that the compiler cannot turn it back into a shift
+__device__ __forceinline__ int mad_hi(int a, int b, int c) {
+  int r;
+  asm("mad.hi.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+// max(0, min(a, b)): VIMNMX.RELU
+__device__ __forceinline__ int min_relu(int a, int b) {
+  int r;
+  asm("min.relu.s32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
 // MB = resident CTAs per SM the register allocation is sized for: 2 (128 registers) or 3 (80 registers; only the
 // transposed depthwise fits that without meaningful spilling).
 // NT = threads per CTA: 256, or 512 for the late layers whose shared-memory footprint (64 KB weight image, four-chunk tiles)
 // leaves one CTA per SM -- 16 warps instead of 8 to hide the phase latencies.
-template <int S, int TR, int ADD, int DWT, int MB, int NT>
+// EPI (ADD == 2 only): residual-ADD epilogue variant.  0 = shifts and clamps on the ALU pipe (round 1); 1 = "multiply-high"
+// form: every arithmetic right shift is an IMAD.HI by a power of two and SRDHM's >> 31 is folded into a wrapped doubled
+// multiplier, so the integer work moves from the saturated ALU pipe (SHF / VIMNMX / LEA) to the FMA pipe (IMAD family),
+// and the [-128, 127] clamp is one VIMNMX.RELU in the +128 domain; 2 = variant 1 with the residual rescale
+// MBQM((r - zp1) << 20, m1, s1) read from a 256-entry shared-memory table instead of computed.
+template <int S, int TR, int ADD, int DWT, int MB, int NT, int EPI = 0>
 __global__ void __launch_bounds__(NT, MB)
 k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles, DsParams P) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -57,9 +74,10 @@ k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles
   unsigned char* sA0 = sB + b_bytes;
   unsigned char* sT0 = sA0 + NAB * a_bytes;
   int4* s_rq = reinterpret_cast<int4*>(sT0 + NST * tile_bytes);
-  int* s_rz = reinterpret_cast<int*>(s_rq + N);
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(s_rz + ((N + 1) & ~1));
+  int* s_rz = reinterpret_cast<int*>(s_rq + N);                 // EPI >= 1: int2 {rz, addc} per channel
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(s_rz + 2 * N);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2);
+  int* s_lut1 = reinterpret_cast<int*>(tmem_slot + 2);          // EPI == 2: residual term per code, [256]
 
   // ---- one-time setup ---------------------------------------------------------------------------
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), (uint32_t)P.tmem_cols);
@@ -70,7 +88,19 @@ k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles
   }
   for (int i = tid; i < b_bytes / 16; i += NT) cp_async16(smem_u32(sB + 16 * i), P.w_img + 16 * (size_t)i);
   cp_async_commit();
-  for (int i = tid; i < N; i += NT) { s_rq[i] = __ldg(P.pw_rq + i); s_rz[i] = __ldg(P.pw_rz + i); }
+  if (EPI == 0) {
+    for (int i = tid; i < N; i += NT) { s_rq[i] = __ldg(P.pw_rq + i); s_rz[i] = __ldg(P.pw_rz + i); }
+  } else {
+    // [N] 2c (64-bit) | [N] {(int)(2 m), 2^(32 - n)} | [N] rz << 32
+    for (int i = tid; i < N; i += NT) {
+      const int4 q = __ldg(P.pw_rq2 + i);
+      reinterpret_cast<int2*>(s_rq)[i] = make_int2(q.x, q.y);
+      reinterpret_cast<int2*>(s_rq)[N + i] = make_int2(q.z, q.w);
+      reinterpret_cast<int2*>(s_rz)[i] = make_int2(0, __ldg(P.pw_rz2 + i).x);
+    }
+    if (EPI == 2)
+      for (int i = tid; i < 256; i += NT) s_lut1[i] = (int)(((unsigned long long)(unsigned)i * (unsigned)P.a_m1 + (unsigned long long)P.a_c1) >> P.a_n1);
+  }
   if (P.C < KP) for (int i = tid; i < NAB * a_bytes / 16; i += NT) *reinterpret_cast<uint4*>(sA0 + 16 * i) = make_uint4(0, 0, 0, 0);
   const unsigned zpw = 0x01010101u * (unsigned)(uint8_t)P.dw_in_zp;
   {  // halo columns hold the zero point for the whole kernel (cp.async never touches them)
@@ -307,9 +337,25 @@ k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles
 #pragma unroll
         for (int jj = 0; jj < 4; jj++) {
           const int c = 16 * g + 4 * gg + jj;
-          const int4 rq = s_rq[c];
+          const int4 rq = (ADD == 2 && EPI >= 1) ? make_int4(0, 0, 0, 0) : s_rq[c];
           if (!ADD) {
             o[jj] = rq_hi(v[4 * gg + jj], rq.x, rq.y, rq.z) >> rq.w;
+          } else if (ADD == 2 && EPI >= 1) {
+            // Every step is hi32(a * b + c64) -- ONE IMAD.HI with a 64-bit addend -- plus at most one add:
+            //   vv = SRDHM(acc + bias', m)   = hi32(acc * (2 m - 2^32) + 2 c) + acc          (2 m wrapped to int32, c = bias' m + 2^30)
+            //   t  = vv + rz + (vv >> 31)    = hi32(vv * 2 + rz 2^32) + vv                   (rounding term, zero point, tie nudge)
+            //   y  = clamp(t >> n) + 128     = min.relu(hi32(t * 2^(32-n) + 128 2^32), 255)
+            const int acc = v[4 * gg + jj];
+            const long long c2 = reinterpret_cast<const long long*>(s_rq)[c];
+            const int2 mp = reinterpret_cast<const int2*>(s_rq)[N + c];
+            const long long rzp = reinterpret_cast<const long long*>(s_rz)[c];
+            const int vv = (int)(((long long)acc * (long long)mp.x + c2) >> 32) + acc;
+            const int t = (int)(((long long)vv * (long long)P.two + rzp) >> 32) + vv;
+            const int y = min_relu((int)(((long long)t * (long long)mp.y + (128ll << 32)) >> 32), 255);
+            const unsigned u = __byte_perm(rw[gg], 0u, 0x4440 + jj);
+            const int s1 = EPI == 2 ? s_lut1[u] : (int)(((unsigned long long)u * (unsigned)P.a_m1 + (unsigned long long)P.a_c1) >> P.a_n1);
+            const int t2 = s1 + (y << 19);                                                    // -(zp2 + 128) << 19 is folded into a_co2
+            o[jj] = (int)(((long long)t2 * (long long)P.a_mo + P.a_co2) >> 32) >> P.a_no;
           } else {
             const int rz = s_rz[c];
             const int y = clamp2(rq64(v[4 * gg + jj], rq.x, rq.y, rq.z, rz, rq.w), P.pw_lo, P.pw_hi);
@@ -407,15 +453,15 @@ size_t ds_smem_bytes(const DsParams& P, int S, int TR) {
   const int nab = P.nst > 1 ? 2 : 1;
   size_t b = (size_t)P.N * P.KP + (size_t)nab * P.MT * 128 * P.KP;
   b += (size_t)P.nst * (((size_t)P.NB * trin * tw * P.C + 15) & ~(size_t)15);
-  b += (size_t)P.N * 16 + (size_t)((P.N + 1) & ~1) * 4 + 32;
+  b += (size_t)P.N * 16 + (size_t)P.N * 8 + 32 + 1024;   // requant constants, mbarriers + TMEM slot, residual table
   return b + 1024;                                   // alignment slack
 }
 
-template <int S, int TR, int ADD, int DWT, int MB, int NT = DS_THREADS>
+template <int S, int TR, int ADD, int DWT, int MB, int NT = DS_THREADS, int EPI = 0>
 static int launch_one(const int8_t* in, int8_t* out, int Bw, int ntiles, int grid, size_t smem, const DsParams& P, cudaStream_t st) {
   static unsigned long long attr = 0;
-  if (first_use_on_device(attr)) cudaFuncSetAttribute(k_ds<S, TR, ADD, DWT, MB, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  k_ds<S, TR, ADD, DWT, MB, NT><<<grid, NT, smem, st>>>(in, out, Bw, ntiles, P);
+  if (first_use_on_device(attr)) cudaFuncSetAttribute(k_ds<S, TR, ADD, DWT, MB, NT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  k_ds<S, TR, ADD, DWT, MB, NT, EPI><<<grid, NT, smem, st>>>(in, out, Bw, ntiles, P);
   return 0;
 }
 
@@ -425,6 +471,19 @@ int launch_ds(const int8_t* in, int8_t* out, int Bw, const DsParams& P, const Ds
   if (grid > ntiles) grid = ntiles;
   if (grid < 1) return 0;
   // 512-thread build for single-CTA layers (transposed depthwise only; the two shapes the late layers use)
+  // residual-ADD blocks with the multiply-high epilogue (transposed depthwise builds only)
+  if (L.add_mode == 2 && L.epi >= 1 && L.dwt && L.S == 1) {
+#define EPI_CASE(tr, mb, nt)                                                                                       \
+    if (L.TR == tr && mb_sel == mb && L.threads == nt)                                                              \
+      return L.epi == 2 ? launch_one<1, tr, 2, 1, mb, nt, 2>(in, out, Bw, ntiles, grid, L.smem, P, st)              \
+                        : launch_one<1, tr, 2, 1, mb, nt, 1>(in, out, Bw, ntiles, grid, L.smem, P, st)
+    const int mb_sel = (L.threads == 512 && L.ctas_per_sm == 1) ? 1 : (L.ctas_per_sm >= 3 ? 3 : 2);
+    EPI_CASE(4, 1, 512);
+    EPI_CASE(4, 2, 256); EPI_CASE(4, 3, 256);
+    EPI_CASE(8, 2, 256); EPI_CASE(8, 3, 256);
+    EPI_CASE(16, 2, 256); EPI_CASE(16, 3, 256);
+#undef EPI_CASE
+  }
   if (L.threads == 512 && L.dwt && L.ctas_per_sm == 1) {
     if (L.S == 1 && L.TR == 4 && L.add_mode == 2) return launch_one<1, 4, 2, 1, 1, 512>(in, out, Bw, ntiles, grid, L.smem, P, st);
     if (L.S == 1 && L.TR == 4 && L.add_mode == 1) return launch_one<1, 4, 1, 1, 1, 512>(in, out, Bw, ntiles, grid, L.smem, P, st);

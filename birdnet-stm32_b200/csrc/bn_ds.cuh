@@ -20,6 +20,10 @@ struct DsParams {
   const uint8_t* w_img;   // N * KP bytes: K-major swizzled shared-memory image of the weights
   const int4* pw_rq;      // [N] saturating form when there is no ADD; else {c_lo, c_hi, mult, n} with c = bias' * mult + 2^30
   const int* pw_rz;       // [N] 2^(n-1) + out_zp * 2^n (ADD blocks: the conv output is signed, tie nudge kept)
+  const int4* pw_rq2;     // [N] multiply-high epilogue (DsLaunch::epi): {2c lo, 2c hi, (int)(2 mult) wrapped, 2^(32 - n)}
+  const int2* pw_rz2;     // [N] {2^(n-1) + zp2 * 2^n, 128}; constant channels: mult = 0, 2^(32-n) = 0, {0, code + 128}
+  long long a_co2;        // a_co with the +128 domain of the clamped conv code folded in
+  int two;                // the constant 2, kept opaque to the compiler (IMAD.HI instead of a shift for v >> 31)
   int C, N, KP, RW;       // depthwise channels (= GEMM K), output channels, padded K, swizzle row width
   int ih, iw, oh, ow, pt, pl;
   int NB, MT;             // chunks per CTA tile, 128-row MMA tiles per CTA tile
@@ -49,6 +53,7 @@ struct DsLaunch {
   int tcdw;               // 1 = run bn_ds_tc.cu (both convolutions on the tensor core)
   int threads;            // 256, or 512 for single-CTA layers (see k_ds)
   int dwt;                // 1 = depthwise with filter rows along the dp4a axis (PRMT transpose, 3 dp4a per output), 0 = masked words (9)
+  int epi;                // residual-ADD epilogue variant of k_ds (add_mode 2): 0 ALU-pipe shifts, 1 multiply-high form, 2 = 1 + residual table
 };
 
 int launch_ds(const int8_t* in, int8_t* out, int Bw, const DsParams& P, const DsLaunch& L, int num_sms, cudaStream_t st);

@@ -19,6 +19,7 @@
 #include <map>
 
 #include "bn_ds.cuh"
+#include "bn_stage.cuh"
 #include "bn_head_tc.cuh"
 #include "bn_kernels.cuh"
 #include "bn_pw_tc.cuh"
@@ -145,7 +146,14 @@ struct Block {
   bool dst_ok = false;
 };
 
+struct StagePlan {                // blocks [first, first + nl) run as ONE kernel (bn_stage.cu)
+  int first = 0, nl = 0;
+  int C0 = 0, C = 0, OH = 0, OW = 0;
+  StageParams sp{};
+};
+
 struct FastImpl {
+  std::vector<StagePlan> stages;
   // op / tensor indices
   int quant_op = -1, mel_op = -1, stem_op = -1, mean_op = -1, fc_op = -1, logi_op = -1, deq_op = -1;
   std::vector<int> region_ops;    // element-wise chain between the mel conv and the transpose
@@ -484,6 +492,47 @@ static bool prep_ds(FastPlan& fp, FastImpl* im, Block& bl) {
     if (s1max + s2max >= (1ll << 30) || vmax + llabs(rzo) + 1 >= (1ll << 31)) { if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: reject at check 15 (line %d)\n", __LINE__); return false; }
     D.a_rzo = (int)rzo; D.a_zpo = (int)zpo;
     D.a_lo = p[BN_ADD_ACT_MIN]; D.a_hi = p[BN_ADD_ACT_MAX];
+    // multiply-high epilogue (bn_ds.cu, EPI >= 1): per channel {2c, (int)(2 m) wrapped, 2^(32 - n)}, {rz, 128}.  Needs the conv
+    // clamp to be the full int8 range, 2 <= n <= 31 on every live channel and 2c inside int64.
+    L.epi = 0;
+    D.two = 2; D.pw_rq2 = nullptr; D.pw_rz2 = nullptr; D.a_co2 = 0;
+    const int want_epi = getenv("BN_DS_EPI") ? atoi(getenv("BN_DS_EPI")) : 1;
+    if (L.add_mode == 2 && want_epi >= 1 && D.pw_lo == -128 && D.pw_hi == 127) {
+      std::vector<int> q2((size_t)N * 4), z2((size_t)N * 2);
+      bool ok = true;
+      for (int c = 0; c < N && ok; c++) {
+        const long long c64 = ((long long)rq[4 * c + 1] << 32) | (unsigned)rq[4 * c + 0];
+        const long long m = rq[4 * c + 2];
+        const int n = rq[4 * c + 3];
+        if (m == 0) {
+          // constant channel.  With all-zero weights (the converter's dead channels: bias +-2^30) the accumulator is 0, so
+          // 2c = (4 code + 2) << 32 with m = 0, n = 2, rz = 0 gives vv = 4 code + 2 -> code for either sign.  A constant
+          // channel with live weights cannot be expressed that way: keep the round-1 epilogue for the layer.
+          const int8_t* wp = (const int8_t*)(fp.h_blob + pw.off[0]) + (size_t)c * C;
+          bool zero_w = true;
+          for (int k = 0; k < C; k++) zero_w = zero_w && wp[k] == 0;
+          if (!zero_w) { ok = false; break; }
+          const int code = clampi(rz[c] >> 1, -128, 127);
+          q2[4 * c + 0] = 0; q2[4 * c + 1] = 4 * code + 2; q2[4 * c + 2] = 0; q2[4 * c + 3] = (int)(1u << 30);
+          z2[2 * c + 0] = 0; z2[2 * c + 1] = 128;
+          continue;
+        }
+        if (m < (1ll << 30) || n < 2 || n > 31 || c64 >= (1ll << 61) || c64 <= -(1ll << 61)) { ok = false; break; }
+        const long long c2 = 2 * c64;
+        q2[4 * c + 0] = (int)(uint32_t)(c2 & 0xffffffffll);
+        q2[4 * c + 1] = (int)(c2 >> 32);
+        q2[4 * c + 2] = (int)(uint32_t)((2 * m) & 0xffffffffll);      // 2 m - 2^32 as int32
+        q2[4 * c + 3] = (int)(1u << (32 - n));
+        z2[2 * c + 0] = rz[c];
+        z2[2 * c + 1] = 128;
+      }
+      if (ok) {
+        D.pw_rq2 = (const int4*)upload(im, q2.data(), q2.size() * 4);
+        D.pw_rz2 = (const int2*)upload(im, z2.data(), z2.size() * 4);
+        D.a_co2 = D.a_co - 128ll * (1ll << 19) * mo;
+        if (D.pw_rq2 && D.pw_rz2) L.epi = want_epi >= 2 ? 2 : 1;
+      }
+    }
   }
   // pick the pipeline depth: score = resident CTAs per SM x (pipelined ? 1.5 : 1); deeper prefetch wins ties
   {
@@ -827,6 +876,31 @@ static bool build_impl(FastPlan& fp) {
       }
     }
     bl.ds_ok = prep_ds(fp, im, bl);
+  }
+  // whole-stage kernels: a stride-2 block without ADD followed by stride-1 residual blocks of the same width whose maps are
+  // one 128-pixel MMA tile (the 8 x 16 stage of the shipped graph), all in the folded-constant domain of the fused DS kernel
+  for (size_t i = 0; i < im->blocks.size();) {
+    const Block& b0 = im->blocks[i];
+    size_t j = i + 1;
+    if (b0.ds_ok && b0.dsl.S == 2 && b0.add_op < 0) {
+      while (j < im->blocks.size() && j - i < (size_t)STAGE_MAX_BLOCKS) {
+        const Block& b = im->blocks[j];
+        if (!(b.ds_ok && b.dsl.S == 1 && b.add_op >= 0 && b.dsl.add_mode == 2 && b.ds.C == b0.ds.N && b.ds.N == b0.ds.N &&
+              b.ds.pw_lo == -128 && b.ds.pw_hi == 127 && b.ds.oh == b0.ds.oh && b.ds.ow == b0.ds.ow)) break;
+        j++;
+      }
+      const int nl = (int)(j - i);
+      if (nl >= 2 && stage_supported(b0.ds.C, b0.ds.N, b0.ds.oh, b0.ds.ow, nl)) {
+        StagePlan sp;
+        sp.first = (int)i; sp.nl = nl; sp.C0 = b0.ds.C; sp.C = b0.ds.N; sp.OH = b0.ds.oh; sp.OW = b0.ds.ow;
+        sp.sp.nl = nl;
+        for (int l = 0; l < nl; l++) { sp.sp.L[l] = im->blocks[i + l].ds; sp.sp.dbg[l] = nullptr; }
+        im->stages.push_back(sp);
+        i = j;
+        continue;
+      }
+    }
+    i++;
   }
   {  // tail
     const bn_blob_op& mo = ops[im->mean_op];
@@ -1535,7 +1609,28 @@ static int run_body(FastPlan& fp, int Bw, float* d_scores, int rounding, int mea
   // blocks
   char name[48];
   int bi = 0;
+  int skip_until = -1, bidx = -1;
   for (const Block& bl : im->blocks) {
+    bidx++;
+    if (bidx < skip_until) { bi++; continue; }
+    if ((fp.fusion & 8) && (fp.fusion & 1) && fp.use_tc && R == 0) {
+      const StagePlan* stg = nullptr;
+      for (const StagePlan& s : im->stages) if (s.first == bidx) stg = &s;
+      if (stg) {
+        StageParams sp = stg->sp;
+        for (int l = 0; l + 1 < stg->nl; l++) sp.dbg[l] = (fp.fusion & 16) ? (int8_t*)im->slot_buf[im->blocks[bidx + l].out_slot] : nullptr;
+        snprintf(name, sizeof name, "K45s_stage_%02d_%02d_c%d_n%d", bi, bi + stg->nl - 1, stg->C0, stg->C);
+        if (prof) prof->begin(name, st);
+        int rc = launch_stage((const int8_t*)im->slot_buf[bl.in_slot], (int8_t*)im->slot_buf[im->blocks[bidx + stg->nl - 1].out_slot], Bw, sp,
+                              stg->C0, stg->C, stg->OH, stg->OW, fp.num_sms, st);
+        if (prof) prof->end(st);
+        if (rc) return rc;
+        (*launches)++;
+        skip_until = bidx + stg->nl;
+        bi++;
+        continue;
+      }
+    }
     const int8_t* bin = (const int8_t*)im->slot_buf[bl.in_slot];
     int8_t* dwo = (int8_t*)im->slot_buf[bl.dw_slot];
     int8_t* bout = (int8_t*)im->slot_buf[bl.out_slot];

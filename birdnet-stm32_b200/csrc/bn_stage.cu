@@ -1,0 +1,307 @@
+// bn_stage.cu -- one STAGE of the DS-CNN per kernel: a stride-2 DS block and the stride-1 residual DS blocks that follow
+// it, with the activations of a chunk resident in shared memory from the first depthwise to the last residual ADD.
+//
+//   in  int8 [B][2 OH][2 OW][C0]                     (one TMA bulk copy per input row, straight into the padded tile)
+//     block 0 : DW 3x3 s2 + ReLU6 -> A operand -> tcgen05.mma (C0 -> C) -> requant + ReLU6 -> sAct   (shared memory)
+//     block l : DW 3x3 s1 + ReLU6 (reads sAct incl. its zero-point halo) -> A -> tcgen05.mma (C -> C) -> requant ->
+//               residual ADD with sAct -> ReLU6 -> back into sAct (in place)           l = 1 .. NL - 1
+//   out int8 [B][OH][OW][C]                           (last block only; earlier block outputs never leave the SM)
+//
+// Reference counterpart: the `for` loop over a stage's blocks in build_dscnn_model (birdnet_stm32/models/dscnn.py:236-247)
+// with ds_conv_block (:28-84), as lowered into DEPTHWISE_CONV_2D / CONV_2D / ADD and run by tf.lite.Interpreter.invoke
+// (models/runners.py:93-95).  Same integer arithmetic as bn_ds.cu, bit-exact; this is kernel (3)
+// of BASELINE.json's north_star ("activations for a tile of chunks kept in shared memory across layers").
+//
+// Shape: OH x OW = 128 output pixels = one 128-row MMA tile per chunk.  A CTA holds the pointwise weight images of ALL
+// blocks of the stage (fetched once by TMA bulk copies) and runs TWO independent groups of 256 threads, each working on its
+// own chunk with its own buffers, named barrier, mbarriers and TMEM columns -- so while one group waits for its MMA or its
+// input tile the other one computes, and the weights are shared.  Per group and chunk the only global traffic is the
+// block-0 input (prefetched for the next chunk as soon as the depthwise of block 0 has consumed the current one) and
+// the final output.
+#include "bn_stage.cuh"
+
+#include "bn_common.cuh"
+#include "bn_tc.cuh"
+
+namespace bn {
+
+namespace {
+
+constexpr int GT = 256;                   // threads per group
+constexpr int NGROUPS = 2;
+
+__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(GT) : "memory"); }
+
+// TMA bulk copy global -> shared (1-D), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ int rq64s(int acc, int c_lo, int c_hi, int mult, int rz, int n) {
+  const long long c = ((long long)c_hi << 32) | (unsigned)c_lo;
+  const long long p = (long long)acc * (long long)mult + c;
+  const int v = (int)(p >> 31);
+  return (v + rz + (v >> 31)) >> n;
+}
+
+// Depthwise 3x3 of one whole map with the taps of a filter row along the dp4a axis (same scheme as depthwise_t of bn_ds.cu):
+// tile sT = [TRIN][TW][C] int8 (halo / padding = zero point), result requantised straight into the swizzled K-major A operand.
+// One strip (a column for S = 2, a pair of columns for S = 1, 4 channels, all OH rows) per thread: OW * C / 4 / NCOL == GT.
+template <int S, int C, int OH, int OW>
+__device__ __forceinline__ void depthwise_map(const unsigned char* sT, unsigned char* sA, const DsParams& P, int tid) {
+  constexpr int CG = C / 4, NCOL = S == 1 ? 2 : 1;
+  constexpr int TRIN = (OH - 1) * S + 3, TW = OW * S + (S == 1 ? 2 : 1);
+  constexpr int RW = C > 128 ? 128 : C;                       // KP == C (C >= 32), one k-half when C <= 128
+  constexpr int SW_SH = RW == 128 ? 0 : (RW == 64 ? 1 : 2), SW_MASK = RW == 128 ? 7 : (RW == 64 ? 3 : 1);
+  constexpr int RW_LOG = RW == 128 ? 7 : (RW == 64 ? 6 : 5);
+  static_assert(OW * CG / NCOL == GT, "one strip per thread");
+  static_assert(C <= 128 && OH * OW == 128 && OW % 8 == 0, "shape");
+  (void)TRIN;
+  const int cg = tid & (CG - 1);
+  int4 wl[3], wr[3];
+#pragma unroll
+  for (int ky = 0; ky < 3; ky++) {
+    wl[ky] = __ldg(P.dw_wt + (2 * ky) * CG + cg);
+    wr[ky] = S == 1 ? __ldg(P.dw_wt + (2 * ky + 1) * CG + cg) : make_int4(0, 0, 0, 0);
+  }
+  int4 drq[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) drq[j] = __ldg(P.dw_rq + 4 * cg + j);
+  const int k0 = 4 * cg;
+  const int a_cc = (k0 & (RW - 1)) >> 4, a_b = k0 & 15;
+  const unsigned a_pairx = SW_SH == 0 ? 16u : 0u;
+  const int ox = (tid / CG) * NCOL;
+  const unsigned* tp = reinterpret_cast<const unsigned*>(sT) + (size_t)(ox * S) * CG + cg;
+  const int a_thr = ((a_cc ^ ((ox >> SW_SH) & SW_MASK)) << 4) | a_b;
+  auto load_row = [&](int ir, unsigned (&t)[4]) {
+    const unsigned* rp = tp + (size_t)ir * TW * CG;
+    const unsigned x0 = rp[0], x1 = rp[CG], x2 = rp[2 * CG];
+    const unsigned a = __byte_perm(x0, x1, 0x5140), b = __byte_perm(x0, x1, 0x7362);
+    if (S == 1) {
+      const unsigned x3 = rp[3 * CG];
+      const unsigned c = __byte_perm(x2, x3, 0x5140), d = __byte_perm(x2, x3, 0x7362);
+      t[0] = __byte_perm(a, c, 0x5410); t[1] = __byte_perm(a, c, 0x7632);
+      t[2] = __byte_perm(b, d, 0x5410); t[3] = __byte_perm(b, d, 0x7632);
+    } else {
+      t[0] = __byte_perm(a, x2, 0x4410); t[1] = __byte_perm(a, x2, 0x5532);
+      t[2] = __byte_perm(b, x2, 0x6610); t[3] = __byte_perm(b, x2, 0x7732);
+    }
+  };
+  unsigned t0[4], t1[4], t2[4];
+  load_row(0, t0);
+  if (S == 1) load_row(1, t1);
+#pragma unroll
+  for (int r = 0; r < OH; r++) {
+    if (S == 2) load_row(2 * r + 1, t1);
+    load_row(r * S + 2, t2);
+    int aL[4], aR[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const int w0 = c == 0 ? wl[0].x : c == 1 ? wl[0].y : c == 2 ? wl[0].z : wl[0].w;
+      const int w1 = c == 0 ? wl[1].x : c == 1 ? wl[1].y : c == 2 ? wl[1].z : wl[1].w;
+      const int w2 = c == 0 ? wl[2].x : c == 1 ? wl[2].y : c == 2 ? wl[2].z : wl[2].w;
+      aL[c] = __dp4a((int)t2[c], w2, __dp4a((int)t1[c], w1, __dp4a((int)t0[c], w0, 0)));
+      if (S == 1) {
+        const int v0 = c == 0 ? wr[0].x : c == 1 ? wr[0].y : c == 2 ? wr[0].z : wr[0].w;
+        const int v1 = c == 0 ? wr[1].x : c == 1 ? wr[1].y : c == 2 ? wr[1].z : wr[1].w;
+        const int v2 = c == 0 ? wr[2].x : c == 1 ? wr[2].y : c == 2 ? wr[2].z : wr[2].w;
+        aR[c] = __dp4a((int)t2[c], v2, __dp4a((int)t1[c], v1, __dp4a((int)t0[c], v0, 0)));
+      }
+    }
+    const int m = r * OW + ox;
+    const unsigned off = (unsigned)((m << RW_LOG) + a_thr);
+    *reinterpret_cast<unsigned*>(sA + off) = pack4_sat(rq_hi(aL[0], drq[0].x, drq[0].y, drq[0].z) >> drq[0].w, rq_hi(aL[1], drq[1].x, drq[1].y, drq[1].z) >> drq[1].w,
+                                                       rq_hi(aL[2], drq[2].x, drq[2].y, drq[2].z) >> drq[2].w, rq_hi(aL[3], drq[3].x, drq[3].y, drq[3].z) >> drq[3].w);
+    if (S == 1)
+      *reinterpret_cast<unsigned*>(sA + ((off + RW) ^ a_pairx)) = pack4_sat(rq_hi(aR[0], drq[0].x, drq[0].y, drq[0].z) >> drq[0].w, rq_hi(aR[1], drq[1].x, drq[1].y, drq[1].z) >> drq[1].w,
+                                                                            rq_hi(aR[2], drq[2].x, drq[2].y, drq[2].z) >> drq[2].w, rq_hi(aR[3], drq[3].x, drq[3].y, drq[3].z) >> drq[3].w);
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      if (S == 1) { t0[c] = t1[c]; t1[c] = t2[c]; }
+      else t0[c] = t2[c];
+    }
+  }
+}
+
+template <int C0, int C, int OH, int OW>
+__global__ void __launch_bounds__(GT* NGROUPS, 1)
+k_stage(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, StageParams SP) {
+  constexpr int NL_MAX = STAGE_MAX_BLOCKS;
+  constexpr int IH = 2 * OH, IW = 2 * OW;
+  constexpr int TRIN0 = 2 * OH + 1, TW0 = IW + 1;              // block 0 (stride 2, SAME pads 0 before / 1 after)
+  constexpr int TRIN1 = OH + 2, TW1 = OW + 2;                  // stride-1 blocks (pad 1 / 1)
+  constexpr int IN_BYTES = (TRIN0 * TW0 * C0 + 15) & ~15;
+  constexpr int ACT_BYTES = (TRIN1 * TW1 * C + 15) & ~15;
+  constexpr int A_BYTES = 128 * C;
+  constexpr int B0_BYTES = C * C0, B1_BYTES = C * C;
+  constexpr int RW0 = C0 > 128 ? 128 : C0, RW1 = C > 128 ? 128 : C;
+  constexpr int NG = C / 16;                                   // 16-column groups of the accumulator
+  constexpr int GROUP_BYTES = (A_BYTES + IN_BYTES + ACT_BYTES + C * 20 + 64 + 1023) & ~1023;   // keeps every group's A operand 1024-aligned
+  static_assert(OH * OW == 128 && C0 <= 128 && C <= 128 && C0 % 32 == 0 && C % 32 == 0, "stage shape");
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int tid_cta = threadIdx.x;
+  const int g = tid_cta / GT, tid = tid_cta - g * GT, warp = tid >> 5, lane = tid & 31;
+  const int nl = SP.nl;
+
+  // ---- carve shared memory ------------------------------------------------------------------------------------------
+  unsigned char* sB = smem;                                   // [B0 | B1 x (NL_MAX - 1)]
+  unsigned char* grp = sB + B0_BYTES + (NL_MAX - 1) * B1_BYTES + (size_t)g * GROUP_BYTES;
+  unsigned char* sA = grp;                                    // 1024-aligned: all sizes before it are multiples of 1024
+  unsigned char* sIn = sA + A_BYTES;
+  unsigned char* sAct = sIn + IN_BYTES;
+  int4* s_rq = reinterpret_cast<int4*>(sAct + ACT_BYTES);
+  int* s_rz = reinterpret_cast<int*>(s_rq + C);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(s_rz + C);     // [0] MMA done, [1] input tile landed
+  unsigned char* tail = sB + B0_BYTES + (NL_MAX - 1) * B1_BYTES + (size_t)NGROUPS * GROUP_BYTES;
+  uint64_t* wbar = reinterpret_cast<uint64_t*>(tail);         // weights landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+
+  // ---- one-time setup -------------------------------------------------------------------------------------------------
+  if (tid_cta < 32) tmem_alloc(smem_u32(tmem_slot), (uint32_t)(NGROUPS * C < 32 ? 32 : NGROUPS * C));
+  if (tid == 0) {
+    mbar_init(smem_u32(&mbar[0]), 1);
+    mbar_init(smem_u32(&mbar[1]), 1);
+    if (g == 0) mbar_init(smem_u32(wbar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  const unsigned zpw = 0x01010101u * (unsigned)(uint8_t)SP.L[0].dw_in_zp;
+  {  // padding of the stride-2 input tile (right column, bottom row) and the whole halo of the activation tile: the zero
+     // point, written once -- the bulk copies and the epilogues only ever touch the interior
+    unsigned* ti = reinterpret_cast<unsigned*>(sIn);
+    for (int i = tid; i < TRIN0 * (C0 / 4); i += GT) { const int row = i / (C0 / 4), w = i - row * (C0 / 4); ti[(row * TW0 + TW0 - 1) * (C0 / 4) + w] = zpw; }
+    for (int i = tid; i < TW0 * (C0 / 4); i += GT) ti[(TRIN0 - 1) * TW0 * (C0 / 4) + i] = zpw;
+    unsigned* ta = reinterpret_cast<unsigned*>(sAct);
+    const unsigned zpa = 0x01010101u * (unsigned)(uint8_t)SP.L[nl > 1 ? 1 : 0].dw_in_zp;
+    for (int i = tid; i < TRIN1 * TW1 * (C / 4); i += GT) ta[i] = zpa;
+  }
+  __syncthreads();                                            // barrier inits visible before anyone arrives / waits
+  if (tid_cta == 0) {                                         // all pointwise weight images of the stage: TMA, once per CTA
+    uint32_t bytes = B0_BYTES + (uint32_t)(nl - 1) * B1_BYTES;
+    mbar_expect_tx(smem_u32(wbar), bytes);
+    bulk_g2s(smem_u32(sB), SP.L[0].w_img, B0_BYTES, smem_u32(wbar));
+    for (int l = 1; l < nl; l++) bulk_g2s(smem_u32(sB + B0_BYTES + (l - 1) * B1_BYTES), SP.L[l].w_img, B1_BYTES, smem_u32(wbar));
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot + (uint32_t)(g * C);
+  const int q = warp & 3, hsel = warp >> 2;
+
+  // chunks of this group: c_k = (blockIdx.x * NGROUPS + g) + k * gridDim.x * NGROUPS
+  const int first = blockIdx.x * NGROUPS + g, stride = gridDim.x * NGROUPS;
+  auto fetch_input = [&](int chunk) {                          // one elected thread: IH bulk copies of one input row each
+    mbar_expect_tx(smem_u32(&mbar[1]), (uint32_t)(IH * IW * C0));
+    const int8_t* src = in + (size_t)chunk * IH * IW * C0;
+    for (int r = 0; r < IH; r++) bulk_g2s(smem_u32(sIn + (size_t)r * TW0 * C0), src + (size_t)r * IW * C0, IW * C0, smem_u32(&mbar[1]));
+  };
+  if (first < Bw && tid == 0) fetch_input(first);
+  mbar_wait(smem_u32(wbar), 0);                               // weights resident (every thread observes the phase)
+
+  uint32_t mma_phase = 0, in_phase = 0;
+  for (int chunk = first; chunk < Bw; chunk += stride) {
+    for (int l = 0; l < nl; l++) {
+      const DsParams& P = SP.L[l];
+      // per-block epilogue constants of this group (the previous block's epilogue ended with a group barrier)
+      for (int i = tid; i < C; i += GT) { s_rq[i] = __ldg(P.pw_rq + i); s_rz[i] = __ldg(P.pw_rz + i); }
+      if (l == 0) {
+        mbar_wait(smem_u32(&mbar[1]), in_phase);
+        in_phase ^= 1;
+        depthwise_map<2, C0, OH, OW>(sIn, sA, P, tid);
+      } else {
+        depthwise_map<1, C, OH, OW>(sAct, sA, P, tid);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      group_sync(g);
+      if (tid == 0) {
+        if (l == 0 && chunk + stride < Bw) fetch_input(chunk + stride);      // sIn is free: prefetch the next chunk under blocks 1..
+        tc_fence_after();
+        const int RW = l == 0 ? RW0 : RW1, KP = l == 0 ? C0 : C;
+        const uint32_t sbo = 8 * RW, lt = RW == 128 ? 2u : (RW == 64 ? 4u : 6u);
+        const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(l == 0 ? sB : sB + B0_BYTES + (l - 1) * B1_BYTES);
+        const uint32_t idesc = make_idesc_i8(128, C);
+        for (int ks = 0; ks < (KP >> 5); ks++)
+          umma_i8(tmem_d, make_desc(a_addr + ks * 32, sbo, lt), make_desc(b_addr + ks * 32, sbo, lt), idesc, ks > 0 ? 1u : 0u);
+        umma_commit(smem_u32(&mbar[0]));
+      }
+      mbar_wait(smem_u32(&mbar[0]), mma_phase);
+      mma_phase ^= 1;
+      tc_fence_after();
+      // ---- epilogue: TMEM -> requant (+ residual ADD with the activation tile) -> activation tile / global ------------
+      const bool last = l == nl - 1;
+      int8_t* gout = last ? out : SP.dbg[l];
+      for (int t = hsel; t < NG; t += GT / 128) {
+        const int m = 32 * q + lane;
+        const int r = m / OW, ox = m - r * OW;
+        int v[16];
+        tmem_ld16(tmem_d + (uint32_t)(16 * t) + ((uint32_t)(32 * q) << 16), v);
+        unsigned char* cell = sAct + ((size_t)(r + 1) * TW1 + ox + 1) * C + 16 * t;
+        uint4 rv = make_uint4(0, 0, 0, 0);
+        if (l > 0) rv = *reinterpret_cast<const uint4*>(cell);
+        const unsigned rw[4] = {rv.x ^ 0x80808080u, rv.y ^ 0x80808080u, rv.z ^ 0x80808080u, rv.w ^ 0x80808080u};
+        unsigned ow4[4];
+#pragma unroll
+        for (int gg = 0; gg < 4; gg++) {
+          int o[4];
+#pragma unroll
+          for (int jj = 0; jj < 4; jj++) {
+            const int c = 16 * t + 4 * gg + jj;
+            const int4 rq = s_rq[c];
+            if (l == 0) {
+              o[jj] = rq_hi(v[4 * gg + jj], rq.x, rq.y, rq.z) >> rq.w;
+            } else {
+              const int rz = s_rz[c];
+              const int y = max(P.pw_lo, min(rq64s(v[4 * gg + jj], rq.x, rq.y, rq.z, rz, rq.w), P.pw_hi));
+              const unsigned u = __byte_perm(rw[gg], 0u, 0x4440 + jj);
+              const int s1 = (int)(((unsigned long long)u * (unsigned)P.a_m1 + (unsigned long long)P.a_c1) >> P.a_n1);
+              const int t2 = s1 + (y << 19);
+              o[jj] = (int)(((long long)t2 * (long long)P.a_mo + P.a_co) >> 32) >> P.a_no;
+            }
+          }
+          ow4[gg] = pack4_sat(o[0], o[1], o[2], o[3]);
+        }
+        const uint4 res = make_uint4(ow4[0], ow4[1], ow4[2], ow4[3]);
+        if (!last) *reinterpret_cast<uint4*>(cell) = res;
+        if (gout) *reinterpret_cast<uint4*>(gout + ((size_t)chunk * 128 + m) * C + 16 * t) = res;
+      }
+      tc_fence_before();
+      group_sync(g);                                           // TMEM drained, activation tile complete, constants free
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid_cta < 32) tmem_dealloc(*tmem_slot, (uint32_t)(NGROUPS * C < 32 ? 32 : NGROUPS * C));
+}
+
+}  // namespace
+
+size_t stage_smem_bytes(int C0, int C, int OH, int OW) {
+  const size_t in_b = ((size_t)(2 * OH + 1) * (2 * OW + 1) * C0 + 15) & ~(size_t)15;
+  const size_t act_b = ((size_t)(OH + 2) * (OW + 2) * C + 15) & ~(size_t)15;
+  const size_t group_b = ((size_t)128 * C + in_b + act_b + (size_t)C * 20 + 64 + 1023) & ~(size_t)1023;
+  return (size_t)C * C0 + (size_t)(STAGE_MAX_BLOCKS - 1) * C * C + NGROUPS * group_b + 64 + 1024;
+}
+
+bool stage_supported(int C0, int C, int OH, int OW, int nl) {
+  return C0 == 64 && C == 128 && OH == 8 && OW == 16 && nl >= 2 && nl <= STAGE_MAX_BLOCKS && stage_smem_bytes(C0, C, OH, OW) <= 227 * 1024;
+}
+
+int launch_stage(const int8_t* in, int8_t* out, int Bw, const StageParams& SP, int C0, int C, int OH, int OW, int num_sms, cudaStream_t st) {
+  if (!stage_supported(C0, C, OH, OW, SP.nl)) return BN_ERR_UNSUPPORTED;
+  static unsigned long long attr = 0;
+  const size_t smem = stage_smem_bytes(C0, C, OH, OW);
+  if (first_use_on_device(attr)) cudaFuncSetAttribute(k_stage<64, 128, 8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  int grid = num_sms;
+  const int need = (Bw + NGROUPS - 1) / NGROUPS;
+  if (grid > need) grid = need;
+  if (grid < 1) return 0;
+  k_stage<64, 128, 8, 16><<<grid, GT * NGROUPS, smem, st>>>(in, out, Bw, SP);
+  return 0;
+}
+
+}  // namespace bn
