@@ -156,15 +156,7 @@ def native_batches(todo: list[str], sr: int, T: int, step: int, cap_chunks: int,
 
     from birdnet_stm32.audio import reader as _rd
 
-    stages = []
-    for _ in range(2):
-        try:
-            from birdnet_stm32.evaluation.gpu_runner import PinnedArray
-
-            pa = PinnedArray((cap_chunks, T), np.int16)
-            stages.append((pa, pa.array))
-        except Exception:                              # no CUDA runtime (stub runners in the CPU tests): ordinary memory
-            stages.append((None, np.empty((cap_chunks, T), dtype=np.int16)))
+    stages = _pinned_stages(cap_chunks, T)
     window = 2048                                      # paths offered to one reader call
     raw_stage: list = [None]
 
@@ -215,9 +207,32 @@ def native_batches(todo: list[str], sr: int, T: int, step: int, cap_chunks: int,
                 yield b
                 slot ^= 1
     finally:
-        for pa, _ in stages:
-            if pa is not None:
-                pa.free()
+        pass                                           # the pinned stages stay cached for the next evaluate() call
+
+
+_STAGE_CACHE: dict = {}
+
+
+def _pinned_stages(cap_chunks: int, T: int) -> list:
+    """Two page-locked int16 [cap, T] batch buffers, kept across `evaluate()` calls: allocating ~1 GB of pinned memory
+    costs more than reading and classifying a few thousand chunks.  One geometry is cached at a time."""
+    key = (int(cap_chunks), int(T))
+    if _STAGE_CACHE.get("key") == key:
+        return _STAGE_CACHE["stages"]
+    for pa, _ in _STAGE_CACHE.get("stages", []):
+        if pa is not None:
+            pa.free()
+    stages = []
+    for _ in range(2):
+        try:
+            from birdnet_stm32.evaluation.gpu_runner import PinnedArray
+
+            pa = PinnedArray((cap_chunks, T), np.int16)
+            stages.append((pa, pa.array))
+        except Exception:                              # no CUDA runtime (stub runners in the CPU tests): ordinary memory
+            stages.append((None, np.empty((cap_chunks, T), dtype=np.int16)))
+    _STAGE_CACHE["key"], _STAGE_CACHE["stages"] = key, stages
+    return stages
 
 
 def python_batches(todo: list[str], sr: int, cd: float, overlap: float, batch_chunks: int, io_workers: int):

@@ -20,6 +20,7 @@
 
 #include "bn_ds.cuh"
 #include "bn_stage.cuh"
+#include "bn_frontend_q.cuh"
 #include "bn_head_tc.cuh"
 #include "bn_kernels.cuh"
 #include "bn_pw_tc.cuh"
@@ -171,6 +172,10 @@ struct FastImpl {
   uint8_t* d_head_lut = nullptr;
   std::vector<int*> d_add_luts;   // per block: 512 ints (res, conv)
   int prepared_rounding = -1;
+  FrontendQParams fq{};           // quantising frontend (bn_frontend_q.cu)
+  bool fq_ok = false;
+  uint8_t* d_aimg = nullptr;      // int8 A-operand image of the mel GEMM, [wave][W / 128][HQ_A_BYTES]
+  unsigned* d_arrive = nullptr;   // per-chunk arrival counters of K1q
   // workspace (per wave)
   float* d_mags = nullptr;
   unsigned* d_mnmx = nullptr;
@@ -769,6 +774,9 @@ static bool build_impl(FastPlan& fp) {
       Q.K_real = im->bins; Q.ldk = K_cat; Q.fill = fill_val; Q.W = im->W;
       Q.q_scale = H.q_scale; Q.q_zp = H.q_zp;
       im->head_tc_ok = Q.w_img && Q.rq;
+      im->fq.q_scale = H.q_scale; im->fq.q_zp = H.q_zp; im->fq.fill = fill_val;
+      // (float32 waveform input -- the ingest path -- needs a larger staging buffer: checked per call, falls back to K1 + K2)
+      im->fq_ok = im->head_tc_ok && frontend_q_supported((int)h->n_fft, im->W, K_cat, im->bins, (int)h->hop, 0);
     }
   }
   {  // stem: weights [16][3][3][1] -> words (w0,w1,w2,0) per (co, fy)
@@ -969,6 +977,11 @@ int fast_plan_alloc_workspace(FastPlan& fp, int wave, size_t* total) {
   im->d_mags = (float*)alloc(sizeof(float) * (size_t)im->W * im->ldk * (wave < FE_SUBWAVE ? wave : FE_SUBWAVE));
   im->d_mnmx = (unsigned*)alloc(sizeof(unsigned) * 2 * wave);
   if (!im->d_mags || !im->d_mnmx) return BN_ERR_CUDA;
+  if (im->fq_ok) {
+    im->d_aimg = (uint8_t*)alloc((size_t)wave * (im->W / 128) * HQ_A_BYTES);
+    im->d_arrive = (unsigned*)alloc(sizeof(unsigned) * wave);
+    if (!im->d_aimg || !im->d_arrive) return BN_ERR_CUDA;
+  }
   std::vector<int> slots = {im->head_out_slot, im->stem_out_slot};
   for (const Block& bl : im->blocks) { slots.push_back(bl.dw_slot); slots.push_back(bl.out_slot); }
   for (int s : slots) {
@@ -985,7 +998,7 @@ void fast_plan_free_workspace(FastPlan& fp) {
   if (!im) return;
   for (void* p : im->owned) cudaFree(p);
   im->owned.clear(); im->slot_buf.clear();
-  im->d_mags = nullptr; im->d_mnmx = nullptr;
+  im->d_mags = nullptr; im->d_mnmx = nullptr; im->d_aimg = nullptr; im->d_arrive = nullptr;
   fp.wave = 0;
 }
 
@@ -1706,6 +1719,22 @@ int fast_run_pcm(FastPlan& fp, const void* d_pcm, int f32, const float* d_peak, 
   if (rc) return rc;
   const bn_blob_header* h = fp.hdr;
   const int T = (int)h->chunk_len;
+  if ((fp.fusion & 32) && (fp.fusion & 2) && im->fq_ok && im->d_aimg && fp.use_tc && rounding == 0 &&
+      frontend_q_supported((int)h->n_fft, im->W, im->ldk, im->bins, (int)h->hop, f32)) {
+    // K1q + K2q: the codes of the graph's QUANTIZE are formed inside the STFT kernel (chunk-wide min / max over a cluster),
+    // the mel GEMM reads them as its A operand: no float32 magnitude scratch
+    if (prof) prof->begin("K1q_stft_quant", st);
+    rc = launch_stft_q(d_pcm, f32, d_peak, im->d_aimg, im->d_mnmx, im->d_arrive, Bw, T, (int)h->n_fft, (int)h->hop, im->W, im->fq, fp.num_sms, st);
+    if (prof) prof->end(st);
+    if (rc) return rc;
+    *launches += 2;
+    if (prof) prof->begin("K2q_head", st);
+    rc = launch_head_q(im->d_aimg, (int8_t*)im->slot_buf[im->head_out_slot], Bw, im->head_tc, fp.num_sms, st);
+    if (prof) prof->end(st);
+    if (rc) return rc;
+    (*launches)++;
+    return run_body(fp, Bw, d_scores, rounding, mean_variant, st, launches, prof);
+  }
   for (int b0 = 0; b0 < Bw; b0 += FE_SUBWAVE) {
     const int nb = Bw - b0 < FE_SUBWAVE ? Bw - b0 : FE_SUBWAVE;
     if (prof) prof->begin("K1_stft", st);

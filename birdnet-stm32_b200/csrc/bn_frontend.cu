@@ -15,86 +15,14 @@
 // (magnitudes are >= +0, so their IEEE bit patterns order like unsigned integers).
 #include "bn_common.cuh"
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <type_traits>
 
+#include "bn_fft.cuh"
 #include "bn_kernels.cuh"
 
 namespace bn {
-
-constexpr int NFFT = 512;
-constexpr int NC = 256;          // complex points
-constexpr int BINS = 257;
-constexpr int FRAMES_PER_CTA = 32;
-constexpr int FE_THREADS = 256;  // 8 warps = 16 half-warps = 16 concurrent FFTs, 2 rounds
-constexpr int TILE_LD = FRAMES_PER_CTA + 1;
-
-// sqrt.approx.f32: max relative error 2^-23, far inside the 1e-4 frontend tolerance
-__device__ __forceinline__ float fast_sqrt(float x) {
-  float r;
-  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-
-__device__ __forceinline__ void cp_async16_fe(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-
-// Packed FP32 pairs (FADD2 on sm_100a): one issue slot adds or subtracts both halves of a complex number with the same
-// IEEE rounding as two scalar FADDs.  K1 is bound by instruction issue, not by the FP32 pipe, so halving the count of the
-// butterfly additions is a direct gain.  The mov.b64 packs / unpacks are register naming only (no SASS is emitted).
-__device__ __forceinline__ float2 add2(float2 a, float2 b) {
-  unsigned long long x, y, z;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(a.x), "f"(a.y));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(y) : "f"(b.x), "f"(b.y));
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(z) : "l"(x), "l"(y));
-  float2 r;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(z));
-  return r;
-}
-__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
-  unsigned long long x, y, z;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(a.x), "f"(a.y));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(y) : "f"(b.x), "f"(b.y));
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(z) : "l"(x), "l"(y));
-  float2 r;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(z));
-  return r;
-}
-
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-
-// In-register 16-point DIF FFT, output in natural order (bit reversal folded into the
-// compile-time unrolled index map).  tw16[j] = exp(-2 pi i j / 16).
-__device__ __forceinline__ void fft16(float2 (&v)[16]) {
-  const float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, r2 = 0.70710678118654752f;
-  const float2 tw[8] = {{1.f, 0.f}, {c1, -s1}, {r2, -r2}, {s1, -c1}, {0.f, -1.f}, {-s1, -c1}, {-r2, -r2}, {-c1, -s1}};
-#pragma unroll
-  for (int half = 8; half >= 1; half >>= 1) {
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-      if ((i & half) == 0) {
-        float2 a = v[i], b = v[i + half];
-        v[i] = add2(a, b);
-        float2 d = sub2(a, b);
-        const int j = (i & (half - 1)) * (8 / half);   // twiddle index into tw (N=16 base)
-        if (j == 0) v[i + half] = d;
-        else if (j == 4) v[i + half] = make_float2(d.y, -d.x);
-        else v[i + half] = cmul(d, tw[j]);
-      }
-    }
-  }
-  // bit-reverse permutation (4 bits)
-  float2 o[16];
-#pragma unroll
-  for (int i = 0; i < 16; i++) {
-    const int r = ((i & 1) << 3) | ((i & 2) << 1) | ((i & 4) >> 1) | ((i & 8) >> 3);
-    o[r] = v[i];
-  }
-#pragma unroll
-  for (int i = 0; i < 16; i++) v[i] = o[i];
-}
 
 // dynamic smem layout:
 //   float  xs[span + 16]                    span = 31*hop + 512 floats (16-byte aligned, indexed like the global buffer)
@@ -331,6 +259,8 @@ static const float4* stft_tables() {
   return d_tab;
 }
 
+const float4* stft_tables_shared() { return stft_tables(); }
+
 size_t stft_smem_bytes(int hop, bool frame_major, bool f32) {
   const int span = (FRAMES_PER_CTA - 1) * hop + NFFT;
   size_t b = sizeof(float) * ((span + 16 + 3) & ~3) + 16 * (size_t)(f32 ? ((span + 16 + 3) >> 2) : ((span + 16 + 7) >> 3));
@@ -386,6 +316,11 @@ int launch_stft_mag_fm(const void* pcm, int f32, const float* peak, float* out, 
   const float4* tab = stft_tables();
   if (!tab) return BN_ERR_CUDA;
   if (W % FRAMES_PER_CTA) return BN_ERR_UNSUPPORTED;
+  if (getenv("BN_DEBUG")) {
+    int n = -1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_stft_mag<true, false>, FE_THREADS, smem);
+    fprintf(stderr, "launch_stft_mag_fm: occupancy API says %d CTAs per SM for K1 with %zu bytes of shared memory\n", n, smem);
+  }
   k_init_minmax<<<(B + 255) / 256, 256, 0, st>>>(mnmx, B);
   if (f32) k_stft_mag<true, true><<<stft_grid(B, W, smem), FE_THREADS, smem, st>>>(pcm, peak, out, mnmx, tab, T, hop, W, ldk, B);
   else k_stft_mag<true, false><<<stft_grid(B, W, smem), FE_THREADS, smem, st>>>(pcm, peak, out, mnmx, tab, T, hop, W, ldk, B);

@@ -51,9 +51,11 @@ __device__ __forceinline__ int rq64s(int acc, int c_lo, int c_hi, int mult, int 
 // Depthwise 3x3 of one whole map with the taps of a filter row along the dp4a axis (same scheme as depthwise_t of bn_ds.cu):
 // tile sT = [TRIN][TW][C] int8 (halo / padding = zero point), result requantised straight into the swizzled K-major A operand.
 // One strip (a column for S = 2, a pair of columns for S = 1, 4 channels, all OH rows) per thread: OW * C / 4 / NCOL == GT.
-template <int S, int C, int OH, int OW>
+// PITCH = bytes per pixel of the tile (>= C; the activation tile pads it so that the epilogue's 16-byte accesses, one pixel per
+// lane, spread over all banks).
+template <int S, int C, int OH, int OW, int PITCH>
 __device__ __forceinline__ void depthwise_map(const unsigned char* sT, unsigned char* sA, const DsParams& P, int tid) {
-  constexpr int CG = C / 4, NCOL = S == 1 ? 2 : 1;
+  constexpr int CG = C / 4, NCOL = S == 1 ? 2 : 1, PW = PITCH / 4;
   constexpr int TRIN = (OH - 1) * S + 3, TW = OW * S + (S == 1 ? 2 : 1);
   constexpr int RW = C > 128 ? 128 : C;                       // KP == C (C >= 32), one k-half when C <= 128
   constexpr int SW_SH = RW == 128 ? 0 : (RW == 64 ? 1 : 2), SW_MASK = RW == 128 ? 7 : (RW == 64 ? 3 : 1);
@@ -75,14 +77,14 @@ __device__ __forceinline__ void depthwise_map(const unsigned char* sT, unsigned 
   const int a_cc = (k0 & (RW - 1)) >> 4, a_b = k0 & 15;
   const unsigned a_pairx = SW_SH == 0 ? 16u : 0u;
   const int ox = (tid / CG) * NCOL;
-  const unsigned* tp = reinterpret_cast<const unsigned*>(sT) + (size_t)(ox * S) * CG + cg;
+  const unsigned* tp = reinterpret_cast<const unsigned*>(sT) + (size_t)(ox * S) * PW + cg;
   const int a_thr = ((a_cc ^ ((ox >> SW_SH) & SW_MASK)) << 4) | a_b;
   auto load_row = [&](int ir, unsigned (&t)[4]) {
-    const unsigned* rp = tp + (size_t)ir * TW * CG;
-    const unsigned x0 = rp[0], x1 = rp[CG], x2 = rp[2 * CG];
+    const unsigned* rp = tp + (size_t)ir * TW * PW;
+    const unsigned x0 = rp[0], x1 = rp[PW], x2 = rp[2 * PW];
     const unsigned a = __byte_perm(x0, x1, 0x5140), b = __byte_perm(x0, x1, 0x7362);
     if (S == 1) {
-      const unsigned x3 = rp[3 * CG];
+      const unsigned x3 = rp[3 * PW];
       const unsigned c = __byte_perm(x2, x3, 0x5140), d = __byte_perm(x2, x3, 0x7362);
       t[0] = __byte_perm(a, c, 0x5410); t[1] = __byte_perm(a, c, 0x7632);
       t[2] = __byte_perm(b, d, 0x5410); t[3] = __byte_perm(b, d, 0x7632);
@@ -135,7 +137,9 @@ k_stage(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, StagePa
   constexpr int TRIN0 = 2 * OH + 1, TW0 = IW + 1;              // block 0 (stride 2, SAME pads 0 before / 1 after)
   constexpr int TRIN1 = OH + 2, TW1 = OW + 2;                  // stride-1 blocks (pad 1 / 1)
   constexpr int IN_BYTES = (TRIN0 * TW0 * C0 + 15) & ~15;
-  constexpr int ACT_BYTES = (TRIN1 * TW1 * C + 15) & ~15;
+  constexpr int APITCH = C + 16;                              // pixel pitch of the activation tile: lane i of a 16-byte access
+                                                              // lands on banks 4 i .. 4 i + 3 (mod 32) instead of all on the same four
+  constexpr int ACT_BYTES = (TRIN1 * TW1 * APITCH + 15) & ~15;
   constexpr int A_BYTES = 128 * C;
   constexpr int B0_BYTES = C * C0, B1_BYTES = C * C;
   constexpr int RW0 = C0 > 128 ? 128 : C0, RW1 = C > 128 ? 128 : C;
@@ -177,7 +181,7 @@ k_stage(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, StagePa
     for (int i = tid; i < TW0 * (C0 / 4); i += GT) ti[(TRIN0 - 1) * TW0 * (C0 / 4) + i] = zpw;
     unsigned* ta = reinterpret_cast<unsigned*>(sAct);
     const unsigned zpa = 0x01010101u * (unsigned)(uint8_t)SP.L[nl > 1 ? 1 : 0].dw_in_zp;
-    for (int i = tid; i < TRIN1 * TW1 * (C / 4); i += GT) ta[i] = zpa;
+    for (int i = tid; i < ACT_BYTES / 4; i += GT) ta[i] = zpa;
   }
   __syncthreads();                                            // barrier inits visible before anyone arrives / waits
   if (tid_cta == 0) {                                         // all pointwise weight images of the stage: TMA, once per CTA
@@ -211,9 +215,9 @@ k_stage(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, StagePa
       if (l == 0) {
         mbar_wait(smem_u32(&mbar[1]), in_phase);
         in_phase ^= 1;
-        depthwise_map<2, C0, OH, OW>(sIn, sA, P, tid);
+        depthwise_map<2, C0, OH, OW, C0>(sIn, sA, P, tid);
       } else {
-        depthwise_map<1, C, OH, OW>(sAct, sA, P, tid);
+        depthwise_map<1, C, OH, OW, APITCH>(sAct, sA, P, tid);
       }
       fence_proxy_async();
       tc_fence_before();
@@ -240,7 +244,7 @@ k_stage(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, StagePa
         const int r = m / OW, ox = m - r * OW;
         int v[16];
         tmem_ld16(tmem_d + (uint32_t)(16 * t) + ((uint32_t)(32 * q) << 16), v);
-        unsigned char* cell = sAct + ((size_t)(r + 1) * TW1 + ox + 1) * C + 16 * t;
+        unsigned char* cell = sAct + ((size_t)(r + 1) * TW1 + ox + 1) * APITCH + 16 * t;
         uint4 rv = make_uint4(0, 0, 0, 0);
         if (l > 0) rv = *reinterpret_cast<const uint4*>(cell);
         const unsigned rw[4] = {rv.x ^ 0x80808080u, rv.y ^ 0x80808080u, rv.z ^ 0x80808080u, rv.w ^ 0x80808080u};
@@ -282,7 +286,7 @@ k_stage(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, StagePa
 
 size_t stage_smem_bytes(int C0, int C, int OH, int OW) {
   const size_t in_b = ((size_t)(2 * OH + 1) * (2 * OW + 1) * C0 + 15) & ~(size_t)15;
-  const size_t act_b = ((size_t)(OH + 2) * (OW + 2) * C + 15) & ~(size_t)15;
+  const size_t act_b = ((size_t)(OH + 2) * (OW + 2) * (C + 16) + 15) & ~(size_t)15;
   const size_t group_b = ((size_t)128 * C + in_b + act_b + (size_t)C * 20 + 64 + 1023) & ~(size_t)1023;
   return (size_t)C * C0 + (size_t)(STAGE_MAX_BLOCKS - 1) * C * C + NGROUPS * group_b + 64 + 1024;
 }
