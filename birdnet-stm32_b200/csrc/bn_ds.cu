@@ -75,7 +75,7 @@ k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles
   unsigned char* sT0 = sA0 + NAB * a_bytes;
   int4* s_rq = reinterpret_cast<int4*>(sT0 + NST * tile_bytes);
   int* s_rz = reinterpret_cast<int*>(s_rq + N);                 // EPI >= 1: int2 {rz, addc} per channel
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(s_rz + 2 * N);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(s_rz + (EPI >= 1 ? 2 * N : ((N + 1) & ~1)));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2);
   int* s_lut1 = reinterpret_cast<int*>(tmem_slot + 2);          // EPI == 2: residual term per code, [256]
 
@@ -453,7 +453,8 @@ size_t ds_smem_bytes(const DsParams& P, int S, int TR) {
   const int nab = P.nst > 1 ? 2 : 1;
   size_t b = (size_t)P.N * P.KP + (size_t)nab * P.MT * 128 * P.KP;
   b += (size_t)P.nst * (((size_t)P.NB * trin * tw * P.C + 15) & ~(size_t)15);
-  b += (size_t)P.N * 16 + (size_t)P.N * 8 + 32 + 1024;   // requant constants, mbarriers + TMEM slot, residual table
+  b += (size_t)P.N * 16 + (size_t)((P.N + 1) & ~1) * 4 + 32;
+  b += (size_t)P.epi_smem;                          // multiply-high epilogue variants: second constant word per channel + residual table
   return b + 1024;                                   // alignment slack
 }
 

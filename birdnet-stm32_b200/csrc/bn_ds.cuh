@@ -24,6 +24,7 @@ struct DsParams {
   const int2* pw_rz2;     // [N] {2^(n-1) + zp2 * 2^n, 128}; constant channels: mult = 0, 2^(32-n) = 0, {0, code + 128}
   long long a_co2;        // a_co with the +128 domain of the clamped conv code folded in
   int two;                // the constant 2, kept opaque to the compiler (IMAD.HI instead of a shift for v >> 31)
+  int epi_smem;           // extra shared memory of the multiply-high epilogue variants (0 for the default epilogue)
   int C, N, KP, RW;       // depthwise channels (= GEMM K), output channels, padded K, swizzle row width
   int ih, iw, oh, ow, pt, pl;
   int NB, MT;             // chunks per CTA tile, 128-row MMA tiles per CTA tile

@@ -446,6 +446,7 @@ static bool prep_ds(FastPlan& fp, FastImpl* im, Block& bl) {
   D.sw_sh = D.RW == 128 ? 0 : (D.RW == 64 ? 1 : 2);
   D.sw_mask = D.RW == 128 ? 7 : (D.RW == 64 ? 3 : 1);
   D.nst = 1;
+  D.epi_smem = (bl.add_op >= 0 && getenv("BN_DS_EPI") && atoi(getenv("BN_DS_EPI")) >= 1) ? N * 4 + 1024 + 16 : 0;
   int cols = 32; while (cols < D.MT * N) cols <<= 1;
   if (cols > 512) { if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: reject at check 9 (line %d)\n", __LINE__); return false; }
   D.tmem_cols = cols;
@@ -501,7 +502,7 @@ static bool prep_ds(FastPlan& fp, FastImpl* im, Block& bl) {
     // clamp to be the full int8 range, 2 <= n <= 31 on every live channel and 2c inside int64.
     L.epi = 0;
     D.two = 2; D.pw_rq2 = nullptr; D.pw_rz2 = nullptr; D.a_co2 = 0;
-    const int want_epi = getenv("BN_DS_EPI") ? atoi(getenv("BN_DS_EPI")) : 1;
+    const int want_epi = getenv("BN_DS_EPI") ? atoi(getenv("BN_DS_EPI")) : 0;   // measured: no gain over the round-1 epilogue
     if (L.add_mode == 2 && want_epi >= 1 && D.pw_lo == -128 && D.pw_hi == 127) {
       std::vector<int> q2((size_t)N * 4), z2((size_t)N * 2);
       bool ok = true;

@@ -214,8 +214,6 @@ k_stft_q(const void* __restrict__ pcm_v, const float* __restrict__ peak, uint8_t
   auto worker_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(wk + 1), "n"(FE_THREADS) : "memory"); };
   // this thread's TMEM scratch: lane = its lane in the warp's quarter, 34 columns per warp half, two tile buffers
   const uint32_t tm0 = *tmem_slot0 + (uint32_t)(wk * TM_COLS) + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * 34);
-  const int zp_bits = 0x4B400000 - Q.q_zp;
-  const unsigned fill7 = 0x01010101u * (unsigned)(uint8_t)Q.fill;
 
   // finalise a tile whose magnitudes are parked in TMEM buffer `fbuf`: chunk-wide min / max (all TILES tiles of chunk fb have
   // published theirs once arrive[fb] == TILES), normalize() + QUANTIZE, scatter into the staged A rows, copy them out
@@ -227,15 +225,26 @@ k_stft_q(const void* __restrict__ pcm_v, const float* __restrict__ peak, uint8_t
     umx = __ldcg(mnmx + 2 * fb + 1);
   };
   auto finalise = [&](int fb, int ft0, int fbuf, unsigned seen, unsigned umn, unsigned umx) {
-    for (unsigned spin = 0; seen < (unsigned)groups_w; spin++) {   // rare: a tile of the chunk had not been published at peek time
-      if (spin > (1u << 22)) __trap();                    // ~1 s: the grid is not co-resident -- fail the launch, never hang the GPU
-      __nanosleep(64);
-      peek(fb, seen, umn, umx);
+    // lane 0 of every warp holds the peeked values (an acquire load invalidates L1: one lane per warp does it, not all 32)
+    float den = 0.0f, qmul = 0.0f, mn = 0.0f;
+    if (lane == 0) {
+      for (unsigned spin = 0; seen < (unsigned)groups_w; spin++) {   // rare: a tile of the chunk had not been published at peek time
+        if (spin > (1u << 22)) __trap();                  // ~1 s: the grid is not co-resident -- fail the launch, never hang the GPU
+        __nanosleep(64);
+        peek(fb, seen, umn, umx);
+      }
+      mn = __uint_as_float(umn);
+      const float mx = __uint_as_float(umx);
+      // normalize(): numpy scalar promotion (float64 add, float32 result)
+      den = (float)((double)(mx - mn) + 1e-10);
+      qmul = (float)(1.0 / ((double)den * (double)Q.q_scale));
     }
-    const float mn = __uint_as_float(umn), mx = __uint_as_float(umx);
+    mn = __shfl_sync(0xffffffffu, mn, 0);
+    den = __shfl_sync(0xffffffffu, den, 0);
+    qmul = __shfl_sync(0xffffffffu, qmul, 0);
     const uint32_t ftm = tm0 + (uint32_t)(fbuf * TM_BUF);
-    const float den = (float)((double)(mx - mn) + 1e-10);   // normalize(): numpy scalar promotion (float64 add, float32 result)
-    const float qmul = (float)(1.0 / ((double)den * (double)Q.q_scale));
+    const int zp_bits = 0x4B400000 - Q.q_zp;
+    const unsigned fill7 = 0x01010101u * (unsigned)(uint8_t)Q.fill;
     // ---- read the magnitudes back, quantise, scatter the codes into the staged A rows (swizzled K-major image) ----
 #pragma unroll 1
     for (int round = 0; round < FRAMES_PER_CTA / 16; round++) {
@@ -303,7 +312,7 @@ k_stft_q(const void* __restrict__ pcm_v, const float* __restrict__ peak, uint8_t
     const float pk = peak ? __ldg(peak + b) : 0.0f;
     const float cs = F32IN ? (pk > 0.0f ? __fdiv_rn(1.0f, pk) : 1.0f) : (pk > 0.0f ? __fdiv_rn(1.0f, 32768.0f * pk) : (1.0f / 32768.0f));
     unsigned p_seen = 0, p_mn = 0, p_mx = 0;
-    if (it > 0) peek(prev_b, p_seen, p_mn, p_mx);
+    if (it > 0 && lane == 0) peek(prev_b, p_seen, p_mn, p_mx);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     for (int grp = tid; grp < ngroups; grp += FE_THREADS) {
       const long rel = g_first + (long)G * grp - chunk_base;

@@ -198,3 +198,29 @@ def test_ten_thousand_chunks_pooled(runner24, oracle24):
     a = np.mean([average_precision_score(y[:, c], host[:, c]) for c in np.where(keep)[0]])
     b = np.mean([average_precision_score(y[:, c], want[:, c]) for c in np.where(keep)[0]])
     assert round(float(a), 3) == round(float(b), 3)
+
+
+def test_quantising_frontend_equals_the_default_frontend_at_bench_config(runner24):
+    """K1q + K2q (BN_OPT_FUSION bit 5: magnitudes parked in tensor memory, chunk-wide min / max exchanged between the tile workers
+    through global atomics on a cooperative grid, int8 A operand fetched by TMA) vs K1 + float32 scratch + K2: identical scores
+    on a wave larger than the resident grid (several persistent iterations per worker) and on ragged small batches."""
+    import torch
+
+    from birdnet_stm32 import _lib as L
+
+    pcm, peak = device_chunks(4096 + 37, seed=77)
+    d_pcm, d_peak = torch.as_tensor(pcm, device="cuda"), torch.as_tensor(peak, device="cuda")
+    outs = {}
+    try:
+        for fusion in (11, 43):
+            runner24.set_option(L.BN_OPT_FUSION, fusion)
+            d_out = torch.empty((len(pcm), 100), dtype=torch.float32, device="cuda")
+            runner24.infer_pcm16_ptr(d_pcm.data_ptr(), d_peak.data_ptr(), len(pcm), d_out.data_ptr())
+            torch.cuda.synchronize()
+            outs[fusion] = d_out.cpu().numpy()
+            for n in (1, 7, 19):
+                small = runner24.predict_pcm16(pcm[:n], peak[:n])
+                np.testing.assert_array_equal(small, outs[fusion][:n])
+    finally:
+        runner24.set_option(L.BN_OPT_FUSION, 11)
+    np.testing.assert_array_equal(outs[11], outs[43])

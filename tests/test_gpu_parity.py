@@ -89,9 +89,9 @@ def test_fused_plan_is_active_and_its_tensors_are_bit_exact(runner, graph, oracl
     # fusion 7 = the variant with the depthwise convs of the stride-1 blocks on the tensor core as well (bn_ds_tc.cu);
     # bit 3 (8) = whole-stage kernel for the 8 x 16 stage (bn_stage.cu): its inner block outputs #112 / #115 / #118 stay in
     # shared memory unless bit 4 (16) asks for them (debug taps); bit 5 (32) = quantising frontend, irrelevant for the
-    # spectrogram entry used here.  43 is the default.
+    # spectrogram entry used here.  11 is the default.
     inner = {112, 115, 118}
-    for fusion, taps in ((43, [t for t in BLOCK_OUT_TAPS if t not in inner]), (59, BLOCK_OUT_TAPS), (3, BLOCK_OUT_TAPS), (7, BLOCK_OUT_TAPS),
+    for fusion, taps in ((11, [t for t in BLOCK_OUT_TAPS if t not in inner]), (27, BLOCK_OUT_TAPS), (3, BLOCK_OUT_TAPS), (7, BLOCK_OUT_TAPS),
                          (0, BLOCK_OUT_TAPS + DW_OUT_TAPS)):
         runner.set_option(L.BN_OPT_FUSION, fusion)
         try:
@@ -104,7 +104,7 @@ def test_fused_plan_is_active_and_its_tensors_are_bit_exact(runner, graph, oracl
                 _, o = oracle_model.run(oracle_spec, tap_id=tid)
                 assert np.array_equal(g, o.reshape(-1)), f"fusion={fusion} tensor {tid} differs in {(g != o.reshape(-1)).sum()} of {g.size}"
         finally:
-            runner.set_option(L.BN_OPT_FUSION, 43)
+            runner.set_option(L.BN_OPT_FUSION, 11)
 
 
 def test_fused_kernels_equal_layer_kernels_on_ragged_batches(blob, cfg, synth):
@@ -120,15 +120,17 @@ def test_fused_kernels_equal_layer_kernels_on_ragged_batches(blob, cfg, synth):
         fused = r.predict_pcm16(pcm, peak)
         r.set_option(L.BN_OPT_FUSION, 7)            # tensor-core depthwise variant, ragged last tile
         np.testing.assert_array_equal(fused, r.predict_pcm16(pcm, peak))
-        r.set_option(L.BN_OPT_FUSION, 11)           # K1 + float32 magnitude scratch + K2 instead of the quantising frontend
+        r.set_option(L.BN_OPT_FUSION, 43)           # quantising frontend K1q + K2q (bn_frontend_q.cu) instead of K1 + float32 scratch + K2
         np.testing.assert_array_equal(fused, r.predict_pcm16(pcm, peak))
+        q = r.predict_pcm16(pcm[:5], peak[:5])       # a batch smaller than one CTA's pair of workers
+        np.testing.assert_array_equal(fused[:5], q)
         r.set_option(L.BN_OPT_FUSION, 3)            # ... and one kernel per DS block instead of the whole-stage kernel
         np.testing.assert_array_equal(fused, r.predict_pcm16(pcm, peak))
         r.set_option(L.BN_OPT_FUSION, 0)
         layer = r.predict_pcm16(pcm, peak)
         np.testing.assert_array_equal(fused, layer)
         for n in (1, 2, 3, 5):
-            r.set_option(L.BN_OPT_FUSION, 43)
+            r.set_option(L.BN_OPT_FUSION, 11)
             a = r.predict_pcm16(pcm[:n], peak[:n])
             np.testing.assert_array_equal(a, layer[:n])
     finally:
