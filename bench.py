@@ -263,6 +263,16 @@ def h2d_peak_gbs(torch, dev, nbytes: int, dist=None) -> float:
     return n / (best / 1e3) / 1e9
 
 
+def emit_line(line: dict) -> None:
+    """The ONE JSON line on the real stdout (see the descriptor juggling around NCCL's banner in run_b200)."""
+    sys.stdout.flush()
+    fd = os.environ.pop("_BN_STDOUT_FD", None)
+    if fd is not None:
+        os.dup2(int(fd), 1)
+        os.close(int(fd))
+    print(json.dumps(line), flush=True)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -314,9 +324,14 @@ def run_b200(args):
         import torch.distributed as dist_
 
         dist = dist_
-        # stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) off it
+        # stdout carries exactly one JSON line: NCCL prints its "NCCL version ..." banner from C to file descriptor 1 on
+        # the first collective, so descriptor 1 points at stderr until the line is printed (emit_line)
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
+        if rank == 0 and "_BN_STDOUT_FD" not in os.environ:
+            sys.stdout.flush()
+            os.environ["_BN_STDOUT_FD"] = str(os.dup(1))
+            os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
 
     cfg = load_cfg_24k()
@@ -494,7 +509,7 @@ def run_b200(args):
         line["cpu_baseline"] = {"value": cpu_v, "unit": "chunks/s", "cores": cpu_cores, "kind": "port", "sample": cpu_sample,
                                 "one_thread": {"value": cpu_1, "sample": cpu_1_sample},
                                 "real_reference": try_real_reference()}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
     if dist is not None:
         dist.destroy_process_group()
 

@@ -25,7 +25,7 @@ EXPORTS = (
     "bn_ingest_create", "bn_ingest_destroy", "bn_ingest_out_len", "bn_ingest_num_chunks", "bn_ingest_filter",
     "bn_ingest_window", "bn_ingest_chunks", "bn_ingest_launch_count",
     # include/bn_metrics.h
-    "bn_metrics_compute",
+    "bn_metrics_compute", "bn_metrics_bootstrap_ap",
     # include/bn_reader.h
     "bn_wav_probe", "bn_read_pcm16_batch", "bn_read_raw_batch",
 )
@@ -144,6 +144,7 @@ def load():
     L.bn_ingest_launch_count.argtypes = [vp]
     L.bn_ingest_launch_count.restype = i64
     L.bn_metrics_compute.argtypes = [vp, vp, i32, i32, i32, C.POINTER(BnMetricsResult), vp]
+    L.bn_metrics_bootstrap_ap.argtypes = [vp, vp, i32, i32, i32, C.c_uint64, vp, vp, i32]
     L.bn_wav_probe.argtypes = [C.c_char_p, C.c_double, C.POINTER(BnReaderFile)]
     L.bn_read_raw_batch.argtypes = [C.POINTER(C.c_char_p), i32, C.c_double, vp, C.c_int64, i32, C.POINTER(BnReaderFile), C.POINTER(C.c_int64)]
     L.bn_read_pcm16_batch.argtypes = [C.POINTER(C.c_char_p), i32, i32, i32, i32, C.c_double, vp, i32, i32, C.POINTER(BnReaderFile),

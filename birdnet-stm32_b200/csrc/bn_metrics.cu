@@ -282,3 +282,186 @@ extern "C" int bn_metrics_compute(const float* y_true, const float* y_score, int
   out->n_launches = launches;
   return BN_OK;
 }
+
+// =================================================================================================================
+// Bootstrap confidence intervals of the per-class average precision (reference evaluation/metrics.py:240-322)
+// =================================================================================================================
+namespace bn {
+
+// Philox-4x32-10 (counter-based: resample r, draw i are the counter, the seed is the key)
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int round = 0; round < 10; round++) {
+    const unsigned hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const unsigned hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+
+// mult[r][i] = how often file i is drawn in resample r0 + r (F draws with replacement)
+__global__ void __launch_bounds__(MT_THREADS)
+k_boot_draw(int* __restrict__ mult, int F, int R, int r0, unsigned long long seed) {
+  const long n4 = ((long)F + 3) / 4;
+  for (long t = blockIdx.x * (long)MT_THREADS + threadIdx.x; t < n4 * R; t += (long)gridDim.x * MT_THREADS) {
+    const int r = (int)(t / n4);
+    const long q = t - (long)r * n4;
+    const uint4 u = philox4x32(make_uint4((unsigned)q, (unsigned)(q >> 32), (unsigned)(r0 + r), 0x424e4231u), make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+    const unsigned v[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      if (4 * q + j < F) atomicAdd(mult + (size_t)r * F + __umulhi(v[j], (unsigned)F), 1);
+  }
+}
+
+// class-major sorted order: lab[c][p] = label of the file at sorted position p, end[c][p] = last position of a run of equal scores
+__global__ void __launch_bounds__(MT_THREADS)
+k_boot_prepare(const float* __restrict__ keys, const int* __restrict__ perm, const float* __restrict__ y_true, unsigned char* __restrict__ lab,
+               unsigned char* __restrict__ end, int F, int C) {
+  for (long k = blockIdx.x * (long)MT_THREADS + threadIdx.x; k < (long)F * C; k += (long)gridDim.x * MT_THREADS) {
+    const int c = (int)(k / F);
+    const long p = k - (long)c * F;
+    lab[k] = y_true[(size_t)perm[k] * C + c] != 0.0f ? 1 : 0;
+    end[k] = (p == F - 1 || keys[k] != keys[k + 1]) ? 1 : 0;
+  }
+}
+
+// One CTA per (resample, class): weighted AP = sum over thresholds of (tp_k - tp_{k-1}) / P * tp_k / cnt_k with tp / cnt the
+// multiplicity-weighted running counts in descending-score order (sklearn's average_precision_score on the materialised
+// resample).  NaN when the resample holds a single class (the reference skips those).
+__global__ void __launch_bounds__(MT_THREADS)
+k_boot_ap(const int* __restrict__ mult, const int* __restrict__ perm, const unsigned char* __restrict__ lab, const unsigned char* __restrict__ end,
+          double* __restrict__ ap, int F, int R, int ld_ap) {
+  typedef cub::BlockScan<int2, MT_THREADS> Scan;
+  __shared__ typename Scan::TempStorage tmp;
+  __shared__ double wsum[MT_THREADS / 32];
+  __shared__ int2 carry;
+  const int r = blockIdx.x, c = blockIdx.y;
+  const int* m = mult + (size_t)r * F;
+  const int* pm = perm + (size_t)c * F;
+  const unsigned char* lb = lab + (size_t)c * F;
+  const unsigned char* en = end + (size_t)c * F;
+  struct Add2 { __device__ int2 operator()(int2 a, int2 b) const { return make_int2(a.x + b.x, a.y + b.y); } };
+  if (threadIdx.x == 0) carry = make_int2(0, 0);
+  __syncthreads();
+  double acc = 0.0;
+  int prev_tp_thread = 0;      // tp at the previous threshold is needed: recomputed through a second scan of "tp at ends"
+  for (int base = 0; base < F; base += MT_THREADS) {
+    const int p = base + threadIdx.x;
+    int w = 0, l = 0, e = 0;
+    if (p < F) { w = m[pm[p]]; l = lb[p]; e = en[p]; }
+    int2 run;
+    Scan(tmp).InclusiveScan(make_int2(w * l, w), run, Add2());
+    const int2 c0 = carry;
+    __syncthreads();
+    const int tp = run.x + c0.x, cnt = run.y + c0.y;
+    // previous-threshold tp: the largest tp among earlier threshold ends = max-scan of (e && cnt > 0 ? tp : 0) shifted by one
+    // (tp is non-decreasing along p, so "tp at the last earlier end" = max over earlier ends)
+    const int mark = (e && w >= 0) ? tp : 0;
+    int prev_end_tp;
+    {
+      typedef cub::BlockScan<int, MT_THREADS> ScanI;
+      __shared__ typename ScanI::TempStorage tmp2;
+      __shared__ int carry2;
+      if (base == 0 && threadIdx.x == 0) carry2 = 0;
+      __syncthreads();
+      int ex;
+      ScanI(tmp2).ExclusiveScan(mark, ex, 0, cub::Max());
+      prev_end_tp = max(ex, carry2);
+      __syncthreads();
+      if (threadIdx.x == MT_THREADS - 1) carry2 = max(prev_end_tp, mark);
+    }
+    if (p < F && e && cnt > 0) acc += (double)(tp - prev_end_tp) * ((double)tp / (double)cnt);
+    if (threadIdx.x == MT_THREADS - 1) carry = make_int2(tp, cnt);
+    __syncthreads();
+  }
+  (void)prev_tp_thread;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < MT_THREADS / 32; i++) t += wsum[i];
+    const int P = carry.x, N = carry.y;
+    ap[(size_t)c * ld_ap + r] = (P > 0 && P < N) ? t / (double)P : NAN;
+  }
+}
+
+}  // namespace bn
+
+extern "C" int bn_metrics_bootstrap_ap(const float* y_true, const float* y_score, int F, int C, int n_boot, unsigned long long seed,
+                                       const int32_t* multiplicities, double* ap_samples, int device) {
+  if (!y_true || !y_score || !ap_samples || F <= 0 || C <= 0 || n_boot <= 0) return set_error(BN_ERR_ARG, "bn_metrics_bootstrap_ap: bad arguments");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    return set_error(BN_ERR_CUDA, "no CUDA device for the metric kernels (there is no CPU fallback)");
+  }
+  MT_CU(cudaSetDevice(device));
+  const long n = (long)F * C;
+  if (n >= (1L << 31)) return set_error(BN_ERR_ARG, "bn_metrics_bootstrap_ap: more than 2^31 cells");
+  const bool dev_in = mt_is_device_ptr(y_score);
+  if (dev_in != mt_is_device_ptr(y_true)) return set_error(BN_ERR_ARG, "y_true and y_score must both be host or both be device pointers");
+  cudaStream_t st = nullptr;
+  DevBuf b_true, b_score, b_keys_in, b_idx_in, b_keys, b_perm, b_lab, b_end, b_mult, b_ap, b_offs, b_tmp;
+  const float* d_true = y_true;
+  const float* d_score = y_score;
+  if (!dev_in) {
+    if (b_true.alloc(sizeof(float) * n) || b_score.alloc(sizeof(float) * n)) return set_error(BN_ERR_CUDA, "cudaMalloc failed (bootstrap inputs)");
+    MT_CU(cudaMemcpyAsync(b_true.p, y_true, sizeof(float) * n, cudaMemcpyHostToDevice, st));
+    MT_CU(cudaMemcpyAsync(b_score.p, y_score, sizeof(float) * n, cudaMemcpyHostToDevice, st));
+    d_true = b_true.as<float>();
+    d_score = b_score.as<float>();
+  }
+  // resamples per pass: multiplicity matrix of at most 256 MB
+  int rblk = (int)((256L << 20) / ((long)F * 4));
+  if (rblk < 1) rblk = 1;
+  if (rblk > n_boot) rblk = n_boot;
+  if (b_keys_in.alloc(sizeof(float) * n) || b_idx_in.alloc(sizeof(int) * n) || b_keys.alloc(sizeof(float) * (n + 1)) || b_perm.alloc(sizeof(int) * n) ||
+      b_lab.alloc(n) || b_end.alloc(n) || b_mult.alloc(sizeof(int) * (size_t)rblk * F) || b_ap.alloc(sizeof(double) * (size_t)C * n_boot) ||
+      b_offs.alloc(sizeof(int) * (C + 1)))
+    return set_error(BN_ERR_CUDA, "cudaMalloc failed (bootstrap workspace)");
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  long gb = (n + MT_THREADS - 1) / MT_THREADS;
+  const int grid = (int)(gb < (long)sms * 8 ? gb : (long)sms * 8);
+  // class-major scores; the sort's values are the file indices (k_transpose writes labels: reuse it for the keys only)
+  {
+    dim3 tg((F + 31) / 32, (C + 31) / 32);
+    k_transpose<<<tg, MT_THREADS, 0, st>>>(d_true, d_score, b_keys_in.as<float>(), b_idx_in.as<int>(), F, C);
+    std::vector<int> idx((size_t)n);
+    for (int c = 0; c < C; c++) for (int f = 0; f < F; f++) idx[(size_t)c * F + f] = f;
+    MT_CU(cudaMemcpyAsync(b_idx_in.p, idx.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+    std::vector<int> offs(C + 1);
+    for (int c = 0; c <= C; c++) offs[c] = (int)((long)c * F);
+    MT_CU(cudaMemcpyAsync(b_offs.p, offs.data(), sizeof(int) * (C + 1), cudaMemcpyHostToDevice, st));
+    size_t t1 = 0;
+    MT_CU(cub::DeviceSegmentedRadixSort::SortPairsDescending(nullptr, t1, b_keys_in.as<float>(), b_keys.as<float>(), b_idx_in.as<int>(), b_perm.as<int>(),
+                                                             (int)n, C, b_offs.as<int>(), b_offs.as<int>() + 1, 0, 32, st));
+    if (b_tmp.alloc(t1)) return set_error(BN_ERR_CUDA, "cudaMalloc failed (bootstrap sort workspace)");
+    MT_CU(cub::DeviceSegmentedRadixSort::SortPairsDescending(b_tmp.p, t1, b_keys_in.as<float>(), b_keys.as<float>(), b_idx_in.as<int>(), b_perm.as<int>(),
+                                                             (int)n, C, b_offs.as<int>(), b_offs.as<int>() + 1, 0, 32, st));
+    MT_CU(cudaStreamSynchronize(st));                 // idx / offs are host vectors
+    k_boot_prepare<<<grid, MT_THREADS, 0, st>>>(b_keys.as<float>(), b_perm.as<int>(), d_true, b_lab.as<unsigned char>(), b_end.as<unsigned char>(), F, C);
+  }
+  for (int r0 = 0; r0 < n_boot; r0 += rblk) {
+    const int nr = n_boot - r0 < rblk ? n_boot - r0 : rblk;
+    if (multiplicities) {
+      MT_CU(cudaMemcpyAsync(b_mult.p, multiplicities + (size_t)r0 * F, sizeof(int) * (size_t)nr * F,
+                            mt_is_device_ptr(multiplicities) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    } else {
+      MT_CU(cudaMemsetAsync(b_mult.p, 0, sizeof(int) * (size_t)nr * F, st));
+      const long work = (((long)F + 3) / 4) * nr;
+      long g2 = (work + MT_THREADS - 1) / MT_THREADS;
+      k_boot_draw<<<(int)(g2 < (long)sms * 16 ? g2 : (long)sms * 16), MT_THREADS, 0, st>>>(b_mult.as<int>(), F, nr, r0, seed);
+    }
+    k_boot_ap<<<dim3(nr, C), MT_THREADS, 0, st>>>(b_mult.as<int>(), b_perm.as<int>(), b_lab.as<unsigned char>(), b_end.as<unsigned char>(),
+                                                  b_ap.as<double>() + r0, F, nr, n_boot);
+  }
+  MT_CU(cudaMemcpyAsync(ap_samples, b_ap.p, sizeof(double) * (size_t)C * n_boot, cudaMemcpyDeviceToHost, st));
+  MT_CU(cudaStreamSynchronize(st));
+  MT_CU(cudaGetLastError());
+  return BN_OK;
+}

@@ -47,6 +47,16 @@ typedef struct bn_metrics_result {
 BN_API int bn_metrics_compute(const float* y_true, const float* y_score, int F, int C, int device, bn_metrics_result* out,
                               double* ap_per_class);
 
+/* Bootstrap resamples of the per-class average precision (reference: bootstrap_ap_ci, evaluation/metrics.py:240-322: n_bootstrap
+ * resamples of the F files with replacement per class, AP of every resample, percentiles).  ap_samples: float64 [C, n_boot]
+ * (host), NaN where the resample holds a single class of that column (the reference skips those).  A resample is a vector of
+ * multiplicities over the files; every class is sorted ONCE and a resample's AP is two running sums in that order.
+ * multiplicities: optional int32 [n_boot, F] (host or device) -- the caller's own resamples, shared by all classes (this is how
+ * the tests compare with the host formulation exactly); NULL = drawn on the device from a counter-based generator
+ * (Philox-4x32-10 keyed by `seed`): statistically equivalent to the reference's intervals, not its numpy PCG64 stream. */
+BN_API int bn_metrics_bootstrap_ap(const float* y_true, const float* y_score, int F, int C, int n_boot, unsigned long long seed,
+                                   const int32_t* multiplicities, double* ap_samples, int device);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,3 +72,53 @@ def test_evaluate_with_device_metrics_backend(tmp_path, blob, cfg):
             evaluate(runner, files, classes, cfg, metrics_backend="nope")
     finally:
         runner.close()
+
+
+@pytest.mark.gpu
+def test_bootstrap_ap_on_the_device():
+    """Row f2 tail (reference `bootstrap_ap_ci`, evaluation/metrics.py:240-322).  (1) Given the SAME resamples (multiplicity vectors)
+    the device APs equal the host formulation (`_weighted_ap_sorted`, itself equal to scikit-learn on the materialised
+    resample) to 1e-12, ties and single-class resamples included; (2) with its own generator the intervals agree with the
+    host version's within Monte-Carlo error and every file is drawn F times per resample."""
+    from sklearn.metrics import average_precision_score
+
+    from birdnet_stm32.evaluation.device_metrics import bootstrap_ap_ci_device, bootstrap_ap_samples_device
+    from birdnet_stm32.evaluation.metrics import bootstrap_ap_ci
+
+    rng = np.random.default_rng(11)
+    F, Cn, R = 700, 9, 64
+    y = (rng.random((F, Cn)) < 0.15).astype(np.float32)
+    y[:, 7] = 0.0                                               # a class without positives
+    y[:, 8] = 0.0
+    y[3, 8] = 1.0                                               # a single positive: many single-class resamples
+    s = np.round(rng.random((F, Cn)), 2).astype(np.float32)     # heavy ties
+    s[:, :3] = rng.random((F, 3)).astype(np.float32)
+    idx = rng.integers(0, F, size=(R, F))
+    mult = np.stack([np.bincount(r, minlength=F) for r in idx]).astype(np.int32)
+    got = bootstrap_ap_samples_device(y, s, R, multiplicities=mult)
+    assert got.shape == (Cn, R)
+    for c in range(Cn):
+        for r in range(0, R, 7):
+            yt, ys = y[idx[r], c], s[idx[r], c]
+            if yt.sum() == 0 or yt.sum() == F:
+                assert np.isnan(got[c, r])
+            else:
+                assert abs(got[c, r] - average_precision_score(yt, ys)) < 1e-12, (c, r)
+    # own generator: multiplicities sum to F, intervals close to the host version's
+    classes = [f"c{i}" for i in range(Cn)]
+    dev = bootstrap_ap_ci_device(y, s, classes, n_bootstrap=600, seed=5)
+    host = bootstrap_ap_ci(y, s, classes, n_bootstrap=600, seed=5)
+    for d, h in zip(dev, host):
+        assert d["class"] == h["class"] and d["n_positive"] == h["n_positive"] and d["n_total"] == h["n_total"]
+        assert abs(d["ap"] - h["ap"]) < 1e-12
+        # two independent sets of 600 resamples: percentile estimates differ by Monte-Carlo error (larger for the class with a
+        # single positive, whose resampled AP takes few distinct values)
+        width = max(h["ci_upper"] - h["ci_lower"], 1e-9)
+        tol = 0.35 * width + 0.003
+        assert abs(d["ci_lower"] - h["ci_lower"]) < tol and abs(d["ci_upper"] - h["ci_upper"]) < tol, (d, h)
+        assert d["ci_lower"] <= d["ci_upper"]
+    a = bootstrap_ap_samples_device(y, s, 16, seed=1)
+    b = bootstrap_ap_samples_device(y, s, 16, seed=1)
+    c = bootstrap_ap_samples_device(y, s, 16, seed=2)
+    np.testing.assert_array_equal(a, b)
+    assert not np.array_equal(a[:3], c[:3])
