@@ -20,6 +20,7 @@
 
 #include "bn_common.cuh"
 #include "bn_fast.cuh"
+#include "bn_generic_tc.cuh"
 #include "bn_kernels.cuh"
 
 using namespace bn;
@@ -81,6 +82,7 @@ struct bn_engine {
   // options
   int rounding = 0, mean_variant = 0, force_generic = 0;
   FastPlan fast;
+  GenAccel* accel = nullptr;          // tensor-core pointwise convolutions of the generic plan
   Profiler prof;
   int64_t launches = 0;
 };
@@ -162,6 +164,7 @@ extern "C" int bn_create(const void* blob, size_t nbytes, int device, bn_engine*
   e->buf.assign(e->hdr->n_tensors, nullptr);
   e->last_ptr.assign(e->hdr->n_tensors, nullptr);
   fast_plan_build(e->fast, e->blob.data(), e->hdr, e->tensors, e->ops, e->d_blob);
+  e->accel = gen_accel_build(e->blob.data(), e->hdr, e->tensors, e->ops);
   { int sms = 148; if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) e->fast.num_sms = sms; }
   *out = e;
   return BN_OK;
@@ -181,6 +184,8 @@ extern "C" void bn_destroy(bn_engine* e) {
   cudaSetDevice(e->device);
   if (e->hdr) free_workspace(e);
   fast_plan_destroy(e->fast);
+  gen_accel_destroy(e->accel);
+  e->accel = nullptr;
   for (int i = 0; i < 2; i++) {
     if (e->d_pcm[i]) cudaFree(e->d_pcm[i]);
     if (e->d_peak[i]) cudaFree(e->d_peak[i]);
@@ -300,7 +305,15 @@ static int run_generic(bn_engine* e, std::vector<void*>& ptr, int Bw, cudaStream
         for (int d = axis; d < 3; d++) { in0 *= ti->dims[d]; in1 *= t1.dims[d]; }
         launch_concat((const int8_t*)x, (const int8_t*)ptr[op.in[1]], (int8_t*)y, outer * Bw, (int)in0, (int)in1, st);
       } break;
-      case BN_OP_CONV2D: { ConvParams P; fill_conv(e, op, P); launch_conv2d((const int8_t*)x, (int8_t*)y, n_out, P, st); } break;
+      case BN_OP_CONV2D: {
+        if (e->accel && e->accel->ops[oi].pw && R == 0 && e->fast.use_tc) {
+          const long M = (long)to.dims[0] * to.dims[1] * Bw;
+          int rc = launch_pw_tc((const int8_t*)x, nullptr, (int8_t*)y, M, e->accel->ops[oi].tc, e->fast.num_sms, st);
+          if (rc) return rc;
+        } else {
+          ConvParams P; fill_conv(e, op, P); launch_conv2d((const int8_t*)x, (int8_t*)y, n_out, P, st);
+        }
+      } break;
       case BN_OP_DWCONV2D: { ConvParams P; fill_conv(e, op, P); launch_dwconv2d((const int8_t*)x, (int8_t*)y, n_out, P, st); } break;
       case BN_OP_FC: {
         ConvParams P; fill_conv(e, op, P);
