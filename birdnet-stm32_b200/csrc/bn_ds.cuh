@@ -60,6 +60,11 @@ struct DsLaunch {
 int launch_ds(const int8_t* in, int8_t* out, int Bw, const DsParams& P, const DsLaunch& L, int num_sms, cudaStream_t st);
 size_t ds_smem_bytes(const DsParams& P, int S, int TR);
 
+// warp-specialised pipeline form of the same block (bn_ds_ws.cu): P.nst = 3 | 4 input-tile buffers, two A operands, two accumulators
+int launch_dsw(const int8_t* in, int8_t* out, int Bw, const DsParams& P, const DsLaunch& L, int num_sms, cudaStream_t st);
+size_t dsw_smem_bytes(const DsParams& P, int S, int TR);
+bool dsw_supported(const DsParams& P, int S, int TR, int add_mode);
+
 int launch_dst(const int8_t* in, int8_t* out, int Bw, const DsParams& P, const DsLaunch& L, int num_sms, cudaStream_t st);
 size_t dst_smem_bytes(const DsParams& P);
 void dst_weight_image(const int8_t* w, int C, std::vector<uint8_t>& img);

@@ -310,11 +310,24 @@ static int run_generic(bn_engine* e, std::vector<void*>& ptr, int Bw, cudaStream
           const long M = (long)to.dims[0] * to.dims[1] * Bw;
           int rc = launch_pw_tc((const int8_t*)x, nullptr, (int8_t*)y, M, e->accel->ops[oi].tc, e->fast.num_sms, st);
           if (rc) return rc;
+        } else if (e->accel && e->accel->ops[oi].stem) {
+          int rc = launch_stem((const int8_t*)x, (int8_t*)y, Bw, e->accel->ops[oi].stp, R, st);
+          if (rc) return rc;
+        } else if (e->accel && e->accel->ops[oi].pwc) {
+          int rc = launch_pw((const int8_t*)x, nullptr, (int8_t*)y, (long)to.dims[0] * to.dims[1] * Bw, e->accel->ops[oi].pwp, R, st);
+          if (rc) return rc;
         } else {
           ConvParams P; fill_conv(e, op, P); launch_conv2d((const int8_t*)x, (int8_t*)y, n_out, P, st);
         }
       } break;
-      case BN_OP_DWCONV2D: { ConvParams P; fill_conv(e, op, P); launch_dwconv2d((const int8_t*)x, (int8_t*)y, n_out, P, st); } break;
+      case BN_OP_DWCONV2D: {
+        if (e->accel && e->accel->ops[oi].dw) {
+          int rc = launch_dw3x3((const int8_t*)x, (int8_t*)y, Bw, e->accel->ops[oi].dwp, R, st);
+          if (rc) return rc;
+        } else {
+          ConvParams P; fill_conv(e, op, P); launch_dwconv2d((const int8_t*)x, (int8_t*)y, n_out, P, st);
+        }
+      } break;
       case BN_OP_FC: {
         ConvParams P; fill_conv(e, op, P);
         launch_fc((const int8_t*)x, (int8_t*)y, n_out, P, st);
@@ -708,7 +721,7 @@ extern "C" int bn_set_option(bn_engine* e, int key, int value) {
     case BN_OPT_TENSOR_CORE:
       e->fast.use_tc = value ? 1 : 0; break;
     case BN_OPT_FUSION:
-      e->fast.fusion = value & 63; break;
+      e->fast.fusion = value & 127; break;
     case BN_OPT_PROFILE:
       cudaDeviceSynchronize();
       e->prof.collect();

@@ -19,6 +19,7 @@
 #include <map>
 
 #include "bn_ds.cuh"
+#include "bn_layer.cuh"
 #include "bn_stage.cuh"
 #include "bn_frontend_q.cuh"
 #include "bn_head_tc.cuh"
@@ -78,37 +79,6 @@ constexpr int HEAD_N = 64;        // mel channels handled by the head kernel
 constexpr int HEAD_M = 128;       // frames per CTA
 constexpr int GEMM_LDA = 132;     // words per k-row of the transposed A tile (128 + 4 pad, keeps 16-byte alignment)
 
-struct PwParams {                 // pointwise conv (+ residual add) -- device pointers
-  const int* wt;                  // [K/4][N] words: 4 consecutive k of channel n
-  const int* bias;                // folded bias'
-  const int* mult;
-  const int* shift;
-  int K, N;
-  int out_zp, act_min, act_max;   // of the conv itself
-  int fast;                       // all channels requantise with a right shift >= 1
-  int has_add;
-  const int* lut_res;             // [256] rescaled residual   (add input 1)
-  const int* lut_conv;            // [256] rescaled conv output (add input 2)
-  int add_mo, add_so, add_out_zp, add_act_min, add_act_max;
-};
-
-struct DwParams {
-  const int* wm;                  // [9][C/4][4] masked weight words
-  const int* bias; const int* mult; const int* shift;   // [C]
-  int C, ih, iw, oh, ow, sh, sw, pt, pl;
-  int in_zp, out_zp, act_min, act_max;
-  int fast;
-};
-
-struct StemParams {
-  const int* w;                   // [16][3] words (w0,w1,w2,0) per (co, fy)
-  const int* bias; const int* mult; const int* shift;
-  int ih, iw, oh, ow, in_zp, out_zp, act_min, act_max;
-  int fast;
-  const int4* pk;                 // [16][2] {w_fy0, w_fy1, w_fy2, n - 1}, {c_lo, c_hi, mult, 0}: saturating form (rq_hi)
-  int sat;                        // pk is valid (zp_out = -128, clamp [-128, 127], int32-safe)
-};
-
 struct HeadParams {
   const int* wt; const int* bias; const int* mult; const int* shift;
   const uint8_t* lut;             // [64][256] folded element-wise chain, indexed by code + 128
@@ -145,6 +115,9 @@ struct Block {
   DsParams dst{};                 // same block with the depthwise conv on the tensor core too (bn_ds_tc.cu)
   DsLaunch dstl{};
   bool dst_ok = false;
+  DsParams dsw{};          // warp-specialised pipeline form (bn_ds_ws.cu), BN_OPT_FUSION bit 6
+  DsLaunch dswl{};
+  bool dsw_ok = false;
 };
 
 struct StagePlan {                // blocks [first, first + nl) run as ONE kernel (bn_stage.cu)
@@ -631,6 +604,39 @@ static bool prep_ds(FastPlan& fp, FastImpl* im, Block& bl) {
         bl.dstl = L; bl.dstl.smem = best_sm; bl.dstl.ctas_per_sm = best_per; bl.dstl.tcdw = 1; bl.dstl.TR = best_tr;
         bl.dst_ok = true;
         if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: tensor-core depthwise C=%d TR=%d MTd=%d plane_px=%d smem=%zu ctas/SM=%d tmem=%d\n", C, best_tr, bl.dst.MTd, bl.dst.plane_px, best_sm, best_per, best_cols);
+      }
+    }
+  }
+  // Warp-specialised pipeline form (bn_ds_ws.cu): own tile height (small tiles cost it nothing: there is no CTA barrier per
+  // tile) and 3 - 4 input-tile buffers; needs two 384-thread CTAs per SM.
+  bl.dsw_ok = false;
+  if (L.dwt && npix >= 128 ? true : (L.dwt && NB * ((TR - 1) * S + 3) <= 32)) {
+    const int limit = 225 * 1024;
+    const int want_tr = getenv("BN_DSW_TR") ? atoi(getenv("BN_DSW_TR")) : 0;
+    const int want_nst = getenv("BN_DSW_NST") ? atoi(getenv("BN_DSW_NST")) : 0;
+    for (int tr : {8, 4}) {
+      if (bl.dsw_ok) break;
+      int nb = 1;
+      if (npix < 128) { if (tr != TR) continue; nb = NB; }
+      else if (tr > D.oh || D.oh % tr || (tr * D.ow) % 128) continue;
+      if (want_tr && npix >= 128 && tr != want_tr) continue;
+      for (int nst : {4, 3}) {
+        if (want_nst && nst != want_nst) continue;
+        DsParams Q = D;
+        Q.NB = nb; Q.MT = tr * D.ow * nb / 128; Q.nst = nst; Q.TRr = tr; Q.epi_smem = 0;
+        Q.trow_log = ilog2_exact(tr * D.ow);
+        if (Q.MT < 1 || Q.trow_log < 0) continue;
+        int c2 = 32; while (c2 < 2 * Q.MT * N) c2 <<= 1;
+        if (c2 > 256) continue;                        // two CTAs per SM share the 512 columns
+        Q.tmem_cols = c2;
+        const size_t sm = dsw_smem_bytes(Q, S, tr);
+        if (2 * (sm + 1024) > (size_t)limit) continue;
+        if (!dsw_supported(Q, S, tr, L.add_mode)) continue;
+        bl.dsw = Q;
+        bl.dswl = L; bl.dswl.TR = tr; bl.dswl.smem = sm; bl.dswl.ctas_per_sm = 2; bl.dswl.threads = 384; bl.dswl.epi = 0;
+        bl.dsw_ok = true;
+        if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: warp-specialised C=%d N=%d S=%d TR=%d NB=%d nst=%d smem=%zu tmem=%d\n", C, N, S, tr, nb, nst, sm, c2);
+        break;
       }
     }
   }
@@ -1568,6 +1574,107 @@ static size_t pw_smem(const PwParams& P) {
   return ((size_t)KW * GEMM_LDA + (size_t)KW * NP + 3 * NP + 512) * 4;
 }
 
+// Stem (3x3 stride-(1,2) convolution, 1 -> 16 channels) for callers outside the fused plan: parameter block from a blob op.
+bool stem_build(const uint8_t* h_blob, const bn_blob_tensor* T, const bn_blob_op& st, std::vector<void*>& owned, StemParams& S) {
+  if (st.kind != BN_OP_CONV2D || st.p[BN_CONV_KH] != 3 || st.p[BN_CONV_KW] != 3 || st.p[BN_CONV_CIN] != 1 || st.p[BN_CONV_COUT] != 16 ||
+      st.p[BN_CONV_SH] != 1 || st.p[BN_CONV_SW] != 2 || st.p[BN_CONV_PAD_T] != 1 || st.p[BN_CONV_PAD_L] != 0) return false;
+  const bn_blob_tensor& ti = T[st.in[0]];
+  const bn_blob_tensor& to = T[st.out];
+  if (ti.dims[2] != 1 || to.dims[2] != 16 || ti.dims[1] % 4 || to.dims[0] != ti.dims[0] || to.dims[1] * 2 != ti.dims[1]) return false;
+  auto up = [&](const void* src, size_t n) -> void* {
+    void* d = nullptr;
+    if (cudaMalloc(&d, n ? n : 4) != cudaSuccess) return nullptr;
+    cudaMemcpy(d, src, n, cudaMemcpyHostToDevice);
+    owned.push_back(d);
+    return d;
+  };
+  const int8_t* w = (const int8_t*)(h_blob + st.off[0]);
+  const int32_t* bias = (const int32_t*)(h_blob + st.off[1]);
+  const int32_t* mult = (const int32_t*)(h_blob + st.off[2]);
+  const int32_t* shift = (const int32_t*)(h_blob + st.off[3]);
+  const int zp = st.p[BN_CONV_IN_ZP];
+  const long xmax = (127 - zp) > (zp + 128) ? (127 - zp) : (zp + 128);
+  std::vector<int> ww(16 * 3), bf(16), m(mult, mult + 16), sh(shift, shift + 16);
+  int fast = 1;
+  for (int co = 0; co < 16; co++) {
+    long ws = 0, wsum = 0;
+    for (int fy = 0; fy < 3; fy++) {
+      unsigned word = 0;
+      for (int fx = 0; fx < 3; fx++) { int8_t v = w[(co * 3 + fy) * 3 + fx]; ws += v; wsum += labs((long)v); word |= (unsigned)(uint8_t)v << (8 * fx); }
+      ww[co * 3 + fy] = (int)word;
+    }
+    bf[co] = (int)((long)bias[co] - (long)zp * ws);
+    if (m[co] == 0) sh[co] = -1;
+    if (sh[co] > -1 || sh[co] < -31) { fast = 0; continue; }
+    const long amax = labs((long)bias[co]) + wsum * xmax;
+    const long vmax = (long)(((__int128)amax * m[co] + (1ll << 30)) >> 31) + 1;
+    if (vmax + (1l << (-sh[co] - 1)) >= (1l << 31)) fast = 0;
+  }
+  S.w = (const int*)up(ww.data(), ww.size() * 4);
+  S.bias = (const int*)up(bf.data(), bf.size() * 4);
+  S.mult = (const int*)up(m.data(), m.size() * 4);
+  S.shift = (const int*)up(sh.data(), sh.size() * 4);
+  S.fast = fast;
+  S.ih = ti.dims[0]; S.iw = ti.dims[1]; S.oh = to.dims[0]; S.ow = to.dims[1];
+  S.in_zp = zp; S.out_zp = st.p[BN_CONV_OUT_ZP]; S.act_min = st.p[BN_CONV_ACT_MIN]; S.act_max = st.p[BN_CONV_ACT_MAX];
+  S.sat = 0; S.pk = nullptr;
+  FastPlan tmp;
+  tmp.h_blob = h_blob;
+  std::vector<int> rq, rz;
+  if (build_rq_folded(tmp, st, 16, rq, rz, true) && S.iw % 8 == 0 && S.ow % 4 == 0) {
+    std::vector<int> pk(16 * 8);
+    for (int co = 0; co < 16; co++) {
+      pk[co * 8 + 0] = ww[co * 3 + 0]; pk[co * 8 + 1] = ww[co * 3 + 1]; pk[co * 8 + 2] = ww[co * 3 + 2]; pk[co * 8 + 3] = rq[4 * co + 3];
+      pk[co * 8 + 4] = rq[4 * co + 0]; pk[co * 8 + 5] = rq[4 * co + 1]; pk[co * 8 + 6] = rq[4 * co + 2]; pk[co * 8 + 7] = 0;
+    }
+    S.pk = (const int4*)up(pk.data(), pk.size() * 4);
+    S.sat = S.pk != nullptr;
+  }
+  return S.w && S.bias && S.mult && S.shift;
+}
+
+int launch_stem(const int8_t* in, int8_t* out, int Bw, const StemParams& S, int R, cudaStream_t st) {
+  if (Bw < 1) return 0;
+  dim3 grid((S.oh + STEM_ROWS - 1) / STEM_ROWS, Bw);
+  const size_t smem = (size_t)(STEM_ROWS + 2) * (S.iw + 8) + 96 * 4;
+  if (S.sat && R == 0) k_stem_sat<<<grid, 256, smem + 32 * 16 + 16, st>>>(in, out, S);
+  else if (S.fast && R == 0) k_stem<true><<<grid, 256, smem, st>>>(in, out, S, R);
+  else k_stem<false><<<grid, 256, smem, st>>>(in, out, S, R);
+  return 0;
+}
+
+// Launchers of the per-layer kernels for callers outside the fused plan (the generic plan's accelerated ops, bn_generic_tc.cu).
+int launch_dw3x3(const int8_t* in, int8_t* out, int Bw, const DwParams& D, int R, cudaStream_t st) {
+  if (D.C % 4 || Bw < 1) return BN_ERR_UNSUPPORTED;
+  const int npair = ((D.ow + 1) / 2) * (D.C / 4);
+  const int rows_per_band = 8;
+  dim3 grid(((npair + DW_THREADS - 1) / DW_THREADS) * ((D.oh + rows_per_band - 1) / rows_per_band), Bw);
+  const bool f = D.fast && R == 0;
+  if (D.sh == 1) { if (f) k_dw3x3<1, true><<<grid, DW_THREADS, 0, st>>>(in, out, D, rows_per_band, R); else k_dw3x3<1, false><<<grid, DW_THREADS, 0, st>>>(in, out, D, rows_per_band, R); }
+  else if (D.sh == 2) { if (f) k_dw3x3<2, true><<<grid, DW_THREADS, 0, st>>>(in, out, D, rows_per_band, R); else k_dw3x3<2, false><<<grid, DW_THREADS, 0, st>>>(in, out, D, rows_per_band, R); }
+  else return BN_ERR_UNSUPPORTED;
+  return 0;
+}
+
+size_t pw_cuda_core_smem(int K, int N) {
+  const int KW = K / 4, NP = N < 64 ? 64 : N;
+  return ((size_t)KW * GEMM_LDA + (size_t)KW * NP + 3 * NP + 512) * 4;
+}
+
+int launch_pw(const int8_t* x, const int8_t* res, int8_t* y, long M, const PwParams& P, int R, cudaStream_t st) {
+  const size_t smem = pw_cuda_core_smem(P.K, P.N);
+  if (P.K % 4 || P.N % 4 || smem > 225 * 1024 || M < 1) return BN_ERR_UNSUPPORTED;
+  static unsigned long long attr = 0;
+  if (first_use_on_device(attr)) {
+    cudaFuncSetAttribute(k_pw<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(k_pw<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  }
+  const int grid = (int)((M + 127) / 128);
+  if (P.fast && R == 0) k_pw<true><<<grid, 256, smem, st>>>(x, res, y, M, P, R);
+  else k_pw<false><<<grid, 256, smem, st>>>(x, res, y, M, P, R);
+  return 0;
+}
+
 // K2 for chunks [b0, b0 + nb) of the wave: src / mnmx already point at the first of them
 static int run_head(FastPlan& fp, int mode, const float* src, const unsigned* mnmx, int b0, int nb, int rounding, cudaStream_t st,
                     int64_t* launches, Profiler* prof) {
@@ -1650,9 +1757,12 @@ static int run_body(FastPlan& fp, int Bw, float* d_scores, int rounding, int mea
     int8_t* bout = (int8_t*)im->slot_buf[bl.out_slot];
     if ((fp.fusion & 1) && bl.ds_ok && fp.use_tc && R == 0) {
       const bool tcdw = (fp.fusion & 4) && bl.dst_ok;
-      snprintf(name, sizeof name, "%s_%02d_c%d_n%d_s%d%s", tcdw ? "K45t_ds" : "K45_ds", bi, bl.ds.C, bl.ds.N, bl.dsl.S, bl.add_op >= 0 ? "_add" : "");
+      const bool ws = !tcdw && (fp.fusion & 64) && bl.dsw_ok;
+      snprintf(name, sizeof name, "%s_%02d_c%d_n%d_s%d%s", tcdw ? "K45t_ds" : ws ? "K45w_ds" : "K45_ds", bi, bl.ds.C, bl.ds.N, bl.dsl.S, bl.add_op >= 0 ? "_add" : "");
       if (prof) prof->begin(name, st);
-      int rc = tcdw ? launch_dst(bin, bout, Bw, bl.dst, bl.dstl, fp.num_sms, st) : launch_ds(bin, bout, Bw, bl.ds, bl.dsl, fp.num_sms, st);
+      int rc = tcdw ? launch_dst(bin, bout, Bw, bl.dst, bl.dstl, fp.num_sms, st)
+             : ws   ? launch_dsw(bin, bout, Bw, bl.dsw, bl.dswl, fp.num_sms, st)
+                    : launch_ds(bin, bout, Bw, bl.ds, bl.dsl, fp.num_sms, st);
       if (prof) prof->end(st);
       if (rc) return rc;
       (*launches)++;

@@ -201,6 +201,56 @@ __global__ void k_mul(const int8_t* __restrict__ a, const int8_t* __restrict__ b
   }
 }
 
+// Four elements per thread (one 32-bit word of each operand) and 32-bit index arithmetic: same arithmetic per element as
+// k_add / k_mul.  Needs n, C and per_chunk to be multiples of 4, word-aligned pointers and n < 2^31.
+__global__ void k_add4(const unsigned* __restrict__ a, const int8_t* __restrict__ b, unsigned* __restrict__ y, unsigned n4,
+                       unsigned per_chunk, AddParams P) {
+  for (unsigned w = blockIdx.x * blockDim.x + threadIdx.x; w < n4; w += gridDim.x * blockDim.x) {
+    const unsigned i = 4u * w;
+    const unsigned bi = P.bcast == 0 ? i : (P.bcast == 1 ? (i % (unsigned)P.C) : ((i / per_chunk) * (unsigned)P.C + (i % (unsigned)P.C)));
+    const unsigned av = a[w], bv = *reinterpret_cast<const unsigned*>(b + bi);
+    unsigned o4 = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int v1 = (int)(int8_t)(av >> (8 * j)) - P.in1_zp;
+      const int v2 = (int)(int8_t)(bv >> (8 * j)) - P.in2_zp;
+      const int s1 = mbqm(v1 << P.left_shift, P.m1, P.s1, P.rounding);
+      const int s2 = mbqm(v2 << P.left_shift, P.m2, P.s2, P.rounding);
+      const int o = mbqm(s1 + s2, P.mo, P.so, P.rounding) + P.out_zp;
+      o4 |= (unsigned)(uint8_t)clampi(o, P.act_min, P.act_max) << (8 * j);
+    }
+    y[w] = o4;
+  }
+}
+
+__global__ void k_mul4(const unsigned* __restrict__ a, const int8_t* __restrict__ b, unsigned* __restrict__ y, unsigned n4,
+                       unsigned per_chunk, int in1_zp, int in2_zp, int out_zp, int mult, int shift, int act_min,
+                       int act_max, int bcast, int C, int R) {
+  for (unsigned w = blockIdx.x * blockDim.x + threadIdx.x; w < n4; w += gridDim.x * blockDim.x) {
+    const unsigned i = 4u * w;
+    const unsigned av = a[w];
+    unsigned bv;
+    if (bcast == 3) bv = 0x01010101u * (unsigned)(uint8_t)b[i / (unsigned)C];
+    else {
+      const unsigned bi = bcast == 0 ? i : (bcast == 1 ? (i % (unsigned)C) : ((i / per_chunk) * (unsigned)C + (i % (unsigned)C)));
+      bv = *reinterpret_cast<const unsigned*>(b + bi);
+    }
+    unsigned o4 = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int v = ((int)(int8_t)(av >> (8 * j)) - in1_zp) * ((int)(int8_t)(bv >> (8 * j)) - in2_zp);
+      const int o = mbqm(v, mult, shift, R) + out_zp;
+      o4 |= (unsigned)(uint8_t)clampi(o, act_min, act_max) << (8 * j);
+    }
+    y[w] = o4;
+  }
+}
+
+static inline bool words_ok(const void* a, const void* b, const void* y, long n, long per_chunk, int C) {
+  return n > 0 && n < (1l << 31) && n % 4 == 0 && per_chunk % 4 == 0 && C % 4 == 0 &&
+         (((uintptr_t)a | (uintptr_t)b | (uintptr_t)y) & 3) == 0;
+}
+
 // PAD with the zero point: x [B][d0][d1][d2] -> y [B][o0][o1][o2], o = d + before + after
 __global__ void k_pad(const int8_t* __restrict__ x, int8_t* __restrict__ y, long n, int d0, int d1, int d2, int o0, int o1, int o2,
                       int b0, int b1, int b2, int val) {
@@ -345,8 +395,19 @@ void launch_concat(const int8_t* x0, const int8_t* x1, int8_t* y, long rows, int
 void launch_conv2d(const int8_t* x, int8_t* y, long n, const ConvParams& P, cudaStream_t st) { LAUNCH(k_conv2d, n, st, x, y, n, P); }
 void launch_dwconv2d(const int8_t* x, int8_t* y, long n, const ConvParams& P, cudaStream_t st) { LAUNCH(k_dwconv2d, n, st, x, y, n, P); }
 void launch_fc(const int8_t* x, int8_t* y, long n, const ConvParams& P, cudaStream_t st) { LAUNCH(k_fc, n, st, x, y, n, P); }
-void launch_add(const int8_t* a, const int8_t* b, int8_t* y, long n, long per_chunk, const AddParams& P, cudaStream_t st) { LAUNCH(k_add, n, st, a, b, y, n, per_chunk, P); }
+void launch_add(const int8_t* a, const int8_t* b, int8_t* y, long n, long per_chunk, const AddParams& P, cudaStream_t st) {
+  if (words_ok(a, b, y, n, per_chunk, P.C)) {
+    LAUNCH(k_add4, n / 4, st, reinterpret_cast<const unsigned*>(a), b, reinterpret_cast<unsigned*>(y), (unsigned)(n / 4), (unsigned)per_chunk, P);
+    return;
+  }
+  LAUNCH(k_add, n, st, a, b, y, n, per_chunk, P);
+}
 void launch_mul(const int8_t* a, const int8_t* b, int8_t* y, long n, long per_chunk, const int* p, int C, int R, cudaStream_t st) {
+  if (words_ok(a, b, y, n, per_chunk, C)) {
+    LAUNCH(k_mul4, n / 4, st, reinterpret_cast<const unsigned*>(a), b, reinterpret_cast<unsigned*>(y), (unsigned)(n / 4), (unsigned)per_chunk,
+           p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], C, R);
+    return;
+  }
   LAUNCH(k_mul, n, st, a, b, y, n, per_chunk, p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], C, R);
 }
 void launch_mean(const int8_t* x, int8_t* y, long n, int N, int C, const int* p, float in_scale, float out_scale, int variant, int R, cudaStream_t st) {

@@ -4,7 +4,9 @@
 // residuals, attention pooling -- reference models/blocks.py:27-175, models/frontend.py:347-358) run one kernel per lowered op.
 // Their 1x1 convolutions hold 85 - 95 % of the MACs; every one whose shape the tcgen05 GEMM of bn_pw_tc.cu supports and whose
 // requantisation lies in the proven closed-form domain is routed through that kernel instead of the one-thread-per-output
-// reference kernel (same integer results; covered by the bit-exact tests of tests/test_ptq.py).
+// reference kernel (same integer results; covered by the bit-exact tests of tests/test_ptq.py).  The 1x1 convolutions the GEMM
+// has no build for (K or N = 512 in the inverted-residual expansions) take the tiled dp4a GEMM of the layer path, and every
+// depthwise 3x3 (stride 1 | 2) the register-window kernel of the layer path (k_pw / k_dw3x3, bn_fast.cu).
 #include "bn_generic_tc.cuh"
 
 #include <cstdlib>
@@ -22,20 +24,110 @@ static void* up(GenAccel* a, const void* src, size_t n) {
   return d;
 }
 
+// closed-form requantisation domain (right shift in [1, 31], |SRDHM(acc)| + 2^(n-1) < 2^31) of channel n with sum |w| = wsum
+static bool rq_domain_ok(long bias, long wsum, long xmax, int mult, int& shift) {
+  if (mult == 0) shift = -1;
+  if (shift > -1 || shift < -31) return false;
+  const long amax = labs(bias) + wsum * xmax;
+  const long vmax = (long)(((__int128)amax * mult + (1ll << 30)) >> 31) + 1;
+  return vmax + (1l << (-shift - 1)) < (1l << 31);
+}
+
+static void build_dw(GenAccel* a, GenAccelOp& g, const uint8_t* h_blob, const bn_blob_tensor* T, const bn_blob_op& op) {
+  const int32_t* p = op.p;
+  const int C = p[BN_CONV_CIN];
+  if (p[BN_CONV_KH] != 3 || p[BN_CONV_KW] != 3 || p[BN_CONV_SH] != p[BN_CONV_SW] || (p[BN_CONV_SH] != 1 && p[BN_CONV_SH] != 2)) return;
+  if (C % 4 || p[BN_CONV_COUT] != C) return;
+  const bn_blob_tensor& ti = T[op.in[0]];
+  const bn_blob_tensor& to = T[op.out];
+  if (ti.dims[2] != C || to.dims[2] != C) return;
+  const int8_t* w = (const int8_t*)(h_blob + op.off[0]);             // [3][3][C]
+  const int32_t* bias = (const int32_t*)(h_blob + op.off[1]);
+  const int32_t* mult = (const int32_t*)(h_blob + op.off[2]);
+  const int32_t* shift = (const int32_t*)(h_blob + op.off[3]);
+  const int zp = p[BN_CONV_IN_ZP];
+  const long xmax = (127 - zp) > (zp + 128) ? (127 - zp) : (zp + 128);
+  std::vector<int> wm((size_t)9 * C), bf(C), m(mult, mult + C), sh(shift, shift + C);
+  int fast = 1;
+  for (int c = 0; c < C; c++) {
+    long ws = 0, wsum = 0;
+    for (int t = 0; t < 9; t++) {
+      const int8_t v = w[t * C + c];
+      ws += v; wsum += labs((long)v);
+      wm[((size_t)t * (C / 4) + c / 4) * 4 + (c & 3)] = (int)((unsigned)(uint8_t)v << (8 * (c & 3)));
+    }
+    bf[c] = (int)((long)bias[c] - (long)zp * ws);
+    if (!rq_domain_ok(bias[c], wsum, xmax, m[c], sh[c])) fast = 0;
+  }
+  DwParams& D = g.dwp;
+  D.wm = (const int*)up(a, wm.data(), wm.size() * 4);
+  D.bias = (const int*)up(a, bf.data(), bf.size() * 4);
+  D.mult = (const int*)up(a, m.data(), m.size() * 4);
+  D.shift = (const int*)up(a, sh.data(), sh.size() * 4);
+  D.C = C; D.ih = ti.dims[0]; D.iw = ti.dims[1]; D.oh = to.dims[0]; D.ow = to.dims[1];
+  D.sh = p[BN_CONV_SH]; D.sw = p[BN_CONV_SW]; D.pt = p[BN_CONV_PAD_T]; D.pl = p[BN_CONV_PAD_L];
+  D.in_zp = zp; D.out_zp = p[BN_CONV_OUT_ZP]; D.act_min = p[BN_CONV_ACT_MIN]; D.act_max = p[BN_CONV_ACT_MAX];
+  D.fast = fast;
+  g.dw = D.wm && D.bias && D.mult && D.shift;
+  if (g.dw) a->n_dw++;
+}
+
+// 1x1 convolution on the tiled dp4a GEMM: weights as [K/4][N] words (4 consecutive k of channel n), bias folded with the input zero point
+static void build_pwc(GenAccel* a, GenAccelOp& g, const uint8_t* h_blob, const bn_blob_op& op, int K, int N) {
+  const int32_t* p = op.p;
+  if (K % 4 || N % 4 || pw_cuda_core_smem(K, N) > 225 * 1024) return;
+  const int8_t* w = (const int8_t*)(h_blob + op.off[0]);             // [N][K]
+  const int32_t* bias = (const int32_t*)(h_blob + op.off[1]);
+  const int32_t* mult = (const int32_t*)(h_blob + op.off[2]);
+  const int32_t* shift = (const int32_t*)(h_blob + op.off[3]);
+  const int zp = p[BN_CONV_IN_ZP];
+  const long xmax = (127 - zp) > (zp + 128) ? (127 - zp) : (zp + 128);
+  const int KW = K / 4;
+  std::vector<int> wt((size_t)KW * N), bf(N), m(mult, mult + N), sh(shift, shift + N);
+  int fast = 1;
+  for (int n = 0; n < N; n++) {
+    long ws = 0, wsum = 0;
+    for (int k = 0; k < K; k++) {
+      const int8_t v = w[(size_t)n * K + k];
+      ws += v; wsum += labs((long)v);
+      wt[(size_t)(k / 4) * N + n] |= (int)((unsigned)(uint8_t)v << (8 * (k & 3)));
+    }
+    bf[n] = (int)((long)bias[n] - (long)zp * ws);
+    if (!rq_domain_ok(bias[n], wsum, xmax, m[n], sh[n])) fast = 0;
+  }
+  PwParams& P = g.pwp;
+  P.wt = (const int*)up(a, wt.data(), wt.size() * 4);
+  P.bias = (const int*)up(a, bf.data(), bf.size() * 4);
+  P.mult = (const int*)up(a, m.data(), m.size() * 4);
+  P.shift = (const int*)up(a, sh.data(), sh.size() * 4);
+  P.K = K; P.N = N;
+  P.out_zp = p[BN_CONV_OUT_ZP]; P.act_min = p[BN_CONV_ACT_MIN]; P.act_max = p[BN_CONV_ACT_MAX];
+  P.fast = fast; P.has_add = 0; P.lut_res = nullptr; P.lut_conv = nullptr;
+  P.add_mo = 0; P.add_so = 0; P.add_out_zp = 0; P.add_act_min = 0; P.add_act_max = 0;
+  g.pwc = P.wt && P.bias && P.mult && P.shift;
+  if (g.pwc) a->n_pwc++;
+}
+
 GenAccel* gen_accel_build(const uint8_t* h_blob, const bn_blob_header* hdr, const bn_blob_tensor* T, const bn_blob_op* ops) {
   GenAccel* a = new GenAccel();
   a->ops.resize(hdr->n_ops);
   if (getenv("BN_GENERIC_TC") && atoi(getenv("BN_GENERIC_TC")) == 0) return a;
   for (uint32_t i = 0; i < hdr->n_ops; i++) {
     const bn_blob_op& op = ops[i];
+    if (op.kind == BN_OP_DWCONV2D) { build_dw(a, a->ops[i], h_blob, T, op); continue; }
     if (op.kind != BN_OP_CONV2D) continue;
     const int32_t* p = op.p;
+    if (p[BN_CONV_KH] == 3 && p[BN_CONV_CIN] == 1) {
+      a->ops[i].stem = stem_build(h_blob, T, op, a->owned, a->ops[i].stp);
+      if (a->ops[i].stem) a->n_stem++;
+      continue;
+    }
     if (p[BN_CONV_KH] != 1 || p[BN_CONV_KW] != 1 || p[BN_CONV_SH] != 1 || p[BN_CONV_SW] != 1 || p[BN_CONV_PAD_T] != 0 || p[BN_CONV_PAD_L] != 0) continue;
     const int K = p[BN_CONV_CIN], N = p[BN_CONV_COUT];
-    if (!pw_tc_supported(K, N)) continue;
     const bn_blob_tensor& ti = T[op.in[0]];
     const bn_blob_tensor& to = T[op.out];
     if (ti.dims[2] != K || to.dims[2] != N || ti.dims[0] != to.dims[0] || ti.dims[1] != to.dims[1]) continue;
+    if (!pw_tc_supported(K, N)) { build_pwc(a, a->ops[i], h_blob, op, K, N); continue; }
     const int8_t* w = (const int8_t*)(h_blob + op.off[0]);            // [N][K]
     const int32_t* bias = (const int32_t*)(h_blob + op.off[1]);
     const int32_t* mult = (const int32_t*)(h_blob + op.off[2]);
@@ -55,7 +147,7 @@ GenAccel* gen_accel_build(const uint8_t* h_blob, const bn_blob_header* hdr, cons
       if (vmax + (1l << (-sh[n] - 1)) >= (1l << 31)) ok = false;
       bf[n] = (int)((long)bias[n] - (long)zp * ws);
     }
-    if (!ok) continue;
+    if (!ok) { build_pwc(a, a->ops[i], h_blob, op, K, N); continue; }
     GenAccelOp& g = a->ops[i];
     PwTcParams& Tc = g.tc;
     std::vector<uint8_t> img;

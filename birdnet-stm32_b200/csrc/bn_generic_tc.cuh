@@ -3,6 +3,7 @@
 #include <vector>
 
 #include "../../include/bn_blob.h"
+#include "bn_layer.cuh"
 #include "bn_pw_tc.cuh"
 
 namespace bn {
@@ -10,12 +11,18 @@ namespace bn {
 struct GenAccelOp {
   bool pw = false;      // 1x1 convolution routed through the tcgen05 GEMM (bn_pw_tc.cu)
   PwTcParams tc{};
+  bool pwc = false;     // 1x1 convolution the tensor-core kernel has no build for (K or N of 512, ...): tiled dp4a GEMM (k_pw, bn_fast.cu)
+  PwParams pwp{};
+  bool stem = false;    // 3x3 stride-(1,2) 1 -> 16 stem convolution: the fused plan's stem kernel (k_stem_sat, bn_fast.cu)
+  StemParams stp{};
+  bool dw = false;      // depthwise 3x3, stride 1 | 2: register-window kernel of the fused plan's layer path (k_dw3x3, bn_fast.cu)
+  DwParams dwp{};
 };
 
 struct GenAccel {
   std::vector<GenAccelOp> ops;   // indexed like the blob's op table
   std::vector<void*> owned;
-  int n_pw = 0;
+  int n_pw = 0, n_pwc = 0, n_dw = 0, n_stem = 0;
 };
 
 GenAccel* gen_accel_build(const uint8_t* h_blob, const bn_blob_header* hdr, const bn_blob_tensor* tensors, const bn_blob_op* ops);

@@ -1,6 +1,6 @@
 """One engine wave, repeated: the short command the ncu captures in profiles/ are taken on.
 
-usage: python profiles/run_wave.py [chunks] [repeats]
+usage: python profiles/run_wave.py [chunks] [repeats] [BN_OPT_FUSION mask]
 """
 import json
 import os
@@ -26,6 +26,9 @@ pcm = bench.synth_device_pcm(torch, n, T, 24000, 7, dev)
 peak = (pcm.abs().amax(dim=1).float() / 32768.0).contiguous()
 out = torch.empty((n, 100), dtype=torch.float32, device=dev)
 r = GpuRunner(blob, cfg, wave=n)
+if len(sys.argv) > 3:
+    from birdnet_stm32 import _lib as L
+    r.set_option(L.BN_OPT_FUSION, int(sys.argv[3]))
 torch.cuda.synchronize()
 for _ in range(reps):
     r.infer_pcm16_ptr(pcm.data_ptr(), peak.data_ptr(), n, out.data_ptr(), torch.cuda.current_stream().cuda_stream)

@@ -89,9 +89,11 @@ def test_fused_plan_is_active_and_its_tensors_are_bit_exact(runner, graph, oracl
     # fusion 7 = the variant with the depthwise convs of the stride-1 blocks on the tensor core as well (bn_ds_tc.cu);
     # bit 3 (8) = whole-stage kernel for the 8 x 16 stage (bn_stage.cu): its inner block outputs #112 / #115 / #118 stay in
     # shared memory unless bit 4 (16) asks for them (debug taps); bit 5 (32) = quantising frontend, irrelevant for the
-    # spectrogram entry used here.  11 is the default.
+    # spectrogram entry used here; bit 6 (64) = warp-specialised pipeline form of the per-block kernel (bn_ds_ws.cu).
+    # 11 is the default.
     inner = {112, 115, 118}
     for fusion, taps in ((11, [t for t in BLOCK_OUT_TAPS if t not in inner]), (27, BLOCK_OUT_TAPS), (3, BLOCK_OUT_TAPS), (7, BLOCK_OUT_TAPS),
+                         (67, BLOCK_OUT_TAPS), (75, [t for t in BLOCK_OUT_TAPS if t not in inner]),
                          (0, BLOCK_OUT_TAPS + DW_OUT_TAPS)):
         runner.set_option(L.BN_OPT_FUSION, fusion)
         try:
@@ -119,6 +121,8 @@ def test_fused_kernels_equal_layer_kernels_on_ragged_batches(blob, cfg, synth):
     try:
         fused = r.predict_pcm16(pcm, peak)
         r.set_option(L.BN_OPT_FUSION, 7)            # tensor-core depthwise variant, ragged last tile
+        np.testing.assert_array_equal(fused, r.predict_pcm16(pcm, peak))
+        r.set_option(L.BN_OPT_FUSION, 67)           # warp-specialised DS blocks (bn_ds_ws.cu), ragged last tile
         np.testing.assert_array_equal(fused, r.predict_pcm16(pcm, peak))
         r.set_option(L.BN_OPT_FUSION, 43)           # quantising frontend K1q + K2q (bn_frontend_q.cu) instead of K1 + float32 scratch + K2
         np.testing.assert_array_equal(fused, r.predict_pcm16(pcm, peak))
