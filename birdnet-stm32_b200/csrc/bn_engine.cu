@@ -164,7 +164,7 @@ extern "C" int bn_create(const void* blob, size_t nbytes, int device, bn_engine*
   e->buf.assign(e->hdr->n_tensors, nullptr);
   e->last_ptr.assign(e->hdr->n_tensors, nullptr);
   fast_plan_build(e->fast, e->blob.data(), e->hdr, e->tensors, e->ops, e->d_blob);
-  e->accel = gen_accel_build(e->blob.data(), e->hdr, e->tensors, e->ops);
+  e->accel = gen_accel_build(e->blob.data(), e->d_blob, e->hdr, e->tensors, e->ops);
   { int sms = 148; if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) e->fast.num_sms = sms; }
   *out = e;
   return BN_OK;
@@ -281,6 +281,7 @@ static int run_generic(bn_engine* e, std::vector<void*>& ptr, int Bw, cudaStream
     const long n_out = t_elems(to) * Bw;
     void* y = ptr[op.out];
     const void* x = op.n_in > 0 ? ptr[op.in[0]] : nullptr;
+    uint32_t skip = 0;
     if (e->prof.on) {
       char nm[40];
       snprintf(nm, sizeof nm, "G%02u_kind%d", oi, op.kind);
@@ -307,8 +308,15 @@ static int run_generic(bn_engine* e, std::vector<void*>& ptr, int Bw, cudaStream
       } break;
       case BN_OP_CONV2D: {
         if (e->accel && e->accel->ops[oi].pw && R == 0 && e->fast.use_tc) {
+          const GenAccelOp& g = e->accel->ops[oi];
           const long M = (long)to.dims[0] * to.dims[1] * Bw;
-          int rc = launch_pw_tc((const int8_t*)x, nullptr, (int8_t*)y, M, e->accel->ops[oi].tc, e->fast.num_sms, st);
+          int rc;
+          if (g.add_fused && (e->fast.fusion & 1)) {       // convolution + the residual ADD behind it in one launch
+            rc = launch_pw_tc((const int8_t*)x, (const int8_t*)ptr[g.add_res_slot], (int8_t*)ptr[g.add_out_slot], M, g.tc_add, e->fast.num_sms, st);
+            skip = 1;
+          } else {
+            rc = launch_pw_tc((const int8_t*)x, nullptr, (int8_t*)y, M, g.tc, e->fast.num_sms, st);
+          }
           if (rc) return rc;
         } else if (e->accel && e->accel->ops[oi].stem) {
           int rc = launch_stem((const int8_t*)x, (int8_t*)y, Bw, e->accel->ops[oi].stp, R, st);
@@ -348,6 +356,13 @@ static int run_generic(bn_engine* e, std::vector<void*>& ptr, int Bw, cudaStream
         break;
       case BN_OP_MEAN: {
         int variant = e->mean_variant ? e->mean_variant : (op.p[BN_MEAN_KEEP_DIMS] ? 3 : 2);
+        if (e->accel && e->accel->ops[oi].se && (e->fast.fusion & 1)) {   // the whole SE gate (this op and the next three)
+          int rc = launch_se_gate((const int8_t*)x, (int8_t*)y, (int8_t*)ptr[e->ops[oi + 1].out], (int8_t*)ptr[e->ops[oi + 2].out],
+                                  (int8_t*)ptr[e->ops[oi + 3].out], Bw, e->accel->ops[oi].sep, variant, R, st);
+          if (rc) return rc;
+          skip = 3;
+          break;
+        }
         launch_mean((const int8_t*)x, (int8_t*)y, n_out, op.p[BN_MEAN_COUNT], ti->dims[2], op.p, ti->scale, to.scale, variant, R, st);
       } break;
       case BN_OP_LOGISTIC: launch_logistic((const int8_t*)x, (int8_t*)y, n_out, (const int8_t*)(e->d_blob + op.off[0]), st); break;
@@ -366,6 +381,7 @@ static int run_generic(bn_engine* e, std::vector<void*>& ptr, int Bw, cudaStream
     }
     if (e->prof.on) e->prof.end(st);
     e->launches++;
+    oi += skip;                                        // ops covered by a fused launch
   }
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return set_err(BN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(ce));

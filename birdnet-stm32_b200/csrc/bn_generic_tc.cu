@@ -108,13 +108,38 @@ static void build_pwc(GenAccel* a, GenAccelOp& g, const uint8_t* h_blob, const b
   if (g.pwc) a->n_pwc++;
 }
 
-GenAccel* gen_accel_build(const uint8_t* h_blob, const bn_blob_header* hdr, const bn_blob_tensor* T, const bn_blob_op* ops) {
+// MEAN -> FULLY_CONNECTED -> FULLY_CONNECTED -> LOGISTIC chained through their outputs: the squeeze-and-excitation gate
+static void build_se(GenAccel* a, uint32_t i, const uint8_t* d_blob, const bn_blob_header* hdr, const bn_blob_tensor* T, const bn_blob_op* ops) {
+  if (i + 3 >= hdr->n_ops) return;
+  const bn_blob_op& mo = ops[i]; const bn_blob_op& f1 = ops[i + 1]; const bn_blob_op& f2 = ops[i + 2]; const bn_blob_op& lg = ops[i + 3];
+  if (f1.kind != BN_OP_FC || f2.kind != BN_OP_FC || lg.kind != BN_OP_LOGISTIC) return;
+  if (f1.in[0] != mo.out || f2.in[0] != f1.out || lg.in[0] != f2.out) return;
+  const bn_blob_tensor& ti = T[mo.in[0]];
+  SeParams P{};
+  P.npix = mo.p[BN_MEAN_COUNT]; P.C = ti.dims[2]; P.C1 = f1.p[BN_CONV_COUT];
+  if (ti.dims[0] * ti.dims[1] != P.npix || f1.p[BN_CONV_CIN] != P.C || f2.p[BN_CONV_CIN] != P.C1 || f2.p[BN_CONV_COUT] != P.C) return;
+  P.mean_in_zp = mo.p[BN_MEAN_IN_ZP]; P.mean_out_zp = mo.p[BN_MEAN_OUT_ZP];
+  P.mean_mult = mo.p[BN_MEAN_MULT]; P.mean_shift = mo.p[BN_MEAN_SHIFT]; P.mean_mult_n = mo.p[BN_MEAN_MULT_N]; P.mean_shift_n = mo.p[BN_MEAN_SHIFT_N];
+  P.in_scale = ti.scale; P.out_scale = T[mo.out].scale;
+  P.w1 = (const int8_t*)(d_blob + f1.off[0]); P.b1 = (const int32_t*)(d_blob + f1.off[1]); P.m1 = (const int32_t*)(d_blob + f1.off[2]); P.s1 = (const int32_t*)(d_blob + f1.off[3]);
+  P.fc1_in_zp = f1.p[BN_CONV_IN_ZP]; P.fc1_out_zp = f1.p[BN_CONV_OUT_ZP]; P.fc1_act_min = f1.p[BN_CONV_ACT_MIN]; P.fc1_act_max = f1.p[BN_CONV_ACT_MAX];
+  P.w2 = (const int8_t*)(d_blob + f2.off[0]); P.b2 = (const int32_t*)(d_blob + f2.off[1]); P.m2 = (const int32_t*)(d_blob + f2.off[2]); P.s2 = (const int32_t*)(d_blob + f2.off[3]);
+  P.fc2_in_zp = f2.p[BN_CONV_IN_ZP]; P.fc2_out_zp = f2.p[BN_CONV_OUT_ZP]; P.fc2_act_min = f2.p[BN_CONV_ACT_MIN]; P.fc2_act_max = f2.p[BN_CONV_ACT_MAX];
+  P.lut = (const int8_t*)(d_blob + lg.off[0]);
+  if (!se_supported(P) || (f1.off[0] & 3) || (f2.off[0] & 3)) return;   // dp4a reads the weight rows as 32-bit words
+  a->ops[i].sep = P;
+  a->ops[i].se = true;
+  a->n_se++;
+}
+
+GenAccel* gen_accel_build(const uint8_t* h_blob, const uint8_t* d_blob, const bn_blob_header* hdr, const bn_blob_tensor* T, const bn_blob_op* ops) {
   GenAccel* a = new GenAccel();
   a->ops.resize(hdr->n_ops);
   if (getenv("BN_GENERIC_TC") && atoi(getenv("BN_GENERIC_TC")) == 0) return a;
   for (uint32_t i = 0; i < hdr->n_ops; i++) {
     const bn_blob_op& op = ops[i];
     if (op.kind == BN_OP_DWCONV2D) { build_dw(a, a->ops[i], h_blob, T, op); continue; }
+    if (op.kind == BN_OP_MEAN) { build_se(a, i, d_blob, hdr, T, ops); continue; }
     if (op.kind != BN_OP_CONV2D) continue;
     const int32_t* p = op.p;
     if (p[BN_CONV_KH] == 3 && p[BN_CONV_CIN] == 1) {
@@ -165,6 +190,33 @@ GenAccel* gen_accel_build(const uint8_t* h_blob, const bn_blob_header* hdr, cons
     Tc.has_add = 0;
     g.pw = Tc.w_img && Tc.bias && Tc.mult && Tc.shift;
     if (g.pw) a->n_pw++;
+    // residual ADD right behind the convolution: same-shape operands, the convolution's output used by nothing else
+    if (g.pw && i + 1 < hdr->n_ops && ops[i + 1].kind == BN_OP_ADD && ops[i + 1].p[BN_ADD_BCAST] == 0) {
+      const bn_blob_op& ad = ops[i + 1];
+      const int32_t* q = ad.p;
+      const int conv_side = ad.in[0] == op.out ? 0 : (ad.in[1] == op.out ? 1 : -1);
+      int users = 0;
+      for (uint32_t j = 0; j < hdr->n_ops; j++)
+        for (int k = 0; k < (int)ops[j].n_in; k++) users += ops[j].in[k] == op.out;
+      if (conv_side >= 0 && users == 1 && ad.in[0] != ad.in[1] && op.out != (int)hdr->output_tensor) {
+        const int res_slot = ad.in[1 - conv_side];
+        const bn_blob_tensor& tr = T[res_slot];
+        PwTcParams A = Tc;
+        A.has_add = 1;
+        // the kernel's ADD input 1 is the residual, input 2 the convolution
+        A.add_in1_zp = conv_side == 1 ? q[BN_ADD_IN1_ZP] : q[BN_ADD_IN2_ZP];
+        A.add_in2_zp = conv_side == 1 ? q[BN_ADD_IN2_ZP] : q[BN_ADD_IN1_ZP];
+        A.add_m1 = conv_side == 1 ? q[BN_ADD_M1] : q[BN_ADD_M2]; A.add_n1 = -(conv_side == 1 ? q[BN_ADD_S1] : q[BN_ADD_S2]);
+        A.add_m2 = conv_side == 1 ? q[BN_ADD_M2] : q[BN_ADD_M1]; A.add_n2 = -(conv_side == 1 ? q[BN_ADD_S2] : q[BN_ADD_S1]);
+        A.add_out_zp = q[BN_ADD_OUT_ZP]; A.add_mo = q[BN_ADD_MO]; A.add_no = -q[BN_ADD_SO];
+        A.add_act_min = q[BN_ADD_ACT_MIN]; A.add_act_max = q[BN_ADD_ACT_MAX];
+        const bool dom = q[BN_ADD_LEFT_SHIFT] == 20 && A.add_n1 >= 0 && A.add_n1 <= 30 && A.add_n2 >= 0 && A.add_n2 <= 30 && A.add_no >= 0 && A.add_no <= 30;
+        if (dom && !tr.is_const && tr.dims[0] == to.dims[0] && tr.dims[1] == to.dims[1] && tr.dims[2] == N) {
+          g.tc_add = A; g.add_res_slot = res_slot; g.add_out_slot = ad.out; g.add_fused = true;
+          a->n_add_fused++;
+        }
+      }
+    }
   }
   return a;
 }

@@ -52,6 +52,10 @@ def test_graph_every_tensor_bit_exact_generic(runner, graph, oracle_model, oracl
         got = runner.predict(oracle_spec)
         ref = oracle_model.predict(oracle_spec)
         np.testing.assert_array_equal(got, ref)
+        # BN_OPT_FUSION = 0: no multi-op launches in the generic plan either (a 1x1 convolution + the ADD behind it would
+        # otherwise leave the convolution's own output unwritten), so every op materialises its tensor
+        runner.set_option(L.BN_OPT_FUSION, 0)
+        np.testing.assert_array_equal(runner.predict(oracle_spec), ref)
         for tid in ACT_TENSORS:
             t = graph.tensor(tid)
             if t.is_const or t.dtype != np.int8:
@@ -61,6 +65,7 @@ def test_graph_every_tensor_bit_exact_generic(runner, graph, oracle_model, oracl
             _, o = oracle_model.run(oracle_spec, tap_id=tid)
             assert np.array_equal(g, o.reshape(-1)), f"tensor {tid} ({t.name}) differs in {(g != o.reshape(-1)).sum()} of {g.size}"
     finally:
+        runner.set_option(L.BN_OPT_FUSION, 11)
         runner.set_option(L.BN_OPT_FORCE_GENERIC, 0)
 
 

@@ -175,18 +175,32 @@ def test_gpu_generic_plan_bit_exact_on_synthesised_graphs(name):
     want = m.predict(x)
     assert got.dtype == np.float32 and got.shape == want.shape
     assert np.array_equal(got, want), np.abs(got - want).max()
-    # every int8 activation tensor, via the debug taps
-    checked = 0
+    # every int8 activation tensor, via the debug taps.  With the default BN_OPT_FUSION a 1x1 convolution whose only consumer is
+    # the ADD right behind it runs fused with that ADD (its own output is not materialised); with BN_OPT_FUSION = 0 every op
+    # writes its output.  The SE gate (MEAN -> FC -> FC -> LOGISTIC as one launch) still writes all four tensors.
+    from birdnet_stm32 import _lib as L
+
+    users = {}
     for op in g.ops:
-        t = g.tensor(op.outputs[0])
-        if t.dtype != np.int8:
-            continue
-        n = int(np.prod(t.shape[1:]))
-        _, tap = m.run(x, tap_id=t.index)
-        dev = runner.dump_tensor(t.index, B * n)
-        assert np.array_equal(dev.reshape(B, n), tap.reshape(B, n)), (name, op.index, op.kind)
-        checked += 1
-    assert checked >= len(g.ops) - 2
+        for t in op.inputs:
+            users[t] = users.get(t, 0) + 1
+    add_inputs = {t for op in g.ops if op.kind == "ADD" for t in op.inputs[:2]}
+    folded = {op.outputs[0] for op in g.ops if op.kind == "CONV_2D" and users.get(op.outputs[0], 0) == 1 and op.outputs[0] in add_inputs}
+    for fusion in (None, 0):
+        if fusion is not None:
+            runner.set_option(L.BN_OPT_FUSION, fusion)
+            assert np.array_equal(runner.predict(x), want)
+        checked = 0
+        for op in g.ops:
+            t = g.tensor(op.outputs[0])
+            if t.dtype != np.int8 or (fusion is None and t.index in folded):
+                continue
+            n = int(np.prod(t.shape[1:]))
+            _, tap = m.run(x, tap_id=t.index)
+            dev = runner.dump_tensor(t.index, B * n)
+            assert np.array_equal(dev.reshape(B, n), tap.reshape(B, n)), (name, op.index, op.kind, fusion)
+            checked += 1
+        assert checked >= len(g.ops) - 2 - (len(folded) if fusion is None else 0)
     runner.close()
 
 
