@@ -329,7 +329,12 @@ static int run_generic(bn_engine* e, std::vector<void*>& ptr, int Bw, cudaStream
         }
       } break;
       case BN_OP_DWCONV2D: {
-        if (e->accel && e->accel->ops[oi].dw) {
+        if (e->accel && e->accel->ops[oi].dsb && R == 0 && e->fast.use_tc && (e->fast.fusion & 1)) {   // the whole DS block in one launch
+          const GenAccelOp& g = e->accel->ops[oi];
+          int rc = launch_ds((const int8_t*)x, (int8_t*)ptr[g.ds_out_slot], Bw, g.ds, g.dsl, e->fast.num_sms, st);
+          if (rc) return rc;
+          skip = (uint32_t)g.ds_skip;
+        } else if (e->accel && e->accel->ops[oi].dw) {
           int rc = launch_dw3x3((const int8_t*)x, (int8_t*)y, Bw, e->accel->ops[oi].dwp, R, st);
           if (rc) return rc;
         } else {

@@ -643,6 +643,88 @@ static bool prep_ds(FastPlan& fp, FastImpl* im, Block& bl) {
   return D.dw_rq && D.dw_rz && D.pw_rq && D.pw_rz;
 }
 
+// Constants of one DS block (depthwise, pointwise (+ADD), tensor-core image, fused-kernel parameters) from its blob ops.
+static bool prep_block(FastPlan& fp, FastImpl* im, Block& bl) {
+  const bn_blob_op* ops = fp.ops;
+  const bn_blob_tensor* T = fp.tensors;
+  {
+    const bn_blob_op& dw = ops[bl.dw_op];
+    const bn_blob_op& pw = ops[bl.pw_op];
+    {  // depthwise: masked words wm[tap][cg][j], folded bias
+      const int C = dw.p[BN_CONV_CIN];
+      const int8_t* w = (const int8_t*)(fp.h_blob + dw.off[0]);   // [3][3][C]
+      const int32_t* bias = (const int32_t*)(fp.h_blob + dw.off[1]);
+      std::vector<int> wm((size_t)9 * C), bf(C);
+      for (int c = 0; c < C; c++) {
+        long ws = 0;
+        for (int t = 0; t < 9; t++) {
+          int8_t v = w[t * C + c];
+          ws += v;
+          wm[((size_t)t * (C / 4) + c / 4) * 4 + (c & 3)] = (int)((unsigned)(uint8_t)v << (8 * (c & 3)));
+        }
+        bf[c] = (int)((long)bias[c] - (long)dw.p[BN_CONV_IN_ZP] * ws);
+      }
+      DwParams& D = bl.dw;
+      D.wm = (const int*)upload(im, wm.data(), wm.size() * 4);
+      D.bias = (const int*)upload(im, bf.data(), bf.size() * 4);
+      prep_requant(fp, im, dw, C, &D.mult, &D.shift, &D.fast);
+      D.C = C; D.ih = T[dw.in[0]].dims[0]; D.iw = T[dw.in[0]].dims[1]; D.oh = T[dw.out].dims[0]; D.ow = T[dw.out].dims[1];
+      D.sh = dw.p[BN_CONV_SH]; D.sw = dw.p[BN_CONV_SW]; D.pt = dw.p[BN_CONV_PAD_T]; D.pl = dw.p[BN_CONV_PAD_L];
+      D.in_zp = dw.p[BN_CONV_IN_ZP]; D.out_zp = dw.p[BN_CONV_OUT_ZP]; D.act_min = dw.p[BN_CONV_ACT_MIN]; D.act_max = dw.p[BN_CONV_ACT_MAX];
+    }
+    {  // pointwise
+      const int K = pw.p[BN_CONV_CIN], N = pw.p[BN_CONV_COUT];
+      std::vector<int> wt, bf;
+      prep_pw_weights(fp, pw, K, N, wt, bf);
+      PwParams& P = bl.pw;
+      P.wt = (const int*)upload(im, wt.data(), wt.size() * 4);
+      P.bias = (const int*)upload(im, bf.data(), bf.size() * 4);
+      prep_requant(fp, im, pw, N, &P.mult, &P.shift, &P.fast);
+      P.K = K; P.N = N;
+      P.out_zp = pw.p[BN_CONV_OUT_ZP]; P.act_min = pw.p[BN_CONV_ACT_MIN]; P.act_max = pw.p[BN_CONV_ACT_MAX];
+      P.has_add = bl.add_op >= 0;
+      int* d_lut = nullptr;
+      if (P.has_add) {
+        if (cudaMalloc(&d_lut, 512 * sizeof(int)) != cudaSuccess) FAIL("cudaMalloc");
+        const int32_t* p = ops[bl.add_op].p;
+        P.add_mo = p[BN_ADD_MO]; P.add_so = p[BN_ADD_SO]; P.add_out_zp = p[BN_ADD_OUT_ZP];
+        P.add_act_min = p[BN_ADD_ACT_MIN]; P.add_act_max = p[BN_ADD_ACT_MAX];
+      }
+      im->d_add_luts.push_back(d_lut);
+      P.lut_res = d_lut; P.lut_conv = d_lut ? d_lut + 256 : nullptr;
+      // tensor-core variant (needs the proven fast-requant domain and right-shift-only ADD rescales)
+      bl.tc_ok = false;
+      if (pw_tc_supported(K, N) && P.fast) {
+        PwTcParams& Tc = bl.tc;
+        std::vector<uint8_t> img;
+        pw_tc_weight_image((const int8_t*)(fp.h_blob + pw.off[0]), K, N, img, &Tc.KP, &Tc.RW);
+        Tc.w_img = (const uint8_t*)upload(im, img.data(), img.size());
+        Tc.bias = P.bias; Tc.mult = P.mult; Tc.shift = P.shift;
+        Tc.K = K; Tc.N = N;
+        int l = 0; while ((16 << l) < K) l++;
+        Tc.cpr_log = l;
+        int tc_cols = 32; while (tc_cols < 2 * N) tc_cols <<= 1;
+        Tc.tmem_cols = tc_cols;
+        Tc.out_zp = P.out_zp; Tc.act_min = P.act_min; Tc.act_max = P.act_max;
+        Tc.has_add = P.has_add;
+        bool ok = true;
+        if (P.has_add) {
+          const int32_t* p = ops[bl.add_op].p;
+          Tc.add_in1_zp = p[BN_ADD_IN1_ZP]; Tc.add_in2_zp = p[BN_ADD_IN2_ZP]; Tc.add_out_zp = p[BN_ADD_OUT_ZP];
+          Tc.add_m1 = p[BN_ADD_M1]; Tc.add_n1 = -p[BN_ADD_S1]; Tc.add_m2 = p[BN_ADD_M2]; Tc.add_n2 = -p[BN_ADD_S2];
+          Tc.add_mo = p[BN_ADD_MO]; Tc.add_no = -p[BN_ADD_SO];
+          Tc.add_act_min = p[BN_ADD_ACT_MIN]; Tc.add_act_max = p[BN_ADD_ACT_MAX];
+          // closed forms need right shifts in [0, 30] and left_shift 20 (|x| <= 255 * 2^20 keeps every step in int32)
+          ok = p[BN_ADD_LEFT_SHIFT] == 20 && Tc.add_n1 >= 0 && Tc.add_n1 <= 30 && Tc.add_n2 >= 0 && Tc.add_n2 <= 30 && Tc.add_no >= 0 && Tc.add_no <= 30;
+        }
+        bl.tc_ok = ok && Tc.w_img != nullptr;
+      }
+    }
+    bl.ds_ok = prep_ds(fp, im, bl);
+  }
+  return true;
+}
+
 static bool build_impl(FastPlan& fp) {
   const bn_blob_header* h = fp.hdr;
   const bn_blob_op* ops = fp.ops;
@@ -817,81 +899,7 @@ static bool build_impl(FastPlan& fp) {
       S.sat = S.pk != nullptr;
     }
   }
-  for (Block& bl : im->blocks) {
-    const bn_blob_op& dw = ops[bl.dw_op];
-    const bn_blob_op& pw = ops[bl.pw_op];
-    {  // depthwise: masked words wm[tap][cg][j], folded bias
-      const int C = dw.p[BN_CONV_CIN];
-      const int8_t* w = (const int8_t*)(fp.h_blob + dw.off[0]);   // [3][3][C]
-      const int32_t* bias = (const int32_t*)(fp.h_blob + dw.off[1]);
-      std::vector<int> wm((size_t)9 * C), bf(C);
-      for (int c = 0; c < C; c++) {
-        long ws = 0;
-        for (int t = 0; t < 9; t++) {
-          int8_t v = w[t * C + c];
-          ws += v;
-          wm[((size_t)t * (C / 4) + c / 4) * 4 + (c & 3)] = (int)((unsigned)(uint8_t)v << (8 * (c & 3)));
-        }
-        bf[c] = (int)((long)bias[c] - (long)dw.p[BN_CONV_IN_ZP] * ws);
-      }
-      DwParams& D = bl.dw;
-      D.wm = (const int*)upload(im, wm.data(), wm.size() * 4);
-      D.bias = (const int*)upload(im, bf.data(), bf.size() * 4);
-      prep_requant(fp, im, dw, C, &D.mult, &D.shift, &D.fast);
-      D.C = C; D.ih = T[dw.in[0]].dims[0]; D.iw = T[dw.in[0]].dims[1]; D.oh = T[dw.out].dims[0]; D.ow = T[dw.out].dims[1];
-      D.sh = dw.p[BN_CONV_SH]; D.sw = dw.p[BN_CONV_SW]; D.pt = dw.p[BN_CONV_PAD_T]; D.pl = dw.p[BN_CONV_PAD_L];
-      D.in_zp = dw.p[BN_CONV_IN_ZP]; D.out_zp = dw.p[BN_CONV_OUT_ZP]; D.act_min = dw.p[BN_CONV_ACT_MIN]; D.act_max = dw.p[BN_CONV_ACT_MAX];
-    }
-    {  // pointwise
-      const int K = pw.p[BN_CONV_CIN], N = pw.p[BN_CONV_COUT];
-      std::vector<int> wt, bf;
-      prep_pw_weights(fp, pw, K, N, wt, bf);
-      PwParams& P = bl.pw;
-      P.wt = (const int*)upload(im, wt.data(), wt.size() * 4);
-      P.bias = (const int*)upload(im, bf.data(), bf.size() * 4);
-      prep_requant(fp, im, pw, N, &P.mult, &P.shift, &P.fast);
-      P.K = K; P.N = N;
-      P.out_zp = pw.p[BN_CONV_OUT_ZP]; P.act_min = pw.p[BN_CONV_ACT_MIN]; P.act_max = pw.p[BN_CONV_ACT_MAX];
-      P.has_add = bl.add_op >= 0;
-      int* d_lut = nullptr;
-      if (P.has_add) {
-        if (cudaMalloc(&d_lut, 512 * sizeof(int)) != cudaSuccess) FAIL("cudaMalloc");
-        const int32_t* p = ops[bl.add_op].p;
-        P.add_mo = p[BN_ADD_MO]; P.add_so = p[BN_ADD_SO]; P.add_out_zp = p[BN_ADD_OUT_ZP];
-        P.add_act_min = p[BN_ADD_ACT_MIN]; P.add_act_max = p[BN_ADD_ACT_MAX];
-      }
-      im->d_add_luts.push_back(d_lut);
-      P.lut_res = d_lut; P.lut_conv = d_lut ? d_lut + 256 : nullptr;
-      // tensor-core variant (needs the proven fast-requant domain and right-shift-only ADD rescales)
-      bl.tc_ok = false;
-      if (pw_tc_supported(K, N) && P.fast) {
-        PwTcParams& Tc = bl.tc;
-        std::vector<uint8_t> img;
-        pw_tc_weight_image((const int8_t*)(fp.h_blob + pw.off[0]), K, N, img, &Tc.KP, &Tc.RW);
-        Tc.w_img = (const uint8_t*)upload(im, img.data(), img.size());
-        Tc.bias = P.bias; Tc.mult = P.mult; Tc.shift = P.shift;
-        Tc.K = K; Tc.N = N;
-        int l = 0; while ((16 << l) < K) l++;
-        Tc.cpr_log = l;
-        int tc_cols = 32; while (tc_cols < 2 * N) tc_cols <<= 1;
-        Tc.tmem_cols = tc_cols;
-        Tc.out_zp = P.out_zp; Tc.act_min = P.act_min; Tc.act_max = P.act_max;
-        Tc.has_add = P.has_add;
-        bool ok = true;
-        if (P.has_add) {
-          const int32_t* p = ops[bl.add_op].p;
-          Tc.add_in1_zp = p[BN_ADD_IN1_ZP]; Tc.add_in2_zp = p[BN_ADD_IN2_ZP]; Tc.add_out_zp = p[BN_ADD_OUT_ZP];
-          Tc.add_m1 = p[BN_ADD_M1]; Tc.add_n1 = -p[BN_ADD_S1]; Tc.add_m2 = p[BN_ADD_M2]; Tc.add_n2 = -p[BN_ADD_S2];
-          Tc.add_mo = p[BN_ADD_MO]; Tc.add_no = -p[BN_ADD_SO];
-          Tc.add_act_min = p[BN_ADD_ACT_MIN]; Tc.add_act_max = p[BN_ADD_ACT_MAX];
-          // closed forms need right shifts in [0, 30] and left_shift 20 (|x| <= 255 * 2^20 keeps every step in int32)
-          ok = p[BN_ADD_LEFT_SHIFT] == 20 && Tc.add_n1 >= 0 && Tc.add_n1 <= 30 && Tc.add_n2 >= 0 && Tc.add_n2 <= 30 && Tc.add_no >= 0 && Tc.add_no <= 30;
-        }
-        bl.tc_ok = ok && Tc.w_img != nullptr;
-      }
-    }
-    bl.ds_ok = prep_ds(fp, im, bl);
-  }
+  for (Block& bl : im->blocks) if (!prep_block(fp, im, bl)) return false;
   // whole-stage kernels: a stride-2 block without ADD followed by stride-1 residual blocks of the same width whose maps are
   // one 128-pixel MMA tile (the 8 x 16 stage of the shipped graph), all in the folded-constant domain of the fused DS kernel
   for (size_t i = 0; i < im->blocks.size();) {
@@ -1572,6 +1580,26 @@ static size_t head_smem(const HeadParams& H) { return (size_t)H.KW * GEMM_LDA * 
 static size_t pw_smem(const PwParams& P) {
   const int KW = P.K / 4, NP = P.N < 64 ? 64 : P.N;
   return ((size_t)KW * GEMM_LDA + (size_t)KW * NP + 3 * NP + 512) * 4;
+}
+
+// Fused DS-block kernel (bn_ds.cu) for callers outside the fused plan: parameters from the block's blob ops (add_op = -1: no
+// residual).  False when the block is outside the kernel's proven domain.  Device constants are appended to `owned`.
+bool ds_block_build(const uint8_t* h_blob, const bn_blob_tensor* T, const bn_blob_op* ops, int dw_op, int pw_op, int add_op,
+                    std::vector<void*>& owned, DsParams& D, DsLaunch& L) {
+  FastPlan tmp;
+  tmp.h_blob = h_blob; tmp.tensors = T; tmp.ops = ops;
+  FastImpl im;
+  Block bl{};
+  bl.dw_op = dw_op; bl.pw_op = pw_op; bl.add_op = add_op;
+  bl.in_slot = ops[dw_op].in[0]; bl.dw_slot = ops[dw_op].out; bl.out_slot = add_op >= 0 ? ops[add_op].out : ops[pw_op].out;
+  const bn_blob_op& pw = ops[pw_op];
+  bool ok = pw.p[BN_CONV_CIN] % 16 == 0 && pw.p[BN_CONV_CIN] <= 256 && pw.p[BN_CONV_COUT] <= 256 &&
+            (pw.p[BN_CONV_COUT] % 64 == 0 || pw.p[BN_CONV_COUT] == 32);
+  ok = ok && prep_block(tmp, &im, bl) && bl.ds_ok;
+  for (void* p : im.d_consts) owned.push_back(p);
+  for (int* p : im.d_add_luts) if (p) owned.push_back(p);
+  if (ok) { D = bl.ds; L = bl.dsl; }
+  return ok;
 }
 
 // Stem (3x3 stride-(1,2) convolution, 1 -> 16 channels) for callers outside the fused plan: parameter block from a blob op.

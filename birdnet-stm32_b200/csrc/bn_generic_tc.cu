@@ -138,7 +138,31 @@ GenAccel* gen_accel_build(const uint8_t* h_blob, const uint8_t* d_blob, const bn
   if (getenv("BN_GENERIC_TC") && atoi(getenv("BN_GENERIC_TC")) == 0) return a;
   for (uint32_t i = 0; i < hdr->n_ops; i++) {
     const bn_blob_op& op = ops[i];
-    if (op.kind == BN_OP_DWCONV2D) { build_dw(a, a->ops[i], h_blob, T, op); continue; }
+    if (op.kind == BN_OP_DWCONV2D) {
+      build_dw(a, a->ops[i], h_blob, T, op);
+      // whole DS block: the 1x1 convolution behind it (sole user of the depthwise output) and, if present, the residual ADD of
+      // the block input (sole user of the convolution output)
+      auto users = [&](int slot) { int u = 0; for (uint32_t j = 0; j < hdr->n_ops; j++) for (int k = 0; k < (int)ops[j].n_in; k++) u += ops[j].in[k] == slot; return u; };
+      if (i + 1 < hdr->n_ops && op.p[BN_CONV_KH] == 3 && op.p[BN_CONV_KW] == 3) {
+        const bn_blob_op& pw = ops[i + 1];
+        const bool pw_ok = pw.kind == BN_OP_CONV2D && pw.p[BN_CONV_KH] == 1 && pw.p[BN_CONV_KW] == 1 && pw.p[BN_CONV_SH] == 1 && pw.p[BN_CONV_SW] == 1 &&
+                           pw.in[0] == op.out && users(op.out) == 1 && op.out != (int)hdr->output_tensor;
+        if (pw_ok) {
+          int add_op = -1;
+          if (i + 2 < hdr->n_ops && ops[i + 2].kind == BN_OP_ADD && ops[i + 2].p[BN_ADD_BCAST] == 0 && ops[i + 2].in[0] == op.in[0] &&
+              ops[i + 2].in[1] == pw.out && users(pw.out) == 1 && pw.p[BN_CONV_CIN] == pw.p[BN_CONV_COUT] && op.p[BN_CONV_SH] == 1)
+            add_op = (int)i + 2;
+          GenAccelOp& g = a->ops[i];
+          if (ds_block_build(h_blob, T, ops, (int)i, (int)i + 1, add_op, a->owned, g.ds, g.dsl)) {
+            g.dsb = true;
+            g.ds_skip = add_op >= 0 ? 2 : 1;
+            g.ds_out_slot = add_op >= 0 ? ops[add_op].out : pw.out;
+            a->n_dsb++;
+          }
+        }
+      }
+      continue;
+    }
     if (op.kind == BN_OP_MEAN) { build_se(a, i, d_blob, hdr, T, ops); continue; }
     if (op.kind != BN_OP_CONV2D) continue;
     const int32_t* p = op.p;

@@ -19,6 +19,10 @@ struct GenAccelOp {
   bool add_fused = false;   // pw: the ADD that follows (op + 1) runs in the GEMM epilogue; tc_add = tc with the ADD constants
   PwTcParams tc_add{};
   int add_res_slot = -1, add_out_slot = -1;
+  bool dsb = false;         // dw: DEPTHWISE 3x3 -> CONV 1x1 [-> ADD with the block input] (ops + 0 .. + ds_skip) as ONE fused DS-block
+  DsParams ds{};            //     kernel launch (k_ds, bn_ds.cu): the depthwise result never leaves the SM
+  DsLaunch dsl{};
+  int ds_out_slot = -1, ds_skip = 0;
   bool se = false;          // MEAN -> FC -> FC -> LOGISTIC (ops + 0 .. + 3) as one launch (bn_se.cu)
   SeParams sep{};
   bool stem = false;    // 3x3 stride-(1,2) 1 -> 16 stem convolution: the fused plan's stem kernel (k_stem_sat, bn_fast.cu)
@@ -30,7 +34,7 @@ struct GenAccelOp {
 struct GenAccel {
   std::vector<GenAccelOp> ops;   // indexed like the blob's op table
   std::vector<void*> owned;
-  int n_pw = 0, n_pwc = 0, n_dw = 0, n_stem = 0, n_add_fused = 0, n_se = 0;
+  int n_pw = 0, n_pwc = 0, n_dw = 0, n_stem = 0, n_add_fused = 0, n_se = 0, n_dsb = 0;
 };
 
 GenAccel* gen_accel_build(const uint8_t* h_blob, const uint8_t* d_blob, const bn_blob_header* hdr, const bn_blob_tensor* tensors,

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../include/bn_blob.h"
+#include "bn_ds.cuh"
 
 namespace bn {
 
@@ -41,6 +42,10 @@ struct StemParams {
   int sat;                        // pk is valid (zp_out = -128, clamp [-128, 127], int32-safe)
 };
 
+// Fused DS-block kernel parameters (k_ds, bn_ds.cu) from the blob ops of a DEPTHWISE_CONV_2D 3x3 -> CONV_2D 1x1 [-> ADD with the
+// block input] group; false when the group is outside the kernel's proven domain.  Launch with launch_ds().
+bool ds_block_build(const uint8_t* h_blob, const bn_blob_tensor* T, const bn_blob_op* ops, int dw_op, int pw_op, int add_op,
+                    std::vector<void*>& owned, DsParams& D, DsLaunch& L);
 // Stem parameter block from a CONV_2D blob op (false when the op is not a 3x3 stride-(1,2) 1 -> 16 convolution); device
 // allocations are appended to `owned`.  in int8 [Bw][ih][iw] -> out int8 [Bw][oh][ow][16].
 bool stem_build(const uint8_t* h_blob, const bn_blob_tensor* T, const bn_blob_op& st, std::vector<void*>& owned, StemParams& S);

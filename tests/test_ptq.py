@@ -186,6 +186,9 @@ def test_gpu_generic_plan_bit_exact_on_synthesised_graphs(name):
             users[t] = users.get(t, 0) + 1
     add_inputs = {t for op in g.ops if op.kind == "ADD" for t in op.inputs[:2]}
     folded = {op.outputs[0] for op in g.ops if op.kind == "CONV_2D" and users.get(op.outputs[0], 0) == 1 and op.outputs[0] in add_inputs}
+    # ... and a depthwise 3x3 whose only consumer is a 1x1 convolution runs inside the fused DS-block kernel with it
+    conv_inputs = {op.inputs[0] for op in g.ops if op.kind == "CONV_2D"}
+    folded |= {op.outputs[0] for op in g.ops if op.kind == "DEPTHWISE_CONV_2D" and users.get(op.outputs[0], 0) == 1 and op.outputs[0] in conv_inputs}
     for fusion in (None, 0):
         if fusion is not None:
             runner.set_option(L.BN_OPT_FUSION, fusion)
@@ -201,6 +204,7 @@ def test_gpu_generic_plan_bit_exact_on_synthesised_graphs(name):
             assert np.array_equal(dev.reshape(B, n), tap.reshape(B, n)), (name, op.index, op.kind, fusion)
             checked += 1
         assert checked >= len(g.ops) - 2 - (len(folded) if fusion is None else 0)
+    runner.set_option(L.BN_OPT_FUSION, 11)
     runner.close()
 
 
