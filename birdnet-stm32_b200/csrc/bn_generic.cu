@@ -246,6 +246,36 @@ __global__ void k_mul4(const unsigned* __restrict__ a, const int8_t* __restrict_
   }
 }
 
+// Sixteen elements per thread (one 16-byte vector of each operand): MUL with n, C and per_chunk multiples of 16.
+__global__ void k_mul16(const uint4* __restrict__ a, const int8_t* __restrict__ b, uint4* __restrict__ y, unsigned n16,
+                        unsigned per_chunk, int in1_zp, int in2_zp, int out_zp, int mult, int shift, int act_min,
+                        int act_max, int bcast, int C, int R) {
+  for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < n16; v += gridDim.x * blockDim.x) {
+    const unsigned i = 16u * v;
+    const uint4 av = a[v];
+    uint4 bv;
+    if (bcast == 3) { const unsigned w = 0x01010101u * (unsigned)(uint8_t)b[i / (unsigned)C]; bv = make_uint4(w, w, w, w); }
+    else {
+      const unsigned bi = bcast == 0 ? i : (bcast == 1 ? (i % (unsigned)C) : ((i / per_chunk) * (unsigned)C + (i % (unsigned)C)));
+      bv = *reinterpret_cast<const uint4*>(b + bi);
+    }
+    const unsigned aw[4] = {av.x, av.y, av.z, av.w}, bw[4] = {bv.x, bv.y, bv.z, bv.w};
+    unsigned ow[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      unsigned o4 = 0;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int p = ((int)(int8_t)(aw[q] >> (8 * j)) - in1_zp) * ((int)(int8_t)(bw[q] >> (8 * j)) - in2_zp);
+        const int o = mbqm(p, mult, shift, R) + out_zp;
+        o4 |= (unsigned)(uint8_t)clampi(o, act_min, act_max) << (8 * j);
+      }
+      ow[q] = o4;
+    }
+    y[v] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  }
+}
+
 static inline bool words_ok(const void* a, const void* b, const void* y, long n, long per_chunk, int C) {
   return n > 0 && n < (1l << 31) && n % 4 == 0 && per_chunk % 4 == 0 && C % 4 == 0 &&
          (((uintptr_t)a | (uintptr_t)b | (uintptr_t)y) & 3) == 0;
@@ -403,6 +433,12 @@ void launch_add(const int8_t* a, const int8_t* b, int8_t* y, long n, long per_ch
   LAUNCH(k_add, n, st, a, b, y, n, per_chunk, P);
 }
 void launch_mul(const int8_t* a, const int8_t* b, int8_t* y, long n, long per_chunk, const int* p, int C, int R, cudaStream_t st) {
+  if (words_ok(a, b, y, n, per_chunk, C) && n % 16 == 0 && per_chunk % 16 == 0 && C % 16 == 0 &&
+      (((uintptr_t)a | (uintptr_t)b | (uintptr_t)y) & 15) == 0) {
+    LAUNCH(k_mul16, n / 16, st, reinterpret_cast<const uint4*>(a), b, reinterpret_cast<uint4*>(y), (unsigned)(n / 16), (unsigned)per_chunk,
+           p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], C, R);
+    return;
+  }
   if (words_ok(a, b, y, n, per_chunk, C)) {
     LAUNCH(k_mul4, n / 4, st, reinterpret_cast<const unsigned*>(a), b, reinterpret_cast<unsigned*>(y), (unsigned)(n / 4), (unsigned)per_chunk,
            p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], C, R);
