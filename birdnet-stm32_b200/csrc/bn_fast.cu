@@ -21,6 +21,7 @@
 #include "bn_ds.cuh"
 #include "bn_layer.cuh"
 #include "bn_stage.cuh"
+#include "bn_stem_tc.cuh"
 #include "bn_frontend_q.cuh"
 #include "bn_head_tc.cuh"
 #include "bn_kernels.cuh"
@@ -137,6 +138,8 @@ struct FastImpl {
   HeadTcParams head_tc{};         // tensor-core head (bn_head_tc.cu)
   bool head_tc_ok = false;
   StemParams stem{};
+  StemTcParams stem_tc{};         // tensor-core stem (bn_stem_tc.cu), BN_OPT_FUSION bit 7
+  bool stem_tc_ok = false;
   TailParams tail{};
   int ldk = 264;
   int bins = 257, W = 256, mel = 64;
@@ -897,6 +900,19 @@ static bool build_impl(FastPlan& fp) {
       }
       S.pk = (const int4*)upload(im, pk.data(), pk.size() * 4);
       S.sat = S.pk != nullptr;
+      if (S.sat && stem_tc_supported(S.ih, S.iw, S.oh, S.ow)) {
+        // im2col GEMM operand: weights [16][9] padded to [16][16] -> SWIZZLE_32B image, same folded requantisation constants
+        std::vector<int8_t> w16(16 * 16, 0);
+        for (int co = 0; co < 16; co++) for (int k = 0; k < 9; k++) w16[co * 16 + k] = w[co * 9 + k];
+        std::vector<uint8_t> img;
+        int kp = 0, rwid = 0;
+        pw_tc_weight_image(w16.data(), 16, 16, img, &kp, &rwid);
+        StemTcParams& Q = im->stem_tc;
+        Q.w_img = (const uint8_t*)upload(im, img.data(), img.size());
+        for (int co = 0; co < 16; co++) Q.rq[co] = make_int4(rq[4 * co + 0], rq[4 * co + 1], rq[4 * co + 2], rq[4 * co + 3]);
+        Q.ih = S.ih; Q.oh = S.oh; Q.in_zp = S.in_zp;
+        im->stem_tc_ok = Q.w_img != nullptr && kp == 32 && rwid == 32;
+      }
     }
   }
   for (Block& bl : im->blocks) if (!prep_block(fp, im, bl)) return false;
@@ -1748,8 +1764,10 @@ static int run_body(FastPlan& fp, int Bw, float* d_scores, int rounding, int mea
     const StemParams& S = im->stem;
     dim3 grid((S.oh + STEM_ROWS - 1) / STEM_ROWS, Bw);
     const size_t smem = (size_t)(STEM_ROWS + 2) * (S.iw + 8) + 96 * 4;
-    if (prof) prof->begin("K3_stem", st);
-    if (S.sat && R == 0) k_stem_sat<<<grid, 256, smem + 32 * 16 + 16, st>>>(head_out, stem_out, S);
+    const bool stc = im->stem_tc_ok && fp.use_tc && R == 0 && (fp.fusion & 128);
+    if (prof) prof->begin(stc ? "K3tc_stem" : "K3_stem", st);
+    if (stc) { int rc = launch_stem_tc(head_out, stem_out, Bw, im->stem_tc, fp.num_sms, st); if (rc) return rc; }
+    else if (S.sat && R == 0) k_stem_sat<<<grid, 256, smem + 32 * 16 + 16, st>>>(head_out, stem_out, S);
     else if (S.fast && R == 0) k_stem<true><<<grid, 256, smem, st>>>(head_out, stem_out, S, R);
     else k_stem<false><<<grid, 256, smem, st>>>(head_out, stem_out, S, R);
     if (prof) prof->end(st);

@@ -51,10 +51,11 @@ struct FastPlan {
   int wave = 0;
   int use_tc = 1;              // pointwise convs on tcgen05 (BN_OPT_TENSOR_CORE)
   int num_sms = 148;
-  int fusion = 11;             // BN_OPT_FUSION -- bit 0: fused DS-block kernels, bit 1: fused frontend, bit 2: depthwise on the tensor core
+  int fusion = 139;            // BN_OPT_FUSION -- bit 0: fused DS-block kernels, bit 1: fused frontend, bit 2: depthwise on the tensor core
                                // too, bit 3: whole-stage kernels (bn_stage.cu), bit 4: stage kernels also write their inner block outputs (taps),
                                // bit 5: quantising frontend K1q / K2q (bn_frontend_q.cu) instead of K1 + float32 scratch + K2 (off by default:
-                               // measured 0.9 % slower end to end, 27 % less DRAM traffic -- DESIGN.md section 5)
+                               // measured 0.9 % slower end to end, 27 % less DRAM traffic -- DESIGN.md section 5), bit 6: warp-specialised DS-block
+                               // kernel (bn_ds_ws.cu; measured equal, off), bit 7: stem as an im2col GEMM on tcgen05 (bn_stem_tc.cu)
   FastImpl* impl = nullptr;
   std::string why;             // why the pattern did not match (diagnostics)
 };

@@ -63,9 +63,16 @@ enum {
   BN_OPT_TENSOR_CORE = 6,   /* 1 (default) = pointwise convs on tcgen05.mma kind::i8, 0 = dp4a CUDA-core GEMM */
   BN_OPT_HOST_WAVE = 8,     /* wave size for calls whose input is in HOST memory (default 592): uploads are double-buffered under
                                compute, so a smaller wave shortens the un-overlapped first upload / last compute of a call */
-  BN_OPT_FUSION = 7         /* bit 0: depthwise + pointwise (+ADD) fused per DS block, bit 1: tensor-core head (quantise +
-                               mel mixer + PWL LUT), bit 2: depthwise conv of stride-1 blocks on the tensor core too
-                               (shifted no-swizzle descriptors; bit-exact, measured slower, off); default 3 */
+  BN_OPT_FUSION = 7         /* bit mask, default 139 = 1 | 2 | 8 | 128.
+                               bit 0 (1): fused kernels: depthwise + pointwise (+ADD) per DS block (bn_ds.cu); in the generic plan also
+                                          the SE gate, 1x1 convolution + ADD and whole DS blocks as single launches
+                               bit 1 (2): fused frontend: frame-major K1 + tensor-core head (quantise + mel mixer + PWL LUT)
+                               bit 2 (4): depthwise conv of stride-1 blocks on the tensor core too (bit-exact, measured slower, off)
+                               bit 3 (8): whole-stage kernel for the 8 x 16 stage (bn_stage.cu)
+                               bit 4 (16): the stage kernel also writes its inner block outputs (taps for bn_dump_tensor)
+                               bit 5 (32): quantising frontend K1q + K2q (bn_frontend_q.cu; 27 % less DRAM traffic, 1 % slower, off)
+                               bit 6 (64): warp-specialised DS-block kernel (bn_ds_ws.cu; measured equal to bit 0's kernel, off)
+                               bit 7 (128): stem convolution as an im2col GEMM on tcgen05 (bn_stem_tc.cu) */
 };
 
 typedef struct bn_info {

@@ -212,7 +212,7 @@ def test_quantising_frontend_equals_the_default_frontend_at_bench_config(runner2
     d_pcm, d_peak = torch.as_tensor(pcm, device="cuda"), torch.as_tensor(peak, device="cuda")
     outs = {}
     try:
-        for fusion in (11, 43):
+        for fusion in (139, 171, 11):
             runner24.set_option(L.BN_OPT_FUSION, fusion)
             d_out = torch.empty((len(pcm), 100), dtype=torch.float32, device="cuda")
             runner24.infer_pcm16_ptr(d_pcm.data_ptr(), d_peak.data_ptr(), len(pcm), d_out.data_ptr())
@@ -222,5 +222,6 @@ def test_quantising_frontend_equals_the_default_frontend_at_bench_config(runner2
                 small = runner24.predict_pcm16(pcm[:n], peak[:n])
                 np.testing.assert_array_equal(small, outs[fusion][:n])
     finally:
-        runner24.set_option(L.BN_OPT_FUSION, 11)
-    np.testing.assert_array_equal(outs[11], outs[43])
+        runner24.set_option(L.BN_OPT_FUSION, 139)
+    np.testing.assert_array_equal(outs[139], outs[171])     # default frontend vs quantising frontend (bit 5)
+    np.testing.assert_array_equal(outs[139], outs[11])      # tensor-core stem (bit 7) vs CUDA-core stem

@@ -65,7 +65,7 @@ def test_graph_every_tensor_bit_exact_generic(runner, graph, oracle_model, oracl
             _, o = oracle_model.run(oracle_spec, tap_id=tid)
             assert np.array_equal(g, o.reshape(-1)), f"tensor {tid} ({t.name}) differs in {(g != o.reshape(-1)).sum()} of {g.size}"
     finally:
-        runner.set_option(L.BN_OPT_FUSION, 11)
+        runner.set_option(L.BN_OPT_FUSION, 139)
         runner.set_option(L.BN_OPT_FORCE_GENERIC, 0)
 
 
@@ -95,10 +95,11 @@ def test_fused_plan_is_active_and_its_tensors_are_bit_exact(runner, graph, oracl
     # bit 3 (8) = whole-stage kernel for the 8 x 16 stage (bn_stage.cu): its inner block outputs #112 / #115 / #118 stay in
     # shared memory unless bit 4 (16) asks for them (debug taps); bit 5 (32) = quantising frontend, irrelevant for the
     # spectrogram entry used here; bit 6 (64) = warp-specialised pipeline form of the per-block kernel (bn_ds_ws.cu).
-    # 11 is the default.
+    # 139 = 11 + 128 is the default.
     inner = {112, 115, 118}
     for fusion, taps in ((11, [t for t in BLOCK_OUT_TAPS if t not in inner]), (27, BLOCK_OUT_TAPS), (3, BLOCK_OUT_TAPS), (7, BLOCK_OUT_TAPS),
                          (67, BLOCK_OUT_TAPS), (75, [t for t in BLOCK_OUT_TAPS if t not in inner]),
+                         (139, [t for t in BLOCK_OUT_TAPS if t not in inner]),     # bit 7 (128): stem as an im2col GEMM on tcgen05 (bn_stem_tc.cu)
                          (0, BLOCK_OUT_TAPS + DW_OUT_TAPS)):
         runner.set_option(L.BN_OPT_FUSION, fusion)
         try:
@@ -111,7 +112,7 @@ def test_fused_plan_is_active_and_its_tensors_are_bit_exact(runner, graph, oracl
                 _, o = oracle_model.run(oracle_spec, tap_id=tid)
                 assert np.array_equal(g, o.reshape(-1)), f"fusion={fusion} tensor {tid} differs in {(g != o.reshape(-1)).sum()} of {g.size}"
         finally:
-            runner.set_option(L.BN_OPT_FUSION, 11)
+            runner.set_option(L.BN_OPT_FUSION, 139)
 
 
 def test_fused_kernels_equal_layer_kernels_on_ragged_batches(blob, cfg, synth):
@@ -127,6 +128,8 @@ def test_fused_kernels_equal_layer_kernels_on_ragged_batches(blob, cfg, synth):
         fused = r.predict_pcm16(pcm, peak)
         r.set_option(L.BN_OPT_FUSION, 7)            # tensor-core depthwise variant, ragged last tile
         np.testing.assert_array_equal(fused, r.predict_pcm16(pcm, peak))
+        r.set_option(L.BN_OPT_FUSION, 139)          # tensor-core stem (bn_stem_tc.cu)
+        np.testing.assert_array_equal(fused, r.predict_pcm16(pcm, peak))
         r.set_option(L.BN_OPT_FUSION, 67)           # warp-specialised DS blocks (bn_ds_ws.cu), ragged last tile
         np.testing.assert_array_equal(fused, r.predict_pcm16(pcm, peak))
         r.set_option(L.BN_OPT_FUSION, 43)           # quantising frontend K1q + K2q (bn_frontend_q.cu) instead of K1 + float32 scratch + K2
@@ -139,7 +142,7 @@ def test_fused_kernels_equal_layer_kernels_on_ragged_batches(blob, cfg, synth):
         layer = r.predict_pcm16(pcm, peak)
         np.testing.assert_array_equal(fused, layer)
         for n in (1, 2, 3, 5):
-            r.set_option(L.BN_OPT_FUSION, 11)
+            r.set_option(L.BN_OPT_FUSION, 139)
             a = r.predict_pcm16(pcm[:n], peak[:n])
             np.testing.assert_array_equal(a, layer[:n])
     finally:

@@ -204,7 +204,7 @@ def test_gpu_generic_plan_bit_exact_on_synthesised_graphs(name):
             assert np.array_equal(dev.reshape(B, n), tap.reshape(B, n)), (name, op.index, op.kind, fusion)
             checked += 1
         assert checked >= len(g.ops) - 2 - (len(folded) if fusion is None else 0)
-    runner.set_option(L.BN_OPT_FUSION, 11)
+    runner.set_option(L.BN_OPT_FUSION, 139)
     runner.close()
 
 
