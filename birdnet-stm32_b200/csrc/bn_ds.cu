@@ -22,6 +22,8 @@
 // Equality with gemmlowp's sequence and the int32-safe domain are checked at plan-build time (bn_fast.cu).
 #include "bn_ds.cuh"
 
+#include <cstdlib>
+
 #include "bn_common.cuh"
 #include "bn_tc.cuh"
 
@@ -57,7 +59,10 @@ __device__ __forceinline__ int min_relu(int a, int b) {
 // multiplier, so the integer work moves from the saturated ALU pipe (SHF / VIMNMX / LEA) to the FMA pipe (IMAD family),
 // and the [-128, 127] clamp is one VIMNMX.RELU in the +128 domain; 2 = variant 1 with the residual rescale
 // MBQM((r - zp1) << 20, m1, s1) read from a 256-entry shared-memory table instead of computed.
-template <int S, int TR, int ADD, int DWT, int MB, int NT, int EPI = 0>
+// NC > 0: the block's output channel count as a compile-time constant (32 | 64).  The epilogue then walks the 16-channel groups of
+// a warp with compile-time channel numbers and reads its requantisation constants from the by-value copies in DsParams
+// (constant bank -> uniform registers, hoisted out of the per-pixel work): no shared-memory constant loads at all.
+template <int S, int TR, int ADD, int DWT, int MB, int NT, int EPI = 0, int NC = 0>
 __global__ void __launch_bounds__(NT, MB)
 k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles, DsParams P) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -315,8 +320,7 @@ k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles
     int b0, oy0;
     tile_origin(tile, b0, oy0);
     const size_t pix0 = ((size_t)b0 * P.oh + oy0) << P.ow_log;
-    for (int t = hsel; t < P.MT * NG; t += NT / 128) {
-      const int j = t / NG, g = t - j * NG;
+    auto unit = [&](const int j, const int g) {
       const int m = j * 128 + 32 * q + lane;
       const int bb = m >> P.trow_log;
       const bool ok = (b0 + bb) < Bw;
@@ -337,7 +341,7 @@ k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles
 #pragma unroll
         for (int jj = 0; jj < 4; jj++) {
           const int c = 16 * g + 4 * gg + jj;
-          const int4 rq = (ADD == 2 && EPI >= 1) ? make_int4(0, 0, 0, 0) : s_rq[c];
+          const int4 rq = (ADD == 2 && EPI >= 1) ? make_int4(0, 0, 0, 0) : (NC > 0 ? P.pw_rqc[c] : s_rq[c]);
           if (!ADD) {
             o[jj] = rq_hi(v[4 * gg + jj], rq.x, rq.y, rq.z) >> rq.w;
           } else if (ADD == 2 && EPI >= 1) {
@@ -357,7 +361,7 @@ k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles
             const int t2 = s1 + (y << 19);                                                    // -(zp2 + 128) << 19 is folded into a_co2
             o[jj] = (int)(((long long)t2 * (long long)P.a_mo + P.a_co2) >> 32) >> P.a_no;
           } else {
-            const int rz = s_rz[c];
+            const int rz = NC > 0 ? P.pw_rzc[c] : s_rz[c];
             const int y = clamp2(rq64(v[4 * gg + jj], rq.x, rq.y, rq.z, rz, rq.w), P.pw_lo, P.pw_hi);
             // residual term RoundingDivideByPOT(SRDHM((r - zp1) << 20, m1), n1): the operand is >= 0, so both
             // roundings are plain "add half, shift" and fold into one 64-bit multiply-add + shift
@@ -378,6 +382,19 @@ k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles
         ow4[gg] = pack4_sat(o[0], o[1], o[2], o[3]);
       }
       if (ok) *reinterpret_cast<uint4*>(out + (pix0 + m) * N + 16 * g) = make_uint4(ow4[0], ow4[1], ow4[2], ow4[3]);
+    };
+    if (NC > 0) {
+      // compile-time channel groups: group gi belongs to the warps with hsel == gi % (NT / 128)
+#pragma unroll
+      for (int gi = 0; gi < NC / 16; gi++) {
+        if ((gi % (NT / 128)) != hsel) continue;
+        for (int j = 0; j < P.MT; j++) unit(j, gi);
+      }
+    } else {
+      for (int t = hsel; t < P.MT * NG; t += NT / 128) {
+        const int j = t / NG;
+        unit(j, t - j * NG);
+      }
     }
   };
 
@@ -458,11 +475,11 @@ size_t ds_smem_bytes(const DsParams& P, int S, int TR) {
   return b + 1024;                                   // alignment slack
 }
 
-template <int S, int TR, int ADD, int DWT, int MB, int NT = DS_THREADS, int EPI = 0>
+template <int S, int TR, int ADD, int DWT, int MB, int NT = DS_THREADS, int EPI = 0, int NC = 0>
 static int launch_one(const int8_t* in, int8_t* out, int Bw, int ntiles, int grid, size_t smem, const DsParams& P, cudaStream_t st) {
   static unsigned long long attr = 0;
-  if (first_use_on_device(attr)) cudaFuncSetAttribute(k_ds<S, TR, ADD, DWT, MB, NT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  k_ds<S, TR, ADD, DWT, MB, NT, EPI><<<grid, NT, smem, st>>>(in, out, Bw, ntiles, P);
+  if (first_use_on_device(attr)) cudaFuncSetAttribute(k_ds<S, TR, ADD, DWT, MB, NT, EPI, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  k_ds<S, TR, ADD, DWT, MB, NT, EPI, NC><<<grid, NT, smem, st>>>(in, out, Bw, ntiles, P);
   return 0;
 }
 
@@ -471,6 +488,20 @@ int launch_ds(const int8_t* in, int8_t* out, int Bw, const DsParams& P, const Ds
   int grid = num_sms * L.ctas_per_sm;
   if (grid > ntiles) grid = ntiles;
   if (grid < 1) return 0;
+  // compile-time channel count builds (constants as kernel-parameter operands): the shapes of the 32- and 64-channel blocks
+  if (P.nc == P.N && (P.N == 32 || P.N == 64) && L.dwt && L.epi == 0 && L.threads == 256) {
+    static const int nc_on = getenv("BN_DS_NC") ? atoi(getenv("BN_DS_NC")) : 1;
+    if (nc_on) {
+#define NC_CASE(s, tr, add, mb)                                                                                    \
+      if (L.S == s && L.TR == tr && L.add_mode == add && mbs == mb)                                                 \
+        return P.N == 32 ? launch_one<s, tr, add, 1, mb, 256, 0, 32>(in, out, Bw, ntiles, grid, L.smem, P, st)      \
+                         : launch_one<s, tr, add, 1, mb, 256, 0, 64>(in, out, Bw, ntiles, grid, L.smem, P, st)
+      const int mbs = L.ctas_per_sm >= 3 ? 3 : 2;
+      NC_CASE(2, 8, 0, 3); NC_CASE(2, 8, 0, 2); NC_CASE(2, 4, 0, 3);
+      NC_CASE(1, 16, 2, 2); NC_CASE(1, 8, 2, 2);
+#undef NC_CASE
+    }
+  }
   // 512-thread build for single-CTA layers (transposed depthwise only; the two shapes the late layers use)
   // residual-ADD blocks with the multiply-high epilogue (transposed depthwise builds only)
   if (L.add_mode == 2 && L.epi >= 1 && L.dwt && L.S == 1) {

@@ -45,6 +45,14 @@ struct DsParams {
   int a_mo, a_no, a_rzo;  long long a_co;   // y = hi32(t * mo + co) >> a_no, a_no = no - 1, rounding + zp folded into co (saturating form)
   int a_zpo;                                // used when no == 0
   int a_lo, a_hi;
+  // Copies of pw_rq / pw_rz for blocks with N <= 64, passed BY VALUE: the k_ds builds with a compile-time channel count (NC)
+  // index them with compile-time channel numbers, so the epilogue constants are constant-bank / uniform-register operands
+  // instead of two or three shared-memory loads per output.  nc = N when filled, else 0.  (Measured for the 128-channel stage
+  // kernel too: 2.04 -> 2.41 ms with a run-time block index into the parameter space, 2.56 ms with the block loop unrolled --
+  // four blocks x 128 channels of constants do not fit the uniform registers -- so bn_stage.cu keeps its shared-memory copies.)
+  int nc;
+  int4 pw_rqc[64];
+  int pw_rzc[64];
 };
 
 struct DsLaunch {

@@ -433,6 +433,11 @@ static bool prep_ds(FastPlan& fp, FastImpl* im, Block& bl) {
   if (!build_rq_folded(fp, pw, N, rq, rz, bl.add_op < 0)) { if (getenv("BN_DEBUG")) fprintf(stderr, "prep_ds: reject at check 11 (line %d)\n", __LINE__); return false; }
   D.pw_rq = (const int4*)upload(im, rq.data(), rq.size() * 4);
   D.pw_rz = (const int*)upload(im, rz.data(), rz.size() * 4);
+  D.nc = 0;
+  if (N <= 64) {
+    for (int c = 0; c < N; c++) { D.pw_rqc[c] = make_int4(rq[4 * c], rq[4 * c + 1], rq[4 * c + 2], rq[4 * c + 3]); D.pw_rzc[c] = rz[c]; }
+    D.nc = N;
+  }
   D.dw_wm = (const int4*)bl.dw.wm;
   {  // filter-row words of the transposed depthwise: [ky][side][cg] int4, component j = channel 4 cg + j
     const int8_t* w = (const int8_t*)(fp.h_blob + dw.off[0]);   // [3][3][C]
