@@ -50,6 +50,14 @@ __device__ __forceinline__ int min_relu(int a, int b) {
   asm("min.relu.s32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
   return r;
 }
+// TMA bulk copy global -> shared (1-D), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void ds_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void ds_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
 // MB = resident CTAs per SM the register allocation is sized for: 2 (128 registers) or 3 (80 registers; only the
 // transposed depthwise fits that without meaningful spilling).
 // NT = threads per CTA: 256, or 512 for the late layers whose shared-memory footprint (64 KB weight image, four-chunk tiles)
@@ -83,12 +91,18 @@ k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles
   uint64_t* mbar = reinterpret_cast<uint64_t*>(s_rz + (EPI >= 1 ? 2 * N : ((N + 1) & ~1)));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2);
   int* s_lut1 = reinterpret_cast<int*>(tmem_slot + 2);          // EPI == 2: residual term per code, [256]
+  // The NC builds fetch the input rows with TMA bulk copies (one cp.async.bulk per row, issued by the lanes of warp 0,
+  // completion in bytes on fbar[buffer]) instead of 16-byte cp.async pieces issued by every thread: the staging was 12 % of the
+  // first block's instructions (ncu source view), now it is a few instructions of one warp.
+  constexpr bool TMA = NC > 0;
+  uint64_t* fbar = reinterpret_cast<uint64_t*>(tmem_slot + 2);  // [3] (aliases s_lut1, which only the EPI == 2 builds use)
 
   // ---- one-time setup ---------------------------------------------------------------------------
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), (uint32_t)P.tmem_cols);
   if (tid == 32) {
     mbar_init(smem_u32(&mbar[0]), 1);
     mbar_init(smem_u32(&mbar[1]), 1);
+    if (TMA) for (int s = 0; s < 3; s++) mbar_init(smem_u32(&fbar[s]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = tid; i < b_bytes / 16; i += NT) cp_async16(smem_u32(sB + 16 * i), P.w_img + 16 * (size_t)i);
@@ -178,6 +192,31 @@ k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles
       const int8_t* src = in + (((size_t)(b0 + bb) * P.ih + iy) * P.iw) * C;
       if (ok) { for (int p = lane; p < ppr; p += 32) cp_async16(smem_u32(dst + 16 * p), src + 16 * p); }
       else { for (int p = lane; p < ppr; p += 32) *reinterpret_cast<uint4*>(dst + 16 * p) = make_uint4(zpw, zpw, zpw, zpw); }
+    }
+  };
+
+  // ---- (1') the same with TMA: lane = input row of the tile (warp 0 only); padding rows are filled by the warp -------------
+  auto stage_tma = [&](int tile, unsigned char* sT, uint64_t* bar) {
+    int b0, oy0;
+    tile_origin(tile, b0, oy0);
+    const bool mine = lane < P.NB * TRIN;
+    const int bb = lane / TRIN, tr = lane - bb * TRIN;
+    const int iy = oy0 * S - P.pt + tr;
+    const bool ok = mine && (b0 + bb) < Bw && iy >= 0 && iy < P.ih;
+    const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+    unsigned padmask = __ballot_sync(0xffffffffu, mine && !ok);
+    const uint32_t row_bytes = (uint32_t)(P.iw * C);
+    if (lane == 0) ds_mbar_expect_tx(smem_u32(bar), (uint32_t)__popc(okmask) * row_bytes);
+    __syncwarp();
+    if (ok) {
+      fence_proxy_async();
+      ds_bulk_g2s(smem_u32(sT + ((size_t)lane * TW + P.pl) * C), in + (((size_t)(b0 + bb) * P.ih + iy) * P.iw) * C, row_bytes, smem_u32(bar));
+    }
+    while (padmask) {
+      const int row = __ffs(padmask) - 1;
+      padmask &= padmask - 1;
+      unsigned char* dst = sT + ((size_t)row * TW + P.pl) * C;
+      for (int p = lane; p < ppr; p += 32) *reinterpret_cast<uint4*>(dst + 16 * p) = make_uint4(zpw, zpw, zpw, zpw);
     }
   };
 
@@ -402,9 +441,14 @@ k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles
     // ---- unpipelined: stage -> depthwise -> MMA -> epilogue per tile --------------------------------------------
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
-      stage(tile, sT0);
-      cp_async_commit();
-      cp_async_wait_all();
+      if (TMA) {
+        if (warp == 0) stage_tma(tile, sT0, &fbar[0]);
+        mbar_wait(smem_u32(&fbar[0]), (uint32_t)(it & 1));
+      } else {
+        stage(tile, sT0);
+        cp_async_commit();
+        cp_async_wait_all();
+      }
       __syncthreads();
       run_dw(sT0, sA0);
       fence_proxy_async();
@@ -426,11 +470,13 @@ k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles
     const int accw = P.MT * N;                         // TMEM columns per accumulator buffer
     auto tile_of = [&](int k) { return blockIdx.x + k * gridDim.x; };
     for (int k = 0; k < NST - 1; k++) {
+      if (TMA) { if (k < nk && warp == 0) stage_tma(tile_of(k), sT0 + (k % NST) * tile_bytes, &fbar[k % NST]); continue; }
       if (k < nk) stage(tile_of(k), sT0 + (k % NST) * tile_bytes);
       cp_async_commit();
     }
     if (nk > 0) {
-      if (NST == 2) cp_async_wait_all(); else asm volatile("cp.async.wait_group 1;" ::: "memory");
+      if (TMA) mbar_wait(smem_u32(&fbar[0]), 0u);
+      else if (NST == 2) cp_async_wait_all(); else asm volatile("cp.async.wait_group 1;" ::: "memory");
       __syncthreads();
       run_dw(sT0, sA0);
       fence_proxy_async();
@@ -440,10 +486,15 @@ k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles
     }
     for (int k = 0; k < nk; k++) {
       const int ab = k & 1;
-      if (k + NST - 1 < nk) stage(tile_of(k + NST - 1), sT0 + ((k + NST - 1) % NST) * tile_bytes);
-      cp_async_commit();
+      if (TMA) {
+        if (k + NST - 1 < nk && warp == 0) stage_tma(tile_of(k + NST - 1), sT0 + ((k + NST - 1) % NST) * tile_bytes, &fbar[(k + NST - 1) % NST]);
+      } else {
+        if (k + NST - 1 < nk) stage(tile_of(k + NST - 1), sT0 + ((k + NST - 1) % NST) * tile_bytes);
+        cp_async_commit();
+      }
       if (k + 1 < nk) {
-        if (NST == 2) cp_async_wait_all(); else asm volatile("cp.async.wait_group 1;" ::: "memory");
+        if (TMA) mbar_wait(smem_u32(&fbar[(k + 1) % NST]), (uint32_t)(((k + 1) / NST) & 1));
+        else if (NST == 2) cp_async_wait_all(); else asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncthreads();
         run_dw(sT0 + ((k + 1) % NST) * tile_bytes, sA0 + (ab ^ 1) * a_bytes);
         fence_proxy_async();
@@ -470,7 +521,7 @@ size_t ds_smem_bytes(const DsParams& P, int S, int TR) {
   const int nab = P.nst > 1 ? 2 : 1;
   size_t b = (size_t)P.N * P.KP + (size_t)nab * P.MT * 128 * P.KP;
   b += (size_t)P.nst * (((size_t)P.NB * trin * tw * P.C + 15) & ~(size_t)15);
-  b += (size_t)P.N * 16 + (size_t)((P.N + 1) & ~1) * 4 + 32;
+  b += (size_t)P.N * 16 + (size_t)((P.N + 1) & ~1) * 4 + 64;     // constants, 2 + 3 mbarriers, TMEM slot
   b += (size_t)P.epi_smem;                          // multiply-high epilogue variants: second constant word per channel + residual table
   return b + 1024;                                   // alignment slack
 }
