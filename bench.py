@@ -44,7 +44,7 @@ WORKLOAD = ("config5: file-sharded evaluation of synthetic multi-chunk files (ch
 # warp instructions of the shipped kernels' inner loops: 256 real 512-point FFTs + |z| + min/max (K1), 65,792 quantisations
 # + 16,384 LUT epilogues (K2), 131,072 stem outputs x 9 taps (K3), 249,856 depthwise outputs, 311,296 pointwise
 # requantisations of which 188,416 carry TFLite's three-multiplier residual ADD (K45), MEAN + FC (K6).
-CUDA_CORE_WARP_INSTR_PER_CHUNK = 452_000
+CUDA_CORE_WARP_INSTR_PER_CHUNK = 429_000      # ncu smsp__inst_executed.sum over one wave / chunks (profiles/r2/ncu_full_summary.md, commit 79169f5)
 
 
 def load_cfg_24k() -> dict:
@@ -228,11 +228,16 @@ def e2e_files_leg(runner, cfg, n_files: int, io_workers: int) -> dict:
         ecfg = dict(cfg, class_names=classes)
         kw = dict(pooling="lme", io_workers=io_workers, metrics_backend="device")
         evaluate(runner, files[: min(64, n_files)], classes, ecfg, **kw)      # warm-up (pinned batch buffers, metric kernels)
-        t0 = time.perf_counter()
-        metrics, per_file, _, _ = evaluate(runner, files, classes, ecfg, **kw)
-        dt = time.perf_counter() - t0
+        # three timed passes, median reported: the leg is host-side work (16 reader threads, page cache) and varies from box to
+        # box and run to run far more than anything on the device
+        runs = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            metrics, per_file, _, _ = evaluate(runner, files, classes, ecfg, **kw)
+            runs.append(time.perf_counter() - t0)
+        dt = sorted(runs)[1]
         return {"value": n_chunks / dt, "unit": "chunks/s", "files": len(per_file), "chunks": n_chunks, "files_per_s": len(per_file) / dt,
-                "seconds": dt, "reader": "native (bn_read_pcm16_batch)", "reader_threads": io_workers, "pooling": "lme", "metrics_backend": "device",
+                "seconds": dt, "seconds_all_passes": [round(x, 4) for x in runs], "reader": "native (bn_read_pcm16_batch)", "reader_threads": io_workers, "pooling": "lme", "metrics_backend": "device",
                 "bytes_read": int(sum(os.path.getsize(f) for f in files)), "skipped_files": metrics.get("skipped_files", 0),
                 "what": "evaluate() on synthetic mono PCM16 WAV files in the page cache: read + chunk + H2D + inference + pooling + metrics"}
     finally:

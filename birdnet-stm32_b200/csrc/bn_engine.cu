@@ -164,7 +164,7 @@ extern "C" int bn_create(const void* blob, size_t nbytes, int device, bn_engine*
   e->buf.assign(e->hdr->n_tensors, nullptr);
   e->last_ptr.assign(e->hdr->n_tensors, nullptr);
   fast_plan_build(e->fast, e->blob.data(), e->hdr, e->tensors, e->ops, e->d_blob);
-  e->accel = gen_accel_build(e->blob.data(), e->d_blob, e->hdr, e->tensors, e->ops);
+  // (the generic plan's accelerated-op records are built on its first use: run_generic)
   { int sms = 148; if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) e->fast.num_sms = sms; }
   *out = e;
   return BN_OK;
@@ -273,6 +273,9 @@ static void fill_conv(const bn_engine* e, const bn_blob_op& op, ConvParams& P) {
 // Runs ops [0, n_ops) on Bw chunks.  ptr[] = per-slot device pointers for this wave.
 static int run_generic(bn_engine* e, std::vector<void*>& ptr, int Bw, cudaStream_t st) {
   const bn_blob_header* h = e->hdr;
+  // first use of the one-kernel-per-op plan: weight images / folded constants of the ops that have a fast kernel (not needed,
+  // and not paid for at bn_create, while the fused plan runs)
+  if (!e->accel) e->accel = gen_accel_build(e->blob.data(), e->d_blob, e->hdr, e->tensors, e->ops);
   const int R = e->rounding;
   for (uint32_t oi = 0; oi < h->n_ops; oi++) {
     const bn_blob_op& op = e->ops[oi];
