@@ -84,8 +84,10 @@ k_stft_mag(const void* __restrict__ pcm_v, const float* __restrict__ peak, float
 
   // Raw int16 samples of a tile arrive through cp.async one tile ahead (group grp of 8 samples is always handled by
   // thread grp % FE_THREADS, so a thread only ever touches its own slots of sraw and no barrier is needed for them).
+  // groups_w is a power of two for every shipped configuration (W = 256): shift instead of an integer division per tile
+  const int gw_log = (groups_w & (groups_w - 1)) == 0 ? 31 - __clz(groups_w) : -1;
   auto tile_geom = [&](int tile_id, int& b, int& t0, long& chunk_base, long& g_first, int& shift, int& ngroups) {
-    b = tile_id / groups_w;
+    b = gw_log >= 0 ? (tile_id >> gw_log) : tile_id / groups_w;
     t0 = (tile_id - b * groups_w) * FRAMES_PER_CTA;
     chunk_base = (long)b * T + a0;                        // in pcm_al sample indices
     const long g_lo = chunk_base + (long)t0 * hop - NFFT / 2;
@@ -96,6 +98,12 @@ k_stft_mag(const void* __restrict__ pcm_v, const float* __restrict__ peak, float
   auto prefetch = [&](int tile_id) {
     int b, t0, shift, ngroups; long chunk_base, g_first;
     tile_geom(tile_id, b, t0, chunk_base, g_first, shift, ngroups);
+    if (g_first >= a0 && g_first + (long)G * ngroups <= a0 + total) {
+      // the whole span lies inside the buffer (every tile but the first / last of the wave): no per-group range checks
+      const raw_t* src = pcm_al + g_first;
+      for (int grp = tid; grp < ngroups; grp += FE_THREADS) cp_async16_fe(sraw + grp, src + G * grp);
+      return;
+    }
     for (int grp = tid; grp < ngroups; grp += FE_THREADS) {
       const long g = g_first + (long)G * grp;
       if (g >= a0 && g + G <= a0 + total) {
@@ -125,6 +133,23 @@ k_stft_mag(const void* __restrict__ pcm_v, const float* __restrict__ peak, float
     // y = (s / 32768) / peak (audio/io.py:114-126) as one multiply by the rounded reciprocal (<= 1.5 ulp from the reference)
     const float cs = F32IN ? (pk > 0.0f ? __fdiv_rn(1.0f, pk) : 1.0f) : (pk > 0.0f ? __fdiv_rn(1.0f, 32768.0f * pk) : (1.0f / 32768.0f));
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+    const int rel0 = (int)(g_first - chunk_base);           // chunk-relative index of the span's first group (|rel0| < 2^31)
+    const bool inside = rel0 >= 0 && rel0 + G * ngroups <= T;   // no zero padding in this tile (all but the chunk's first / last)
+    if (!F32IN && inside) {
+      for (int grp = tid; grp < ngroups; grp += FE_THREADS) {
+        const uint4 wv = sraw[grp];
+        const unsigned ww[4] = {wv.x, wv.y, wv.z, wv.w};
+        float fv[8];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int lo = (int)(short)(ww[j] & 0xffffu), hi = (int)ww[j] >> 16;
+          fv[2 * j] = (__int_as_float(0x4B400000 + lo) - 12582912.0f) * cs;
+          fv[2 * j + 1] = (__int_as_float(0x4B400000 + hi) - 12582912.0f) * cs;
+        }
+        *reinterpret_cast<float4*>(xs + 8 * grp) = make_float4(fv[0], fv[1], fv[2], fv[3]);
+        *reinterpret_cast<float4*>(xs + 8 * grp + 4) = make_float4(fv[4], fv[5], fv[6], fv[7]);
+      }
+    } else
     for (int grp = tid; grp < ngroups; grp += FE_THREADS) {
       const long rel = g_first + (long)G * grp - chunk_base;   // chunk-relative index of the group's first sample
       const uint4 wv = sraw[grp];
