@@ -13,10 +13,12 @@ constexpr int FRAMES_PER_CTA = 32;
 constexpr int FE_THREADS = 256;  // 8 warps = 16 half-warps = 16 concurrent FFTs, 2 rounds
 constexpr int TILE_LD = FRAMES_PER_CTA + 1;
 
-// sqrt.approx.f32: max relative error 2^-23, far inside the 1e-4 frontend tolerance
+// sqrt.approx.ftz.f32: max relative error 2^-23, far inside the 1e-4 frontend tolerance.  .ftz makes it ONE MUFU.SQRT: without it
+// every call carries a subnormal-range fix-up (FSETP + two predicated FMULs); a squared magnitude below 1.2e-38 (an input of
+// 1e-19 of full scale -- digital silence is exactly 0 either way) now gives 0 instead of a value below 1.1e-19.
 __device__ __forceinline__ float fast_sqrt(float x) {
   float r;
-  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
 

@@ -210,6 +210,8 @@ k_stft_mag(const void* __restrict__ pcm_v, const float* __restrict__ peak, float
       // real-FFT split, two bins per step: with E = Z[k] + conj(Z[N-k]), O = (Z[k] - conj(Z[N-k])) / i (Z carries the
       // factor 1/2) and T = W512^k O:   X[k] = E + T   and   X[N-k] = conj(E - T)   (N = 256), so |X[N-k]| = |E - T|.
       float* orow = FRAME_MAJOR ? out + ((long)b * W + t0 + f) * ldk : tile + f;
+      float* const oa = orow + l;                         // bins l + 16 j and 256 - l - 16 j: per-thread bases, compile-time offsets
+      float* const ob = orow + NC - l;
 #pragma unroll
       for (int j = 0; j < 8; j++) {
         const int k = l + 16 * j;                         // 0..127, partner bin 256 - k
@@ -221,7 +223,7 @@ k_stft_mag(const void* __restrict__ pcm_v, const float* __restrict__ peak, float
         const float2 xa = add2(e, t), xb = sub2(e, t);
         const float ar = xa.x, ai = xa.y, br = xb.x, bi = xb.y;
         const float ma = fast_sqrt(ar * ar + ai * ai), mb = fast_sqrt(br * br + bi * bi);
-        if (FRAME_MAJOR) { orow[k] = ma; orow[NC - k] = mb; }   // 16 lanes -> 64 contiguous bytes each
+        if (FRAME_MAJOR) { oa[16 * j] = ma; ob[-16 * j] = mb; }   // 16 lanes -> 64 contiguous bytes each
         else { orow[k * TILE_LD] = ma; orow[(NC - k) * TILE_LD] = mb; }
         lmin = fminf(lmin, fminf(ma, mb));
         lmax = fmaxf(lmax, fmaxf(ma, mb));
