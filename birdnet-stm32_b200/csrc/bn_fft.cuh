@@ -83,4 +83,18 @@ __device__ __forceinline__ void fft16(float2 (&v)[16]) {
   for (int i = 0; i < 16; i++) v[i] = o[i];
 }
 
+// Real-FFT split partner without shared memory.  After the second radix-16 pass lane l of a half-warp holds
+// Z[l + 16 k2] in v[k2].  The split pairs bin k = l + 16 j (j < 8) with bin 256 - k = (16 - l) + 16 (15 - j): lane (16 - l) & 15,
+// register 15 - j -- one shuffle per component.  Lane 0 pairs with itself (256 - 16 j = 16 (16 - j), and Z[256] = Z[0]).
+// All 32 lanes of the warp must call this (the two half-warps shuffle independently inside one instruction).
+template <int J>
+__device__ __forceinline__ float2 split_partner(const float2 (&v)[16], int l, int lane_in_warp) {
+  const int src = (lane_in_warp & 16) | ((16 - l) & 15);
+  float2 zn;
+  zn.x = __shfl_sync(0xffffffffu, v[15 - J].x, src);
+  zn.y = __shfl_sync(0xffffffffu, v[15 - J].y, src);
+  if (l == 0) zn = v[(16 - J) & 15];
+  return zn;
+}
+
 }  // namespace bn

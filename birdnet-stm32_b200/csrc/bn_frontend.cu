@@ -204,19 +204,16 @@ k_stft_mag(const void* __restrict__ pcm_v, const float* __restrict__ peak, float
       for (int n2 = 0; n2 < 16; n2++) v[n2] = zb[l * 17 + n2];
       __syncwarp(hmask);
       fft16(v);                                           // over n2 -> k2 ; Z[k1 + 16 k2] = v[k2]
-#pragma unroll
-      for (int k2 = 0; k2 < 16; k2++) zb[l + 16 * k2] = v[k2];   // natural order Z[0..255]
-      __syncwarp(hmask);
       // real-FFT split, two bins per step: with E = Z[k] + conj(Z[N-k]), O = (Z[k] - conj(Z[N-k])) / i (Z carries the
       // factor 1/2) and T = W512^k O:   X[k] = E + T   and   X[N-k] = conj(E - T)   (N = 256), so |X[N-k]| = |E - T|.
+      // Z[k] is the thread's own v[j]; its partner Z[N-k] comes from lane 16 - l by register shuffle (split_partner): the
+      // second shared-memory exchange (16 stores + 17 loads of 8 bytes per thread) is gone -- K1 runs at 70 % of the
+      // shared-memory data pipe, its tightest resource.
       float* orow = FRAME_MAJOR ? out + ((long)b * W + t0 + f) * ldk : tile + f;
       float* const oa = orow + l;                         // bins l + 16 j and 256 - l - 16 j: per-thread bases, compile-time offsets
       float* const ob = orow + NC - l;
-#pragma unroll
-      for (int j = 0; j < 8; j++) {
+      auto split_step = [&](const float2 zk, const float2 zn, const int j) {
         const int k = l + 16 * j;                         // 0..127, partner bin 256 - k
-        const float2 zk = zb[k];
-        const float2 zn = zb[(NC - k) & 255];
         const float2 e = make_float2(zk.x + zn.x, zk.y - zn.y);
         const float2 o = make_float2(zk.y + zn.y, zn.x - zk.x);
         const float2 t = cmul(o, tws[j]);
@@ -227,15 +224,20 @@ k_stft_mag(const void* __restrict__ pcm_v, const float* __restrict__ peak, float
         else { orow[k * TILE_LD] = ma; orow[(NC - k) * TILE_LD] = mb; }
         lmin = fminf(lmin, fminf(ma, mb));
         lmax = fmaxf(lmax, fmaxf(ma, mb));
-      }
-      if (l == 0) {                                       // bin 128 pairs with itself: |X[128]| = 2 |Z[128]|
-        const float2 z = zb[128];
+      };
+      const int lw = tid & 31;
+      split_step(v[0], split_partner<0>(v, l, lw), 0); split_step(v[1], split_partner<1>(v, l, lw), 1);
+      split_step(v[2], split_partner<2>(v, l, lw), 2); split_step(v[3], split_partner<3>(v, l, lw), 3);
+      split_step(v[4], split_partner<4>(v, l, lw), 4); split_step(v[5], split_partner<5>(v, l, lw), 5);
+      split_step(v[6], split_partner<6>(v, l, lw), 6); split_step(v[7], split_partner<7>(v, l, lw), 7);
+      if (l == 0) {                                       // bin 128 = Z[0 + 16 * 8] pairs with itself: |X[128]| = 2 |Z[128]|
+        const float2 z = v[8];
         const float m = 2.0f * fast_sqrt(z.x * z.x + z.y * z.y);
         if (FRAME_MAJOR) orow[128] = m; else orow[128 * TILE_LD] = m;
         lmin = fminf(lmin, m);
         lmax = fmaxf(lmax, m);
       }
-      __syncwarp(hmask);
+      __syncwarp(hmask);                                  // zb is reused by the next round's first exchange
     }
 
     // CTA reduction of min / max

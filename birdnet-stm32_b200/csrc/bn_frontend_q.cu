@@ -366,15 +366,8 @@ k_stft_q(const void* __restrict__ pcm_v, const float* __restrict__ peak, uint8_t
       for (int n2 = 0; n2 < 16; n2++) v[n2] = zb[l * 17 + n2];
       __syncwarp(hmask);
       fft16(v);
-#pragma unroll
-      for (int k2 = 0; k2 < 16; k2++) zb[l + 16 * k2] = v[k2];
-      __syncwarp(hmask);
       float mg[16];                                       // mg[2 j] = |X[l + 16 j]|, mg[2 j + 1] = |X[256 - (l + 16 j)]|
-#pragma unroll
-      for (int j = 0; j < 8; j++) {
-        const int k = l + 16 * j;
-        const float2 zk = zb[k];
-        const float2 zn = zb[(NC - k) & 255];
+      auto split_step = [&](const float2 zk, const float2 zn, const int j) {   // partner by register shuffle: see bn_frontend.cu
         const float2 e = make_float2(zk.x + zn.x, zk.y - zn.y);
         const float2 o = make_float2(zk.y + zn.y, zn.x - zk.x);
         const float2 t = cmul(o, tws[j]);
@@ -383,8 +376,13 @@ k_stft_q(const void* __restrict__ pcm_v, const float* __restrict__ peak, uint8_t
         mg[2 * j] = ma; mg[2 * j + 1] = mb;
         lmin = fminf(lmin, fminf(ma, mb));
         lmax = fmaxf(lmax, fmaxf(ma, mb));
-      }
-      const float2 z128 = zb[128];                        // bin 128 pairs with itself: |X[128]| = 2 |Z[128]| (used from lane l == 0)
+      };
+      const int lw = threadIdx.x & 31;
+      split_step(v[0], split_partner<0>(v, l, lw), 0); split_step(v[1], split_partner<1>(v, l, lw), 1);
+      split_step(v[2], split_partner<2>(v, l, lw), 2); split_step(v[3], split_partner<3>(v, l, lw), 3);
+      split_step(v[4], split_partner<4>(v, l, lw), 4); split_step(v[5], split_partner<5>(v, l, lw), 5);
+      split_step(v[6], split_partner<6>(v, l, lw), 6); split_step(v[7], split_partner<7>(v, l, lw), 7);
+      const float2 z128 = v[8];                           // bin 128 pairs with itself: |X[128]| = 2 |Z[128]| (meaningful in lane l == 0)
       const float m128 = 2.0f * fast_sqrt(z128.x * z128.x + z128.y * z128.y);
       if (l == 0) { lmin = fminf(lmin, m128); lmax = fmaxf(lmax, m128); }
       __syncwarp();
