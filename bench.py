@@ -44,7 +44,7 @@ WORKLOAD = ("config5: file-sharded evaluation of synthetic multi-chunk files (ch
 # warp instructions of the shipped kernels' inner loops: 256 real 512-point FFTs + |z| + min/max (K1), 65,792 quantisations
 # + 16,384 LUT epilogues (K2), 131,072 stem outputs x 9 taps (K3), 249,856 depthwise outputs, 311,296 pointwise
 # requantisations of which 188,416 carry TFLite's three-multiplier residual ADD (K45), MEAN + FC (K6).
-CUDA_CORE_WARP_INSTR_PER_CHUNK = 429_000      # ncu smsp__inst_executed.sum over one wave / chunks (profiles/r2/ncu_full_summary.md, commit 79169f5)
+CUDA_CORE_WARP_INSTR_PER_CHUNK = 408_000      # ncu smsp__inst_executed.sum over one wave / chunks (profiles/r2/ncu_full_summary.md, commit 7620eb1)
 
 
 def load_cfg_24k() -> dict:
