@@ -188,6 +188,11 @@ k_stft_q(const void* __restrict__ pcm_v, const float* __restrict__ peak, uint8_t
   auto prefetch = [&](int tile_id) {
     int b, t0, shift, ngroups; long chunk_base, g_first;
     tile_geom(tile_id, b, t0, chunk_base, g_first, shift, ngroups);
+    if (g_first >= a0 && g_first + (long)G * ngroups <= a0 + total) {   // whole span inside the buffer: no per-group range checks
+      const raw_t* src = pcm_al + g_first;
+      for (int grp = tid; grp < ngroups; grp += FE_THREADS) cp_async16_fe(sraw + grp, src + G * grp);
+      return;
+    }
     for (int grp = tid; grp < ngroups; grp += FE_THREADS) {
       const long g = g_first + (long)G * grp;
       if (g >= a0 && g + G <= a0 + total) {
@@ -314,6 +319,23 @@ k_stft_q(const void* __restrict__ pcm_v, const float* __restrict__ peak, uint8_t
     unsigned p_seen = 0, p_mn = 0, p_mx = 0;
     if (it > 0 && lane == 0) peek(prev_b, p_seen, p_mn, p_mx);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+    const int rel0 = (int)(g_first - chunk_base);
+    const bool inside = rel0 >= 0 && rel0 + G * ngroups <= T;   // no zero padding in this tile (all but the chunk's first / last)
+    if (!F32IN && inside) {
+      for (int grp = tid; grp < ngroups; grp += FE_THREADS) {
+        const uint4 wv = sraw[grp];
+        const unsigned ww[4] = {wv.x, wv.y, wv.z, wv.w};
+        float fv[8];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int lo = (int)(short)(ww[j] & 0xffffu), hi = (int)ww[j] >> 16;
+          fv[2 * j] = (__int_as_float(0x4B400000 + lo) - 12582912.0f) * cs;
+          fv[2 * j + 1] = (__int_as_float(0x4B400000 + hi) - 12582912.0f) * cs;
+        }
+        *reinterpret_cast<float4*>(xs + 8 * grp) = make_float4(fv[0], fv[1], fv[2], fv[3]);
+        *reinterpret_cast<float4*>(xs + 8 * grp + 4) = make_float4(fv[4], fv[5], fv[6], fv[7]);
+      }
+    } else
     for (int grp = tid; grp < ngroups; grp += FE_THREADS) {
       const long rel = g_first + (long)G * grp - chunk_base;
       const uint4 wv = sraw[grp];
