@@ -70,7 +70,9 @@ __device__ __forceinline__ void ds_mbar_expect_tx(uint32_t bar, uint32_t bytes) 
 // NC > 0: the block's output channel count as a compile-time constant (32 | 64).  The epilogue then walks the 16-channel groups of
 // a warp with compile-time channel numbers and reads its requantisation constants from the by-value copies in DsParams
 // (constant bank -> uniform registers, hoisted out of the per-pixel work): no shared-memory constant loads at all.
-template <int S, int TR, int ADD, int DWT, int MB, int NT, int EPI = 0, int NC = 0>
+// STEM = 1 (S = 2, TR = 4, NC = 32, unpipelined; the first block of the shipped graph): `in` is the head output and the input
+// tile is PRODUCED in the kernel by the stem's im2col GEMM instead of being loaded (see DsParams::stem).
+template <int S, int TR, int ADD, int DWT, int MB, int NT, int EPI = 0, int NC = 0, int STEM = 0>
 __global__ void __launch_bounds__(NT, MB)
 k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles, DsParams P) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -437,11 +439,93 @@ k_ds(const int8_t* __restrict__ in, int8_t* __restrict__ out, int Bw, int ntiles
     }
   };
 
+  // ---- (0) STEM builds: the tile's TRIN stem rows from TRIN + 2 head rows ---------------------------------------------------------
+  //   scratch at smem + P.stem_off: head rows [TRIN + 2][272] | im2col operand [TRIN][128][32] (SWIZZLE_32B) | weight image [16][32]
+  //   tensor memory: pointwise accumulators at columns [0, MT * N), stem accumulators at [MT * N, MT * N + 16 TRIN)
+  auto stem_rows = [&](int tile, unsigned char* sT, int it) {
+    constexpr int HP = 272;                              // head row pitch: 256 bytes + right halo
+    unsigned char* sH = smem + P.stem_off;
+    unsigned char* sAs = sH + ((TRIN + 2) * HP + 1023) / 1024 * 1024;
+    unsigned char* sBs = sAs + TRIN * 4096;
+    const StemTcParams& Q = P.stem;
+    int b0, oy0;
+    tile_origin(tile, b0, oy0);
+    const unsigned hzp = 0x01010101u * (unsigned)(uint8_t)Q.in_zp;
+    if (it == 0) {                                       // once per CTA: weight image, zeroed operand, right halo of the head rows
+      for (int i = tid; i < 512 / 16; i += NT) *reinterpret_cast<uint4*>(sBs + 16 * i) = __ldg(reinterpret_cast<const uint4*>(Q.w_img) + i);
+      for (int i = tid; i < TRIN * 4096 / 16; i += NT) *reinterpret_cast<uint4*>(sAs + 16 * i) = make_uint4(0, 0, 0, 0);
+      for (int i = tid; i < (TRIN + 2) * 4; i += NT) *reinterpret_cast<unsigned*>(sH + (i >> 2) * HP + 256 + 4 * (i & 3)) = hzp;
+    }
+    const int sr0 = oy0 * S - P.pt;                      // first stem row of the tile (S = 2, pt = 0: 2 oy0)
+    if (tid < (TRIN + 2) * 16) {
+      const int r = tid >> 4, p = tid & 15;
+      const int iy = sr0 - 1 + r;
+      uint4 v = make_uint4(hzp, hzp, hzp, hzp);
+      if (iy >= 0 && iy < Q.ih && b0 < Bw) v = __ldg(reinterpret_cast<const uint4*>(in + ((size_t)b0 * Q.ih + iy) * 256) + p);
+      *reinterpret_cast<uint4*>(sH + r * HP + 16 * p) = v;
+    }
+    __syncthreads();
+    for (int task = tid; task < TRIN * 64; task += NT) {  // im2col: (stem row ry, pixel pair pp), see bn_stem_tc.cu
+      const int ry = task >> 6, pp = task & 63;
+      unsigned e[3], o[3];
+#pragma unroll
+      for (int fy = 0; fy < 3; fy++) {
+        const unsigned* rp = reinterpret_cast<const unsigned*>(sH + (ry + fy) * HP) + pp;
+        e[fy] = rp[0]; o[fy] = __byte_perm(rp[0], rp[1], 0x4432);
+      }
+      const uint4 ae = make_uint4(__byte_perm(e[0], e[1], 0x4210), __byte_perm(e[1], e[2], 0x5421), __byte_perm(e[2], 0u, 0x4442), 0u);
+      const uint4 ao = make_uint4(__byte_perm(o[0], o[1], 0x4210), __byte_perm(o[1], o[2], 0x5421), __byte_perm(o[2], 0u, 0x4442), 0u);
+      const int m = 2 * pp;
+      unsigned char* ap = sAs + ry * 4096 + m * 32 + (((m >> 2) & 1) << 4);
+      *reinterpret_cast<uint4*>(ap) = ae;
+      *reinterpret_cast<uint4*>(ap + 32) = ao;
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    const uint32_t tm_stem = tmem_base + (uint32_t)(P.MT * N);
+    if (tid == 0) {
+      tc_fence_after();
+      const uint64_t bd = make_desc(smem_u32(sBs), 256, 6u);
+      const uint32_t idesc_s = make_idesc_i8(128, 16);
+#pragma unroll
+      for (int ry = 0; ry < TRIN; ry++) umma_i8(tm_stem + (uint32_t)(ry * 16), make_desc(smem_u32(sAs) + ry * 4096, 256, 6u), bd, idesc_s, 0u);
+      umma_commit(smem_u32(&mbar[1]));
+    }
+    mbar_wait(smem_u32(&mbar[1]), (uint32_t)(it & 1));
+    tc_fence_after();
+    // stem epilogue: thread = pixel 32 q + lane of rows hsel, hsel + 2, ...; 16 channels -> one 16-byte store into the input tile
+    for (int ry = hsel; ry < TRIN; ry += NT / 128) {
+      unsigned char* dst = sT + ((size_t)ry * TW + P.pl + 32 * q + lane) * C;
+      if (sr0 + ry >= P.ih) {                             // SAME padding row below the map
+        *reinterpret_cast<uint4*>(dst) = make_uint4(zpw, zpw, zpw, zpw);
+        continue;
+      }
+      int v[16];
+      tmem_ld16(tm_stem + (uint32_t)(ry * 16) + ((uint32_t)(32 * q) << 16), v);
+      unsigned ow4[4];
+#pragma unroll
+      for (int g = 0; g < 4; g++) {
+        int y[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int4 rq = Q.rq[4 * g + j];
+          y[j] = rq_hi(v[4 * g + j], rq.x, rq.y, rq.z) >> rq.w;
+        }
+        ow4[g] = pack4_sat(y[0], y[1], y[2], y[3]);
+      }
+      *reinterpret_cast<uint4*>(dst) = make_uint4(ow4[0], ow4[1], ow4[2], ow4[3]);
+    }
+    tc_fence_before();
+  };
+
   if (NST == 1) {
     // ---- unpipelined: stage -> depthwise -> MMA -> epilogue per tile --------------------------------------------
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
-      if (TMA) {
+      if (STEM) {
+        stem_rows(tile, sT0, it);
+      } else if (TMA) {
         if (warp == 0) stage_tma(tile, sT0, &fbar[0]);
         mbar_wait(smem_u32(&fbar[0]), (uint32_t)(it & 1));
       } else {
@@ -531,6 +615,31 @@ static int launch_one(const int8_t* in, int8_t* out, int Bw, int ntiles, int gri
   static unsigned long long attr = 0;
   if (first_use_on_device(attr)) cudaFuncSetAttribute(k_ds<S, TR, ADD, DWT, MB, NT, EPI, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   k_ds<S, TR, ADD, DWT, MB, NT, EPI, NC><<<grid, NT, smem, st>>>(in, out, Bw, ntiles, P);
+  return 0;
+}
+
+// ---- stem + first block --------------------------------------------------------------------------------------------------------------
+bool ds_stem_supported(const DsParams& P, int S, int add_mode) {
+  return S == 2 && add_mode == 0 && P.C == 16 && P.N == 32 && P.nc == 32 && P.iw == 128 && P.ow == 64 && P.pt == 0 && P.pl == 0 &&
+         P.NB == 1 && P.oh % 4 == 0 && P.ih == 2 * P.oh && P.KP == 32 && P.RW == 32;
+}
+
+size_t ds_stem_smem_bytes(const DsParams& P, int* stem_off) {
+  const int TRIN = 9;
+  size_t b = ds_smem_bytes(P, 2, 4);                  // includes 1 KB of alignment slack
+  b = (b + 1023) & ~(size_t)1023;
+  *stem_off = (int)(b - 1024);                        // relative to the 1024-aligned base the kernel computes
+  return b + (((TRIN + 2) * 272 + 1023) / 1024 * 1024) + TRIN * 4096 + 1024;
+}
+
+int launch_ds_stem(const int8_t* head_out, int8_t* out, int Bw, const DsParams& P, size_t smem, int num_sms, cudaStream_t st) {
+  const int ntiles = Bw * (P.oh / 4);
+  int grid = num_sms * 2;
+  if (grid > ntiles) grid = ntiles;
+  if (grid < 1) return 0;
+  static unsigned long long attr = 0;
+  if (first_use_on_device(attr)) cudaFuncSetAttribute(k_ds<2, 4, 0, 1, 2, 256, 0, 32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  k_ds<2, 4, 0, 1, 2, 256, 0, 32, 1><<<grid, 256, smem, st>>>(head_out, out, Bw, ntiles, P);
   return 0;
 }
 

@@ -5,6 +5,8 @@
 
 #include <vector>
 
+#include "bn_stem_tc.cuh"
+
 namespace bn {
 
 // One DS block of models/dscnn.py:28-84 (ds_conv_block): DEPTHWISE_CONV_2D 3x3 (+ReLU6) -> CONV_2D 1x1
@@ -53,6 +55,11 @@ struct DsParams {
   int nc;
   int4 pw_rqc[64];
   int pw_rzc[64];
+  // k_ds<..., STEM = 1> (first block only): the kernel's input is the HEAD output int8 [B][ih][256]; the stem convolution of the
+  // tile's input rows is computed in the kernel (im2col GEMM of bn_stem_tc.cu) straight into the shared-memory input tile, so the
+  // stem output tensor (131 KB per chunk written and read back) never exists in global memory.
+  StemTcParams stem;
+  int stem_off;           // byte offset of the stem scratch (head rows, im2col operand, weight image) in dynamic shared memory
 };
 
 struct DsLaunch {
@@ -67,6 +74,10 @@ struct DsLaunch {
 
 int launch_ds(const int8_t* in, int8_t* out, int Bw, const DsParams& P, const DsLaunch& L, int num_sms, cudaStream_t st);
 size_t ds_smem_bytes(const DsParams& P, int S, int TR);
+// stem + first DS block in one kernel (P.stem / P.stem_off filled, P.nst = 1, TR = 4): in = head output
+bool ds_stem_supported(const DsParams& P, int S, int add_mode);
+size_t ds_stem_smem_bytes(const DsParams& P, int* stem_off);
+int launch_ds_stem(const int8_t* head_out, int8_t* out, int Bw, const DsParams& P, size_t smem, int num_sms, cudaStream_t st);
 
 // warp-specialised pipeline form of the same block (bn_ds_ws.cu): P.nst = 3 | 4 input-tile buffers, two A operands, two accumulators
 int launch_dsw(const int8_t* in, int8_t* out, int Bw, const DsParams& P, const DsLaunch& L, int num_sms, cudaStream_t st);

@@ -745,7 +745,7 @@ extern "C" int bn_set_option(bn_engine* e, int key, int value) {
     case BN_OPT_TENSOR_CORE:
       e->fast.use_tc = value ? 1 : 0; break;
     case BN_OPT_FUSION:
-      e->fast.fusion = value & 255; break;
+      e->fast.fusion = value & 511; break;
     case BN_OPT_PROFILE:
       cudaDeviceSynchronize();
       e->prof.collect();

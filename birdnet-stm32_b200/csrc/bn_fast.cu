@@ -140,6 +140,9 @@ struct FastImpl {
   StemParams stem{};
   StemTcParams stem_tc{};         // tensor-core stem (bn_stem_tc.cu), BN_OPT_FUSION bit 7
   bool stem_tc_ok = false;
+  DsParams ds0s{};                // stem + first DS block in one kernel (k_ds<..., STEM>), BN_OPT_FUSION bit 8
+  size_t ds0s_smem = 0;
+  bool ds0s_ok = false;
   TailParams tail{};
   int ldk = 264;
   int bins = 257, W = 256, mel = 64;
@@ -921,6 +924,19 @@ static bool build_impl(FastPlan& fp) {
     }
   }
   for (Block& bl : im->blocks) if (!prep_block(fp, im, bl)) return false;
+  // stem + first block: the first DS block's parameters re-tiled to 4 output rows, stem constants attached
+  if (im->stem_tc_ok && !im->blocks.empty() && im->blocks[0].ds_ok && im->blocks[0].in_slot == im->stem_out_slot) {
+    const Block& b0 = im->blocks[0];
+    DsParams D = b0.ds;
+    D.NB = 1; D.MT = 4 * D.ow / 128; D.trow_log = ilog2_exact(4 * D.ow); D.nst = 1; D.TRr = 4; D.epi_smem = 0; D.tmem_cols = 256;
+    D.stem = im->stem_tc;
+    if (D.MT >= 1 && D.trow_log >= 0 && ds_stem_supported(D, b0.dsl.S, b0.dsl.add_mode) && im->stem_tc.oh == D.ih && D.MT * D.N + 16 * 9 <= 256) {
+      im->ds0s_smem = ds_stem_smem_bytes(D, &D.stem_off);
+      im->ds0s = D;
+      im->ds0s_ok = 2 * (im->ds0s_smem + 1024) <= 225 * 1024;
+      if (getenv("BN_DEBUG")) fprintf(stderr, "stem + ds_00 kernel: smem=%zu stem_off=%d ok=%d\n", im->ds0s_smem, D.stem_off, (int)im->ds0s_ok);
+    }
+  }
   // whole-stage kernels: a stride-2 block without ADD followed by stride-1 residual blocks of the same width whose maps are
   // one 128-pixel MMA tile (the 8 x 16 stage of the shipped graph), all in the folded-constant domain of the fused DS kernel
   for (size_t i = 0; i < im->blocks.size();) {
@@ -1763,9 +1779,10 @@ static int run_body(FastPlan& fp, int Bw, float* d_scores, int rounding, int mea
   FastImpl* im = fp.impl;
   const int R = rounding;
   int8_t* head_out = (int8_t*)im->slot_buf[im->head_out_slot];
-  // K3 stem
+  // K3 stem (skipped when the first block's kernel computes it itself: BN_OPT_FUSION bit 8)
   int8_t* stem_out = (int8_t*)im->slot_buf[im->stem_out_slot];
-  {
+  const bool sds = (fp.fusion & 256) && (fp.fusion & 1) && im->ds0s_ok && fp.use_tc && R == 0;
+  if (!sds) {
     const StemParams& S = im->stem;
     dim3 grid((S.oh + STEM_ROWS - 1) / STEM_ROWS, Bw);
     const size_t smem = (size_t)(STEM_ROWS + 2) * (S.iw + 8) + 96 * 4;
@@ -1806,6 +1823,16 @@ static int run_body(FastPlan& fp, int Bw, float* d_scores, int rounding, int mea
     const int8_t* bin = (const int8_t*)im->slot_buf[bl.in_slot];
     int8_t* dwo = (int8_t*)im->slot_buf[bl.dw_slot];
     int8_t* bout = (int8_t*)im->slot_buf[bl.out_slot];
+    if (sds && bidx == 0) {
+      snprintf(name, sizeof name, "K345_stem_ds_%02d_c%d_n%d_s%d", bi, bl.ds.C, bl.ds.N, bl.dsl.S);
+      if (prof) prof->begin(name, st);
+      int rc = launch_ds_stem(head_out, bout, Bw, im->ds0s, im->ds0s_smem, fp.num_sms, st);
+      if (prof) prof->end(st);
+      if (rc) return rc;
+      (*launches)++;
+      bi++;
+      continue;
+    }
     if ((fp.fusion & 1) && bl.ds_ok && fp.use_tc && R == 0) {
       const bool tcdw = (fp.fusion & 4) && bl.dst_ok;
       const bool ws = !tcdw && (fp.fusion & 64) && bl.dsw_ok;

@@ -55,7 +55,8 @@ struct FastPlan {
                                // too, bit 3: whole-stage kernels (bn_stage.cu), bit 4: stage kernels also write their inner block outputs (taps),
                                // bit 5: quantising frontend K1q / K2q (bn_frontend_q.cu) instead of K1 + float32 scratch + K2 (off by default:
                                // measured 0.9 % slower end to end, 27 % less DRAM traffic -- DESIGN.md section 5), bit 6: warp-specialised DS-block
-                               // kernel (bn_ds_ws.cu; measured equal, off), bit 7: stem as an im2col GEMM on tcgen05 (bn_stem_tc.cu)
+                               // kernel (bn_ds_ws.cu; measured equal, off), bit 7: stem as an im2col GEMM on tcgen05 (bn_stem_tc.cu),
+                               // bit 8: stem computed inside the first DS block's kernel (k_ds<..., STEM>; measured slower, off)
   FastImpl* impl = nullptr;
   std::string why;             // why the pattern did not match (diagnostics)
 };

@@ -72,7 +72,9 @@ enum {
                                bit 4 (16): the stage kernel also writes its inner block outputs (taps for bn_dump_tensor)
                                bit 5 (32): quantising frontend K1q + K2q (bn_frontend_q.cu; 27 % less DRAM traffic, 1 % slower, off)
                                bit 6 (64): warp-specialised DS-block kernel (bn_ds_ws.cu; measured equal to bit 0's kernel, off)
-                               bit 7 (128): stem convolution as an im2col GEMM on tcgen05 (bn_stem_tc.cu) */
+                               bit 7 (128): stem convolution as an im2col GEMM on tcgen05 (bn_stem_tc.cu)
+                               bit 8 (256): stem computed inside the first DS block's kernel (no stem tensor in global memory: 262 KB less DRAM
+                                            traffic per chunk; measured 36 % slower for the two layers, off) */
 };
 
 typedef struct bn_info {

@@ -100,6 +100,7 @@ def test_fused_plan_is_active_and_its_tensors_are_bit_exact(runner, graph, oracl
     for fusion, taps in ((11, [t for t in BLOCK_OUT_TAPS if t not in inner]), (27, BLOCK_OUT_TAPS), (3, BLOCK_OUT_TAPS), (7, BLOCK_OUT_TAPS),
                          (67, BLOCK_OUT_TAPS), (75, [t for t in BLOCK_OUT_TAPS if t not in inner]),
                          (139, [t for t in BLOCK_OUT_TAPS if t not in inner]),     # bit 7 (128): stem as an im2col GEMM on tcgen05 (bn_stem_tc.cu)
+                         (395, [t for t in BLOCK_OUT_TAPS if t not in inner and t != 97]),   # bit 8 (256): stem computed inside the first block's kernel (#97 stays on the SM)
                          (0, BLOCK_OUT_TAPS + DW_OUT_TAPS)):
         runner.set_option(L.BN_OPT_FUSION, fusion)
         try:
@@ -127,6 +128,8 @@ def test_fused_kernels_equal_layer_kernels_on_ragged_batches(blob, cfg, synth):
     try:
         fused = r.predict_pcm16(pcm, peak)
         r.set_option(L.BN_OPT_FUSION, 7)            # tensor-core depthwise variant, ragged last tile
+        np.testing.assert_array_equal(fused, r.predict_pcm16(pcm, peak))
+        r.set_option(L.BN_OPT_FUSION, 395)          # stem inside the first DS block's kernel, ragged last tile
         np.testing.assert_array_equal(fused, r.predict_pcm16(pcm, peak))
         r.set_option(L.BN_OPT_FUSION, 139)          # tensor-core stem (bn_stem_tc.cu)
         np.testing.assert_array_equal(fused, r.predict_pcm16(pcm, peak))
