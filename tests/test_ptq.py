@@ -208,6 +208,33 @@ def test_gpu_generic_plan_bit_exact_on_synthesised_graphs(name):
     runner.close()
 
 
+@pytest.mark.gpu
+def test_gpu_generic_plan_fusions_follow_the_rounding_and_mean_options():
+    """The single-launch SE gate (MEAN -> FC -> FC -> LOGISTIC) and the other fast kernels of the generic plan under the
+    non-default TFLite builds the engine can be told to match (single rounding; MEAN variants 1 and 3): scores equal to the
+    oracle with the same options, with the multi-op launches on (default) and off."""
+    from birdnet_stm32 import _lib as L
+    from birdnet_stm32.evaluation.gpu_runner import GpuRunner
+    from oracle import bn_oracle
+
+    name = "wide_se_attn_per_channel"
+    fg, _, g, blob = _case(name)
+    _, cfg, _ = CASES[name]
+    x = ptq.synth_calibration(fg, 5, seed=321)
+    runner = GpuRunner(blob, cfg)
+    try:
+        for rounding, variant in ((0, 0), (1, 0), (0, 1), (0, 3), (1, 2)):
+            want = bn_oracle.OracleModel(blob, rounding=rounding, mean_variant=variant).predict(x)
+            runner.set_option(L.BN_OPT_ROUNDING, rounding)
+            runner.set_option(L.BN_OPT_MEAN_VARIANT, variant)
+            for fusion in (139, 0):
+                runner.set_option(L.BN_OPT_FUSION, fusion)
+                got = runner.predict(x)
+                assert np.array_equal(got, want), (rounding, variant, fusion, np.abs(got - want).max())
+    finally:
+        runner.close()
+
+
 def test_ptq_weight_quantiser_reproduces_the_real_converter_output(graph):
     """Row f3 against the reference's own artefacts: the weight quantiser of `conversion/ptq.py`, fed with the
     BatchNorm-folded float weights of the shipped Keras checkpoint, must give the int8 weights and scales that the REAL
