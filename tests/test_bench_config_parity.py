@@ -200,6 +200,60 @@ def test_ten_thousand_chunks_pooled(runner24, oracle24):
     assert round(float(a), 3) == round(float(b), 3)
 
 
+def test_full_bench_size_wave_properties(runner24):
+    """At the size `bench.py` runs (one device wave of 21,710 chunks, 3.1 GB of PCM -- far more than the oracle can check in a
+    test) the result is pinned through size-independent properties: a chunk's scores do not depend on where in the wave it
+    sits (a permuted wave gives the permuted result; the first 4,096 rows equal those of a 4,096-chunk wave, which the
+    sweep above checks against the oracle), identical chunks get identical scores, the pooled file scores of the wave equal
+    the pooling of its chunk scores, and a second run is bit-identical (no dependence on scheduling)."""
+    import torch
+
+    from bench import synth_device_pcm
+    from oracle import bn_oracle
+
+    n = 21710
+    dev = torch.device("cuda", 0)
+    pcm = synth_device_pcm(torch, n, T24, SR24, seed=7, device=dev)
+    pcm[5000:5008] = pcm[100:108]                        # duplicates far apart in the wave
+    peak = (pcm.abs().amax(dim=1).float() / 32768.0).contiguous()
+    out = torch.empty((n, 100), dtype=torch.float32, device=dev)
+    runner24.infer_pcm16_ptr(pcm.data_ptr(), peak.data_ptr(), n, out.data_ptr())
+    torch.cuda.synchronize()
+    base = out.clone()
+    assert torch.equal(base[5000:5008], base[100:108])
+    assert float(base.min()) >= 0.0 and float(base.max()) <= 1.0 and bool(torch.isfinite(base).all())
+    # second run: bit-identical
+    runner24.infer_pcm16_ptr(pcm.data_ptr(), peak.data_ptr(), n, out.data_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(out, base)
+    # permuted wave
+    perm = torch.randperm(n, device=dev, generator=torch.Generator(device=dev).manual_seed(3))
+    pcm_p, peak_p = pcm[perm].contiguous(), peak[perm].contiguous()
+    runner24.infer_pcm16_ptr(pcm_p.data_ptr(), peak_p.data_ptr(), n, out.data_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(out, base[perm])
+    del pcm_p
+    # prefix of the big wave == a smaller wave
+    small = torch.empty((4096, 100), dtype=torch.float32, device=dev)
+    runner24.infer_pcm16_ptr(pcm.data_ptr(), peak.data_ptr(), 4096, small.data_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(small, base[:4096])
+    # pooled file scores of the wave == pooling of its chunk scores (files of 1..20 chunks)
+    rng = np.random.default_rng(11)
+    counts = []
+    while sum(counts) < n:
+        counts.append(int(min(rng.integers(1, 21), n - sum(counts))))
+    offs = np.zeros(len(counts) + 1, np.int32)
+    offs[1:] = np.cumsum(counts)
+    d_offs = torch.as_tensor(offs, device=dev)
+    pooled = torch.empty((len(counts), 100), dtype=torch.float32, device=dev)
+    runner24.infer_pool_ptr(pcm.data_ptr(), peak.data_ptr(), d_offs.data_ptr(), len(counts), "lme", 10.0, pooled.data_ptr())
+    torch.cuda.synchronize()
+    host = base.cpu().numpy()
+    want = np.stack([bn_oracle.pool_scores(host[a:b], "lme", 10.0) for a, b in zip(offs[:-1], offs[1:])])
+    assert np.abs(pooled.cpu().numpy() - want).max() <= 3e-6
+
+
 def test_quantising_frontend_equals_the_default_frontend_at_bench_config(runner24):
     """K1q + K2q (BN_OPT_FUSION bit 5: magnitudes parked in tensor memory, chunk-wide min / max exchanged between the tile workers
     through global atomics on a cooperative grid, int8 A operand fetched by TMA) vs K1 + float32 scratch + K2: identical scores
